@@ -1,0 +1,223 @@
+/*
+ * vkgs_b200.h — C ABI of the B200-native 3DGS forward rasterization path.
+ *
+ * Drop-in boundary for ONE path of nvpro-samples/vk_gaussian_splatting: the VK3DGSR splat
+ * render call, i.e. the body of GaussianSplatting::renderHybridPipeline for PIPELINE_MESH /
+ * PIPELINE_VERT (src/gaussian_splatting.cpp:494-958):
+ *     updateAndUploadFrameInfoUBO  -> vkgs_frame_params (filled by the host, or by
+ *                                     vkgs_frame_params_from_camera)
+ *     processSortingOnGPU          -> dist/cull kernel + device radix sort   (vkgs_render)
+ *     drawSplatPrimitives          -> project/SH + tile binning + tile blend (vkgs_render)
+ * The reference has no FFI; its seam is C++ (nvapp::IAppElement::onRender implemented by
+ * GaussianSplatting, src/gaussian_splatting.h:124-136,240-244). Every entry point below names
+ * the reference interface it replaces. See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions: plain pointers and sizes only; return 0 (VKGS_OK) or a negative error code, never
+ * an exception; one context per GPU; a context is single-caller (like the reference's render
+ * thread); the context owns all device memory; output buffers are caller-owned.
+ * The library REQUIRES a CUDA device for every compute entry point — there is no CPU fallback.
+ */
+#ifndef VKGS_B200_H_
+#define VKGS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VKGS_API __attribute__((visibility("default")))
+#else
+#define VKGS_API
+#endif
+
+#define VKGS_OK 0
+#define VKGS_ERR_INVALID_ARGUMENT (-1)
+#define VKGS_ERR_CUDA (-2)          /* a CUDA runtime call failed (see vkgs_last_error) */
+#define VKGS_ERR_NO_DEVICE (-3)     /* no usable sm_100 device: the path never falls back to CPU */
+#define VKGS_ERR_NOT_UPLOADED (-4)  /* vkgs_render before vkgs_upload */
+#define VKGS_ERR_OVERFLOW (-5)      /* tile-list capacity exceeded even after regrow */
+#define VKGS_ERR_UNSUPPORTED (-6)   /* option outside the hot-path scope */
+#define VKGS_ERR_IO (-7)            /* loader: file missing / malformed */
+
+/* value sets = the reference's shader macros (shaders/shaderio.h:23-103) */
+#define VKGS_FORMAT_FLOAT32 0
+#define VKGS_FORMAT_FLOAT16 1
+#define VKGS_FORMAT_UINT8 2
+#define VKGS_FRUSTUM_CULLING_NONE 0
+#define VKGS_FRUSTUM_CULLING_AT_DIST 1
+#define VKGS_FRUSTUM_CULLING_AT_RASTER 2
+#define VKGS_SIZE_CULLING_DISABLED 0
+#define VKGS_SIZE_CULLING_ENABLED 1
+
+typedef struct vkgs_ctx vkgs_ctx;
+
+/* Host view of a splat set: the SoA layout of struct SplatSet (src/splat_set.h:33-48).
+ * All pointers are HOST pointers, borrowed for the duration of the call only.
+ *   positions[3N] f_dc[3N] opacity[N] (logit) scale[3N] (log) rotation[4N] (w,x,y,z)
+ *   f_rest[f_rest_per_splat*N], channel-major per splat (R0..R14,G0..G14,B0..B14);
+ *   f_rest_per_splat is 45 (SH degree 3) or 0 (degree 0) — the only two layouts the
+ *   reference's shaders read correctly (fetchShFromBuffer uses a fixed stride of 45,
+ *   shaders/threedgs_particle_buffers.h.slang:110). */
+typedef struct vkgs_splat_set_view
+{
+  const float* positions;
+  const float* f_dc;
+  const float* f_rest;
+  const float* opacity;
+  const float* scale;
+  const float* rotation;
+  uint64_t     count;
+  uint32_t     f_rest_per_splat;
+  uint32_t     _pad;
+} vkgs_splat_set_view;
+
+/* The compile-time shader macro set of the path (src/gaussian_splatting.cpp:1653-1698). */
+typedef struct vkgs_options
+{
+  uint32_t frustum_culling_mode;     /* FRUSTUM_CULLING_MODE, default AT_DIST (1) */
+  uint32_t size_culling_mode;        /* SIZE_CULLING_MODE, default DISABLED */
+  uint32_t front_to_back;            /* FRONT_TO_BACK: 0 = back-to-front "over" (reference default,
+                                        alpha = sum of alphas), 1 = front-to-back "under" (alpha = 1-T) */
+  uint32_t ms_antialiasing;          /* MS_ANTIALIASING (mip-splatting opacity compensation) */
+  uint32_t sh_format;                /* SH_FORMAT   (VKGS_FORMAT_*) */
+  uint32_t rgba_format;              /* RGBA_FORMAT (VKGS_FORMAT_*) */
+  uint32_t point_cloud_mode;         /* POINT_CLOUD_MODE */
+  uint32_t show_sh_only;             /* SHOW_SH_ONLY */
+  uint32_t disable_opacity_gaussian; /* DISABLE_OPACITY_GAUSSIAN */
+  float    transmittance_epsilon;    /* front_to_back only: stop compositing a pixel once the
+                                        remaining transmittance 1-A drops below this (0 = never,
+                                        the reference's exact behaviour). Error bound: eps*max|rgb|. */
+  uint32_t _reserved[6];
+} vkgs_options;
+
+/* Per-frame parameters: the fields of shaderio::FrameInfo the path reads
+ * (shaders/shaderio.h:238-317), as filled by updateAndUploadFrameInfoUBO
+ * (src/gaussian_splatting.cpp:1150-1295), plus the single splat-set instance transform
+ * (SplatSetDesc.transform / transformInverse, shaders/shaderio.h:439-481).
+ * Matrices are glm column-major float[16], exactly the bytes the reference uploads. */
+typedef struct vkgs_frame_params
+{
+  float    view[16];           /* FrameInfo.viewMatrix  = glm::lookAt(eye,ctr,up) */
+  float    proj[16];           /* FrameInfo.projectionMatrix = perspectiveRH_ZO, [1][1] *= -1 */
+  float    model[16];          /* SplatSetDesc.transform */
+  float    model_inverse[16];  /* SplatSetDesc.transformInverse */
+  float    camera_position[3]; /* FrameInfo.cameraPosition (world) */
+  float    focal[2];           /* FrameInfo.focal = (P00*W/2, P11*H/2); focal[1] < 0 */
+  float    viewport[2];        /* FrameInfo.viewport = (W,H) */
+  float    basis_viewport[2];  /* FrameInfo.basisViewport = (1/W,1/H) */
+  float    inverse_focal_adjustment; /* 1 */
+  float    splat_scale;              /* FrameInfo.splatScale, default 1 */
+  float    frustum_dilation;         /* default 0.2 */
+  float    alpha_cull_threshold;     /* default 1/255 */
+  float    size_culling_min_pixels;  /* default 1 */
+  uint32_t sh_degree;                /* FrameInfo.shDegree, default 3 */
+  uint32_t width, height;
+} vkgs_frame_params;
+
+/* The fields of struct Camera (src/camera_set.h:44-63) the pinhole path uses. */
+typedef struct vkgs_camera
+{
+  float eye[3], ctr[3], up[3];
+  float fov_deg; /* vertical */
+  float znear, zfar;
+} vkgs_camera;
+
+/* Per-frame results. Mirrors what the reference exposes after a frame: COLOR_MAIN
+ * (src/gaussian_splatting.h:346), the sorted index buffer, IndirectParams.instanceCount
+ * (shaders/shaderio.h:343-356), and the profiler sections "GPU Dist" / "GPU Sort" /
+ * "Rasterization" (src/gaussian_splatting.cpp:1324,1346,567). */
+typedef struct vkgs_outputs
+{
+  float*    rgba;       /* HOST, W*H*4 fp32, row 0 = top; may be NULL (frame stays on the device) */
+  uint32_t* sorted_ids; /* HOST, optional, capacity sorted_ids_capacity */
+  uint32_t* sorted_keys;/* HOST, optional, same capacity */
+  uint64_t  sorted_ids_capacity;
+  uint32_t  visible_count;   /* V = IndirectParams.instanceCount */
+  uint32_t  _pad;
+  uint64_t  tile_pairs;      /* (splat,tile) pairs binned this frame (implementation overhead) */
+  float     ms_dist;         /* "GPU Dist"      : dist/cull + projection/SH kernel */
+  float     ms_sort;         /* "GPU Sort"      : radix sort of (key,id) */
+  float     ms_raster;       /* "Rasterization" : binning + tile sort + blend */
+  float     ms_total;        /* first kernel to framebuffer complete (device time) */
+  float     ms_kernel[16];   /* per-kernel device time, see VKGS_K_* */
+  uint64_t  bytes_algorithmic; /* 12N + (132+SH(d))V + 16P, SURVEY.md §8(d) */
+} vkgs_outputs;
+
+/* indices into vkgs_outputs.ms_kernel */
+#define VKGS_K_PREPROCESS 0   /* dist/cull + project + SH (one fused kernel) */
+#define VKGS_K_SORT_SCAN 1
+#define VKGS_K_SORT_PASS0 2   /* .. +3 = passes 0..3 */
+#define VKGS_K_BIN_EMIT 6
+#define VKGS_K_TILE_HIST 7
+#define VKGS_K_TILE_SORT0 8   /* .. +1 */
+#define VKGS_K_TILE_RANGES 10
+#define VKGS_K_BLEND 11
+#define VKGS_K_COUNT 12
+
+/* ---- lifetime (replaces GaussianSplatting::onAttach/onDetach, src/gaussian_splatting.h:124-127) */
+VKGS_API int vkgs_create(int device, vkgs_ctx** out);
+VKGS_API int vkgs_destroy(vkgs_ctx* ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own. */
+VKGS_API int vkgs_set_stream(vkgs_ctx* ctx, void* cuda_stream);
+VKGS_API const char* vkgs_last_error(const vkgs_ctx* ctx);
+VKGS_API const char* vkgs_version(void);
+/* sizeof() of the ABI structs as compiled, for binding validation:
+ * 0 vkgs_splat_set_view, 1 vkgs_options, 2 vkgs_frame_params, 3 vkgs_camera, 4 vkgs_outputs */
+VKGS_API uint32_t vkgs_abi_struct_size(int which);
+
+/* ---- scene upload (replaces SplatSetVk::initDataStorage/initDataBuffers,
+ *      src/splat_set_vk.cpp:117-170,188-480 and the sorting-buffer allocation,
+ *      src/splat_set_manager_vk.cpp:2426-2517). Packs on the host exactly like the reference
+ *      (cov6, clamped rgba, coefficient-major SH), copies to HBM; caller may free after return. */
+VKGS_API int vkgs_upload(vkgs_ctx* ctx, const vkgs_splat_set_view* set, const vkgs_options* opt);
+/* The host half of vkgs_upload alone (no GPU needed): writes the device layouts into caller
+ * buffers — centers[3N] f32, cov6[6N] f32, rgba[4N] and sh[45N] in opt->rgba_format / sh_format
+ * (sh may be NULL for degree-0 sets). This is SplatSetVk::initDataBuffers without the upload. */
+VKGS_API int vkgs_pack_host(const vkgs_splat_set_view* set, const vkgs_options* opt, float* centers, float* cov6, void* rgba,
+                            void* sh);
+VKGS_API void vkgs_default_options(vkgs_options* opt);
+
+/* ---- frame (replaces updateAndUploadFrameInfoUBO + processSortingOnGPU + drawSplatPrimitives,
+ *      src/gaussian_splatting.cpp:1150,1298,1369). */
+VKGS_API int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t width, uint32_t height, vkgs_frame_params* out);
+VKGS_API void vkgs_default_camera(vkgs_camera* cam);
+/* Synchronous: returns after the frame (and the requested copies to host) completed. */
+VKGS_API int vkgs_render(vkgs_ctx* ctx, const vkgs_frame_params* fp, vkgs_outputs* out);
+/* Stream-ordered: enqueue one frame, result stays in the device framebuffer. */
+VKGS_API int vkgs_render_async(vkgs_ctx* ctx, const vkgs_frame_params* fp);
+VKGS_API int vkgs_sync(vkgs_ctx* ctx);
+/* Enable per-kernel cudaEvent timing for subsequent frames (off by default). */
+VKGS_API int vkgs_set_profiling(vkgs_ctx* ctx, int enabled);
+/* Stats of the most recent frame (syncs). Fills everything in vkgs_outputs except the buffers. */
+VKGS_API int vkgs_last_frame_stats(vkgs_ctx* ctx, vkgs_outputs* out);
+/* Device pointer of the fp32 RGBA framebuffer of the last frame (W*H*4 floats). */
+VKGS_API const void* vkgs_device_framebuffer(const vkgs_ctx* ctx);
+/* Number of kernels launched by this context since creation. */
+VKGS_API uint64_t vkgs_launch_count(const vkgs_ctx* ctx);
+
+/* ---- stand-alone key/value radix sort (replaces vrdxCmdSortKeyValueIndirect,
+ *      3rdparty/vrdx/src/vk_radix_sort.cc:249-258): stable ascending LSD sort of n (u32 key,
+ *      u32 value) pairs. Host in, host out; ms_device = device time of the sort alone,
+ *      averaged over `repeats` runs (>=1) on the same input. */
+VKGS_API int vkgs_sort_pairs(vkgs_ctx* ctx, const uint32_t* keys, const uint32_t* values, uint64_t n,
+                    uint32_t* keys_out, uint32_t* values_out, int repeats, float* ms_device);
+
+/* ---- parity/debug read-backs of per-splat intermediates of the last frame ----------------
+ * Per-splat record, indexed by splat id (only ids that passed the dist-stage cull are valid):
+ *   12 x 32-bit words: centre px (x,y), fragPos basis w1 (x,y), w2 (x,y), rgba (r,g,b,a),
+ *   pixel bbox packed (x0 | y0<<16), (x1 | y1<<16); an empty bbox (x1<x0) = rejected splat. */
+VKGS_API int vkgs_read_records(vkgs_ctx* ctx, uint32_t* records12, uint64_t first, uint64_t count);
+/* Packed device arrays as uploaded (fp32 formats): centers[3N], cov6[6N], rgba[4N], sh[45N]. */
+VKGS_API int vkgs_read_packed(vkgs_ctx* ctx, float* centers, float* cov6, float* rgba, float* sh);
+
+/* ---- deterministic synthetic scene generator; host only, no GPU needed.
+ *      Arrays are caller-allocated with the vkgs_splat_set_view sizes; sh_degree is 0 or 3. */
+VKGS_API int vkgs_synth_scene(uint64_t n, uint32_t sh_degree, uint64_t seed, float* positions, float* f_dc, float* f_rest,
+                     float* opacity, float* scale, float* rotation);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKGS_B200_H_ */

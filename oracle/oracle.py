@@ -1,0 +1,171 @@
+"""ctypes/numpy wrapper of oracle/libvkgs_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this.
+The struct layouts come from the product's public header through vk_gaussian_splatting_b200._abi
+(plain-old-data only); every number is computed by oracle/vkgs_oracle.c and oracle/cpu_sorter.cpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from vk_gaussian_splatting_b200 import _abi as A
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libvkgs_oracle.so"
+
+f32p, u32p = A.f32p, A.u32p
+
+
+class Quad(C.Structure):
+    _fields_ = [("center", C.c_float * 2), ("basis1", C.c_float * 2), ("basis2", C.c_float * 2), ("w1", C.c_float * 2),
+                ("w2", C.c_float * 2), ("rgba", C.c_float * 4), ("ndc_z", C.c_float), ("valid", C.c_uint32)]
+
+
+QUAD_DTYPE = np.dtype([("center", "<f4", 2), ("basis1", "<f4", 2), ("basis2", "<f4", 2), ("w1", "<f4", 2), ("w2", "<f4", 2),
+                       ("rgba", "<f4", 4), ("ndc_z", "<f4"), ("valid", "<u4")])
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", str(HERE), "libvkgs_oracle.so"], check=True, stdout=subprocess.DEVNULL)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            build()
+        l = C.CDLL(str(LIB_PATH))
+        l.orc_look_at.argtypes = [f32p, f32p, f32p, f32p]
+        l.orc_perspective.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, f32p]
+        l.orc_frame_params_from_camera.argtypes = [C.POINTER(A.Camera), C.c_uint32, C.c_uint32, C.POINTER(A.FrameParams)]
+        l.orc_to_uint8.argtypes = [C.c_float, C.c_float, C.c_float]
+        l.orc_to_uint8.restype = C.c_uint8
+        l.orc_pack_half.argtypes = [C.c_float]
+        l.orc_pack_half.restype = C.c_uint16
+        l.orc_unpack_half.argtypes = [C.c_uint16]
+        l.orc_unpack_half.restype = C.c_float
+        l.orc_pack_cov6.argtypes = [f32p, f32p, f32p]
+        l.orc_pack_rgba.argtypes = [f32p, C.c_float, f32p]
+        l.orc_pack.argtypes = [C.POINTER(A.SplatSetView), C.c_uint32, C.c_uint32, f32p, f32p, f32p, f32p]
+        l.orc_encode_min_max_fp32.argtypes = [C.c_float]
+        l.orc_encode_min_max_fp32.restype = C.c_uint32
+        l.orc_dist_cull.argtypes = [f32p, f32p, C.c_uint64, C.POINTER(A.FrameParams), C.POINTER(A.Options), u32p, u32p]
+        l.orc_dist_cull.restype = C.c_uint32
+        l.orc_radix_sort_pairs.argtypes = [u32p, u32p, C.c_uint64]
+        l.orc_project_splat.argtypes = [C.c_uint32, f32p, f32p, f32p, f32p, C.c_uint32, C.POINTER(A.FrameParams),
+                                        C.POINTER(A.Options), C.POINTER(Quad)]
+        l.orc_expf.argtypes = [C.c_float]
+        l.orc_expf.restype = C.c_float
+        l.orc_raster_quad.argtypes = [C.POINTER(Quad), C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p]
+        l.orc_render.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams),
+                                 C.POINTER(A.Options), f32p, u32p, u32p, C.c_void_p]
+        l.orc_render.restype = C.c_uint32
+        l.orc_quad_size.restype = C.c_uint32
+        l.orc_cpu_sort.argtypes = [f32p, C.c_uint64, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, u32p, f32p,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        l.orc_cpu_sort.restype = C.c_int
+        l.orc_hardware_concurrency.restype = C.c_int
+        assert l.orc_quad_size() == C.sizeof(Quad) == QUAD_DTYPE.itemsize
+        _lib = l
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(f32p) if a is not None else None
+
+
+def _u(a):
+    return a.ctypes.data_as(u32p) if a is not None else None
+
+
+def frame_params(cam: A.Camera, w: int, h: int) -> A.FrameParams:
+    fp = A.FrameParams()
+    lib().orc_frame_params_from_camera(C.byref(cam), w, h, C.byref(fp))
+    return fp
+
+
+def default_options(**kw) -> A.Options:
+    """Reference defaults restated independently of the product (src/parameters.h, shaderio.h)."""
+    o = A.Options()
+    o.frustum_culling_mode = A.FRUSTUM_CULLING_AT_DIST
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Packed:
+    """Device-layout arrays of a splat set as the reference's initDataBuffers would build them,
+    decoded to fp32 the way the shaders fetch them."""
+
+    def __init__(self, splats, sh_format=A.FORMAT_FLOAT32, rgba_format=A.FORMAT_FLOAT32):
+        n = splats.size()
+        self.n = n
+        self.sh_degree = 3 if splats.f_rest.shape[1] == 45 else 0
+        self.centers = np.empty((n, 3), np.float32)
+        self.cov6 = np.empty((n, 6), np.float32)
+        self.rgba = np.empty((n, 4), np.float32)
+        self.sh = np.empty((n, 45), np.float32) if self.sh_degree else None
+        self.scale = np.ascontiguousarray(splats.scale, np.float32)
+        v = splats.view()
+        lib().orc_pack(C.byref(v), sh_format, rgba_format, _p(self.centers), _p(self.cov6), _p(self.rgba), _p(self.sh))
+
+
+def dist_cull(packed: Packed, fp, opt):
+    keys = np.empty(packed.n, np.uint32)
+    ids = np.empty(packed.n, np.uint32)
+    v = lib().orc_dist_cull(_p(packed.centers), _p(packed.scale), packed.n, C.byref(fp), C.byref(opt), _u(keys), _u(ids))
+    return keys[:v].copy(), ids[:v].copy()
+
+
+def radix_sort_pairs(keys, vals):
+    k = np.ascontiguousarray(keys, np.uint32).copy()
+    v = np.ascontiguousarray(vals, np.uint32).copy()
+    lib().orc_radix_sort_pairs(_u(k), _u(v), k.size)
+    return k, v
+
+
+def render(packed: Packed, fp, opt, want_quads=False):
+    """Full oracle frame. Returns (image [H,W,4], sorted_keys, sorted_ids, quads or None)."""
+    img = np.zeros((fp.height, fp.width, 4), np.float32)
+    keys = np.empty(packed.n, np.uint32)
+    ids = np.empty(packed.n, np.uint32)
+    quads = np.zeros(packed.n, QUAD_DTYPE) if want_quads else None
+    v = lib().orc_render(_p(packed.centers), _p(packed.cov6), _p(packed.rgba), _p(packed.sh), _p(packed.scale), packed.n,
+                         packed.sh_degree, C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids),
+                         quads.ctypes.data_as(C.c_void_p) if want_quads else None)
+    return img, keys[:v].copy(), ids[:v].copy(), quads
+
+
+def project_splat(packed: Packed, idx: int, fp, opt) -> Quad:
+    q = Quad()
+    lib().orc_project_splat(idx, _p(packed.centers), _p(packed.cov6), _p(packed.rgba), _p(packed.sh), packed.sh_degree,
+                            C.byref(fp), C.byref(opt), C.byref(q))
+    return q
+
+
+def cpu_sort(positions, model, direction, cop, front_to_back=False, mode=1, threads=None):
+    """Reference CPU sorter restatement. Returns (indices, distances, ms_dist, ms_sort)."""
+    l = lib()
+    pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    n = pos.shape[0]
+    threads = threads or l.orc_hardware_concurrency()
+    idx = np.empty(n, np.uint32)
+    dist = np.empty(n, np.float32)
+    m = np.ascontiguousarray(model, np.float32).reshape(16)
+    d = np.ascontiguousarray(direction, np.float32)
+    c = np.ascontiguousarray(cop, np.float32)
+    t0, t1 = C.c_double(0), C.c_double(0)
+    rc = l.orc_cpu_sort(_p(pos), n, _p(m), _p(d), _p(c), int(front_to_back), mode, threads, _u(idx), _p(dist), C.byref(t0),
+                        C.byref(t1))
+    assert rc == 0
+    return idx, dist, t0.value, t1.value
+
+
+def hardware_concurrency() -> int:
+    return lib().orc_hardware_concurrency()

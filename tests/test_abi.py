@@ -1,0 +1,90 @@
+"""The C-ABI shared library loads on a machine without a GPU, exports every symbol declared in
+include/vkgs_b200.h, agrees with the ctypes mirror on struct sizes, and refuses to compute without
+a device (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import vk_gaussian_splatting_b200 as g
+from vk_gaussian_splatting_b200 import _abi as A
+
+HEADER = Path(__file__).resolve().parent.parent / "include" / "vkgs_b200.h"
+
+
+def declared_symbols():
+    txt = HEADER.read_text()
+    return sorted(set(re.findall(r"VKGS_API[^;()]*?\b(vkgs_\w+)\s*\(", txt)))
+
+
+def test_header_declares_and_library_exports_every_symbol():
+    names = declared_symbols()
+    assert len(names) >= 20
+    l = A.lib()
+    for n in names:
+        assert hasattr(l, n), f"library does not export {n}"
+    assert sorted(A.SYMBOLS) == names, "ctypes mirror and header disagree"
+
+
+def test_struct_sizes_match_compiled_abi():
+    l = A.lib()
+    for which, st in enumerate([A.SplatSetView, A.Options, A.FrameParams, A.Camera, A.Outputs]):
+        assert l.vkgs_abi_struct_size(which) == C.sizeof(st), st.__name__
+    assert l.vkgs_abi_struct_size(99) == 0
+
+
+def test_version_and_defaults():
+    l = A.lib()
+    assert b"sm_100a" in l.vkgs_version()
+    opt = g.default_options()
+    assert (opt.frustum_culling_mode, opt.front_to_back, opt.sh_format, opt.rgba_format) == (1, 0, 0, 0)
+    cam = g.default_camera()
+    assert [round(x, 4) for x in cam.eye] == [1.7, 1.5, 1.7] and cam.fov_deg == 60.0 and cam.znear == pytest.approx(0.1)
+    fp = g.frame_params(cam, 1920, 1080)
+    assert fp.frustum_dilation == pytest.approx(0.2) and fp.alpha_cull_threshold == pytest.approx(1 / 255)
+    assert fp.sh_degree == 3 and fp.splat_scale == 1.0
+
+
+def test_error_codes_on_bad_arguments():
+    l = A.lib()
+    assert l.vkgs_frame_params_from_camera(None, 10, 10, None) == A.VKGS_ERR_INVALID_ARGUMENT
+    cam, fp = g.default_camera(), A.FrameParams()
+    assert l.vkgs_frame_params_from_camera(C.byref(cam), 0, 10, C.byref(fp)) == A.VKGS_ERR_INVALID_ARGUMENT
+    assert l.vkgs_create(0, None) == A.VKGS_ERR_INVALID_ARGUMENT
+    assert l.vkgs_destroy(None) == A.VKGS_ERR_INVALID_ARGUMENT
+    assert l.vkgs_render(None, None, None) == A.VKGS_ERR_INVALID_ARGUMENT
+    s = g.synth_scene(16, 0, 1)
+    bad = g.SplatSet(s.positions, s.f_dc, np.zeros((16, 9), np.float32), s.opacity, s.scale, s.rotation)
+    with pytest.raises(g.VkgsError) as e:
+        g.pack_host(bad)
+    assert e.value.code == A.VKGS_ERR_UNSUPPORTED  # only 0 or 45 f_rest components per splat
+    assert l.vkgs_synth_scene(0, 0, 0, None, None, None, None, None, None) == A.VKGS_ERR_INVALID_ARGUMENT
+
+
+def test_synth_scene_is_deterministic_and_in_range():
+    a, b = g.synth_scene(5000, 3, 123), g.synth_scene(5000, 3, 123)
+    for f in ("positions", "f_dc", "f_rest", "opacity", "scale", "rotation"):
+        assert np.array_equal(getattr(a, f), getattr(b, f))
+    c = g.synth_scene(5000, 3, 124)
+    assert not np.array_equal(a.positions, c.positions)
+    assert np.abs(a.positions).max() <= 1.0
+    s0 = 0.002 * (1e6 / 5000) ** (1 / 3)
+    assert a.scale.min() >= np.log(s0) - 1e-5 and a.scale.max() <= np.log(10 * s0) + 1e-5
+    assert -2 <= a.opacity.min() and a.opacity.max() <= 4
+    assert abs(a.f_rest.std() - 0.1) < 0.005 and abs(a.rotation.std() - 1.0) < 0.03
+    assert a.max_sh_degree() == 3 and g.synth_scene(10, 0, 1).max_sh_degree() == 0
+    # prefix property: element i does not depend on n except through the scale law
+    d = g.synth_scene(100, 3, 123)
+    assert np.array_equal(d.positions, a.positions[:100]) and np.array_equal(d.f_rest, a.f_rest[:100])
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert A.lib().vkgs_create(0, C.byref(h)) == A.VKGS_ERR_NO_DEVICE
+    with pytest.raises(g.VkgsError):
+        g.GaussianSplatting(0)

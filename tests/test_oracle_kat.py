@@ -1,0 +1,215 @@
+"""Known-answer tests of the CPU oracle itself: analytic cases that pin the
+restated shader arithmetic independently of any GPU."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import vk_gaussian_splatting_b200 as g
+from vk_gaussian_splatting_b200 import _abi as A
+from oracle import oracle as O
+from util import f32_bits, ulp_diff
+
+
+def enc(x):
+    return O.lib().orc_encode_min_max_fp32(float(np.float32(x)))
+
+
+def test_encode_min_max_fp32_bit_patterns():
+    assert enc(0.0) == 0x80000000
+    assert enc(-0.0) == 0x7FFFFFFF
+    assert enc(1.0) == 0xBF800000
+    assert enc(-1.0) == 0x407FFFFF
+    assert enc(np.inf) == 0xFF800000
+    assert enc(-np.inf) == 0x007FFFFF
+
+
+def test_encode_min_max_fp32_is_monotonic():
+    rng = np.random.default_rng(1)
+    v = np.concatenate([rng.normal(size=4000), rng.normal(size=1000) * 1e-30, rng.normal(size=1000) * 1e30,
+                        [0.0, -0.0, 1.0, -1.0]]).astype(np.float32)
+    v = np.unique(v)  # sorted ascending, unique values (-0.0 == 0.0 collapses)
+    e = np.array([enc(x) for x in v], np.uint64)
+    assert np.all(np.diff(e.astype(np.int64)) > 0)
+
+
+def test_radix_sort_is_stable_ascending():
+    rng = np.random.default_rng(2)
+    keys = rng.integers(0, 1 << 32, size=50000, dtype=np.uint64).astype(np.uint32)
+    keys[::3] = keys[0]  # many ties
+    vals = np.arange(keys.size, dtype=np.uint32)
+    k, v = O.radix_sort_pairs(keys, vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order])
+    assert np.array_equal(v, vals[order])
+
+
+def test_expf_within_1ulp_of_libm_on_fragment_domain():
+    x = np.linspace(-4.0, 0.0, 20001, dtype=np.float32)
+    got = np.array([O.lib().orc_expf(float(v)) for v in x], np.float32)
+    want = np.exp(x.astype(np.float64)).astype(np.float32)
+    assert ulp_diff(got, want).max() <= 1
+    assert O.lib().orc_expf(0.0) == 1.0
+
+
+def _one_splat(pos, log_scale, quat=(1, 0, 0, 0), opacity=10.0, dc=(0.0, 0.0, 0.0), rest=None):
+    rest = np.zeros((1, 0), np.float32) if rest is None else np.asarray(rest, np.float32).reshape(1, 45)
+    return g.SplatSet(np.array([pos], np.float32), np.array([dc], np.float32), rest, np.array([opacity], np.float32),
+                      np.array([[log_scale] * 3], np.float32), np.array([quat], np.float32))
+
+
+def _front_camera(dist=4.0):
+    return g.make_camera((0, 0, dist), (0, 0, 0), (0, 1, 0), 60.0, 0.1, 100.0)
+
+
+def test_single_isotropic_splat_has_analytic_alpha_profile():
+    W = H = 256
+    sigma, dist = 0.05, 4.0
+    s = _one_splat((0, 0, 0), math.log(sigma), opacity=20.0, dc=(1.0, -1.0, 0.25))
+    fp = O.frame_params(_front_camera(dist), W, H)
+    pk = O.Packed(s)
+    q = O.project_splat(pk, 0, fp, O.default_options())
+    assert q.valid == 1
+    assert abs(q.center[0] - W / 2) < 1e-3 and abs(q.center[1] - H / 2) < 1e-3
+    focal = H / (2 * math.tan(math.radians(30)))
+    var_px = (sigma * focal / dist) ** 2 + 0.3  # EWA projection + 0.3 dilation (threedgs.h.slang:69-70)
+    # isotropic: both eigenvalues equal up to sqrt(max(0.1, .)) quirk: lambda = var +- sqrt(0.1)
+    l1, l2 = var_px + math.sqrt(0.1), var_px - math.sqrt(0.1)
+    r1 = math.hypot(q.basis1[0], q.basis1[1])
+    r2 = math.hypot(q.basis2[0], q.basis2[1])
+    assert r1 == pytest.approx(math.sqrt(8 * l1), rel=1e-4)
+    assert r2 == pytest.approx(math.sqrt(8 * l2), rel=1e-4)
+    assert abs(q.basis1[0] * q.basis2[0] + q.basis1[1] * q.basis2[1]) < 1e-3  # orthogonal
+    img, _, ids, _ = O.render(pk, fp, O.default_options())
+    assert ids.tolist() == [0]
+    a = float(pk.rgba[0, 3])
+    rgb = pk.rgba[0, :3]
+    assert rgb[0] == pytest.approx(0.5 + 0.28209479177387814, rel=1e-6) and rgb[1] == pytest.approx(0.5 - 0.28209479177387814, rel=1e-6)
+    # along the first eigenvector the profile is exp(-d^2 / (2 lambda1))
+    e1 = np.array([q.basis1[0], q.basis1[1]]) / r1
+    e2 = np.array([q.basis2[0], q.basis2[1]]) / r2
+    checked = 0
+    for j in range(H):
+        for i in range(W):
+            d = np.array([i + 0.5 - q.center[0], j + 0.5 - q.center[1]])
+            u, v = d @ e1, d @ e2
+            A_ = u * u / l1 + v * v / l2
+            alpha = math.exp(-0.5 * A_) * a
+            if A_ < 7.99 and alpha > 1 / 255 * 1.001:
+                assert img[j, i, 3] == pytest.approx(alpha, rel=2e-4)
+                assert img[j, i, 0] == pytest.approx(alpha * rgb[0], rel=2e-4)  # over black, BTF
+                checked += 1
+            elif A_ > 8.01 or alpha < 1 / 255 * 0.999:
+                assert img[j, i, 3] == 0.0
+    assert checked > 150
+
+
+def test_two_overlapping_splats_btf_equals_ftb_rgb():
+    W = H = 128
+    s1 = _one_splat((0.0, 0.0, 0.0), math.log(0.1), opacity=0.3, dc=(1.5, 0.0, -1.0))
+    s2 = _one_splat((0.05, 0.02, 1.0), math.log(0.08), opacity=-0.2, dc=(-1.0, 1.2, 0.4))
+    s = g.SplatSet(np.vstack([s1.positions, s2.positions]), np.vstack([s1.f_dc, s2.f_dc]), np.zeros((2, 0)),
+                   np.concatenate([s1.opacity, s2.opacity]), np.vstack([s1.scale, s2.scale]), np.vstack([s1.rotation, s2.rotation]))
+    fp = O.frame_params(_front_camera(4.0), W, H)
+    pk = O.Packed(s)
+    btf, _, ids_b, _ = O.render(pk, fp, O.default_options(front_to_back=0))
+    ftb, _, ids_f, _ = O.render(pk, fp, O.default_options(front_to_back=1))
+    assert ids_b.tolist() == [0, 1]  # farthest (z=0) first; camera at z=4 looks down -z
+    assert ids_f.tolist() == [1, 0]
+    assert np.abs(btf[..., :3] - ftb[..., :3]).max() < 1e-6
+    both = (btf[..., 3] > 0) & (ftb[..., 3] > 0)
+    assert both.sum() > 100
+    # alpha differs by definition: BTF = a1 + a2, FTB = 1 - (1-a1)(1-a2)
+    assert np.all(btf[..., 3] >= ftb[..., 3] - 1e-6)
+
+
+def test_sh_degree1_axis_directions():
+    """rgb += C1 * (-s0*y + s1*z - s2*x) with dir = normalize(center - cam) (storage.h.slang:122)."""
+    C1 = 0.4886025119029199
+    rest = np.zeros(45, np.float32)
+    # channel-major source layout: R coefficients 0..14, G 15..29, B 30..44
+    rest[0], rest[15 + 1], rest[30 + 2] = 0.5, 0.25, -0.75  # R: s0, G: s1, B: s2
+    s = _one_splat((0, 0, 0), math.log(0.05), opacity=5.0, rest=rest)
+    pk = O.Packed(s)
+    assert pk.sh[0, 0] == 0.5 and pk.sh[0, 3 * 1 + 1] == 0.25 and pk.sh[0, 3 * 2 + 2] == -0.75  # coefficient-major, RGB inner
+    for eye, d in (((0, 0, 4), (0, 0, -1)), ((4, 0, 0), (-1, 0, 0)), ((0, 4, 0.0001), (0, -1, 0))):
+        fp = O.frame_params(g.make_camera(eye, (0, 0, 0), (0, 1, 0) if eye[1] == 0 else (0, 0, -1), 60, 0.1, 100), 64, 64)
+        fp.sh_degree = 1
+        q = O.project_splat(pk, 0, fp, O.default_options())
+        x, y, z = d
+        assert q.rgba[0] == pytest.approx(0.5 + C1 * (-0.5 * y), abs=1e-4)
+        assert q.rgba[1] == pytest.approx(0.5 + C1 * (0.25 * z), abs=1e-4)
+        assert q.rgba[2] == pytest.approx(0.5 + C1 * (0.75 * x), abs=1e-4)
+
+
+def test_sh_degree3_matches_float64_evaluation():
+    rng = np.random.default_rng(5)
+    n = 200
+    s = g.synth_scene(n, 3, 77)
+    pk = O.Packed(s)
+    fp = O.frame_params(g.default_camera(), 640, 360)
+    C1 = 0.4886025119029199
+    C2 = [1.0925484, -1.0925484, 0.3153916, -1.0925484, 0.5462742]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+    cam = np.array(fp.camera_position, np.float64)
+    for i in range(n):
+        q = O.project_splat(pk, i, fp, O.default_options())
+        if pk.rgba[i, 3] < 1 / 255:
+            continue
+        d = pk.centers[i].astype(np.float64) - cam
+        x, y, z = d / np.linalg.norm(d)
+        sh = pk.sh[i].astype(np.float64).reshape(15, 3)
+        rgb = pk.rgba[i, :3].astype(np.float64) + C1 * (-sh[0] * y + sh[1] * z - sh[2] * x)
+        rgb += C2[0] * x * y * sh[3] + C2[1] * y * z * sh[4] + C2[2] * (2 * z * z - x * x - y * y) * sh[5] + C2[3] * x * z * sh[6] + C2[4] * (x * x - y * y) * sh[7]
+        rgb += (C3[0] * sh[8] * (3 * x * x - y * y) * y + C3[1] * sh[9] * x * y * z + C3[2] * sh[10] * (4 * z * z - x * x - y * y) * y
+                + C3[3] * sh[11] * z * (2 * z * z - 3 * x * x - 3 * y * y) + C3[4] * sh[12] * x * (4 * z * z - x * x - y * y)
+                + C3[5] * sh[13] * (x * x - y * y) * z + C3[6] * sh[14] * x * (x * x - 3 * y * y))
+        assert np.allclose(np.array(q.rgba[:3]), rgb, atol=5e-6)
+
+
+def test_dist_cull_frustum_and_depth_order():
+    pts = np.array([[0, 0, 0], [0, 0, 1], [0, 0, 3.95], [0, 0, 5], [100, 0, 0], [0, 0, -2100]], np.float32)
+    n = len(pts)
+    s = g.SplatSet(pts, np.zeros((n, 3)), np.zeros((n, 0)), np.ones(n), np.full((n, 3), -3.0), np.tile([1, 0, 0, 0], (n, 1)))
+    pk = O.Packed(s)
+    fp = O.frame_params(_front_camera(4.0), 128, 128)
+    keys, ids = O.dist_cull(pk, fp, O.default_options())
+    # kept: 0,1 (in front), 2 (closer than near: ndc.z<0 but > -0.2? no: z=0.05 from camera -> ndc.z<-0.2 culled)
+    assert 3 not in ids and 4 not in ids and 5 not in ids  # behind camera, off to the side, beyond far
+    assert ids.tolist()[:2] == [0, 1]
+    k0, k1 = keys[0], keys[1]
+    assert k0 < k1  # BTF key = enc(-depth): farther splat (id 0) sorts first
+    keys_f, _ = O.dist_cull(pk, fp, O.default_options(front_to_back=1))
+    assert keys_f[0] > keys_f[1]
+    keys_n, ids_n = O.dist_cull(pk, fp, O.default_options(frustum_culling_mode=A.FRUSTUM_CULLING_NONE))
+    assert ids_n.tolist() == list(range(n))  # no culling at the dist stage
+
+
+def test_depth_clip_and_alpha_cull_reject_quads():
+    fp = O.frame_params(_front_camera(4.0), 128, 128)
+    # alpha cull: sigmoid(-8) < 1/255
+    s = _one_splat((0, 0, 0), math.log(0.05), opacity=-8.0)
+    assert O.project_splat(O.Packed(s), 0, fp, O.default_options()).valid == 0
+    # closer than the near plane but inside the dilated frustum -> kept by dist cull when dilation allows, clipped by depth
+    s = _one_splat((0, 0, 3.92), math.log(0.01), opacity=5.0)
+    pk = O.Packed(s)
+    q = O.project_splat(pk, 0, fp, O.default_options())
+    assert q.ndc_z < 0 and q.valid == 0
+
+
+def test_cpu_sorter_orders_by_plane_distance():
+    s = g.synth_scene(20000, 0, 9)
+    cam = g.default_camera()
+    eye = np.array(cam.eye, np.float32)
+    d = np.array(cam.ctr, np.float32) - eye
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    for ftb in (False, True):
+        for mode in (0, 1):
+            idx, dist, _, _ = O.cpu_sort(s.positions, ident, d, eye, front_to_back=ftb, mode=mode, threads=4)
+            assert sorted(idx.tolist()) == list(range(20000))
+            ds = dist[idx]
+            assert np.all(np.diff(ds) >= 0) if ftb else np.all(np.diff(ds) <= 0)
+    want = np.abs((s.positions.astype(np.float64) - eye) @ (d / np.linalg.norm(d)))
+    assert np.allclose(dist, want, atol=1e-5)

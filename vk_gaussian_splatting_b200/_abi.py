@@ -1,0 +1,111 @@
+"""ctypes mirror of include/vkgs_b200.h and loader of the in-tree CUDA library.
+
+The library is REQUIRED: importing succeeds without it (so CPU-only tooling can import the
+package), but every call goes through `lib()` which raises if libvkgs_b200.so is missing —
+there is no Python/CPU fallback for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libvkgs_b200.so"
+
+VKGS_OK = 0
+VKGS_ERR_INVALID_ARGUMENT = -1
+VKGS_ERR_CUDA = -2
+VKGS_ERR_NO_DEVICE = -3
+VKGS_ERR_NOT_UPLOADED = -4
+VKGS_ERR_OVERFLOW = -5
+VKGS_ERR_UNSUPPORTED = -6
+VKGS_ERR_IO = -7
+
+FORMAT_FLOAT32, FORMAT_FLOAT16, FORMAT_UINT8 = 0, 1, 2
+FRUSTUM_CULLING_NONE, FRUSTUM_CULLING_AT_DIST, FRUSTUM_CULLING_AT_RASTER = 0, 1, 2
+SIZE_CULLING_DISABLED, SIZE_CULLING_ENABLED = 0, 1
+
+K_NAMES = ["preprocess", "sort_scan", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "bin_emit",
+           "tile_hist", "tile_sort0", "tile_sort1", "tile_ranges", "blend"]
+K_COUNT = 12
+
+f32p = C.POINTER(C.c_float)
+u32p = C.POINTER(C.c_uint32)
+
+
+class SplatSetView(C.Structure):
+    _fields_ = [("positions", f32p), ("f_dc", f32p), ("f_rest", f32p), ("opacity", f32p), ("scale", f32p),
+                ("rotation", f32p), ("count", C.c_uint64), ("f_rest_per_splat", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class Options(C.Structure):
+    _fields_ = [("frustum_culling_mode", C.c_uint32), ("size_culling_mode", C.c_uint32), ("front_to_back", C.c_uint32),
+                ("ms_antialiasing", C.c_uint32), ("sh_format", C.c_uint32), ("rgba_format", C.c_uint32),
+                ("point_cloud_mode", C.c_uint32), ("show_sh_only", C.c_uint32), ("disable_opacity_gaussian", C.c_uint32),
+                ("transmittance_epsilon", C.c_float), ("_reserved", C.c_uint32 * 6)]
+
+
+class FrameParams(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("model", C.c_float * 16),
+                ("model_inverse", C.c_float * 16), ("camera_position", C.c_float * 3), ("focal", C.c_float * 2),
+                ("viewport", C.c_float * 2), ("basis_viewport", C.c_float * 2), ("inverse_focal_adjustment", C.c_float),
+                ("splat_scale", C.c_float), ("frustum_dilation", C.c_float), ("alpha_cull_threshold", C.c_float),
+                ("size_culling_min_pixels", C.c_float), ("sh_degree", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("ctr", C.c_float * 3), ("up", C.c_float * 3), ("fov_deg", C.c_float),
+                ("znear", C.c_float), ("zfar", C.c_float)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("rgba", f32p), ("sorted_ids", u32p), ("sorted_keys", u32p), ("sorted_ids_capacity", C.c_uint64),
+                ("visible_count", C.c_uint32), ("_pad", C.c_uint32), ("tile_pairs", C.c_uint64), ("ms_dist", C.c_float),
+                ("ms_sort", C.c_float), ("ms_raster", C.c_float), ("ms_total", C.c_float), ("ms_kernel", C.c_float * 16),
+                ("bytes_algorithmic", C.c_uint64)]
+
+
+# every symbol include/vkgs_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "vkgs_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "vkgs_destroy": (C.c_int, [C.c_void_p]),
+    "vkgs_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vkgs_last_error": (C.c_char_p, [C.c_void_p]),
+    "vkgs_version": (C.c_char_p, []),
+    "vkgs_abi_struct_size": (C.c_uint32, [C.c_int]),
+    "vkgs_pack_host": (C.c_int, [C.POINTER(SplatSetView), C.POINTER(Options), f32p, f32p, C.c_void_p, C.c_void_p]),
+    "vkgs_upload": (C.c_int, [C.c_void_p, C.POINTER(SplatSetView), C.POINTER(Options)]),
+    "vkgs_default_options": (None, [C.POINTER(Options)]),
+    "vkgs_frame_params_from_camera": (C.c_int, [C.POINTER(Camera), C.c_uint32, C.c_uint32, C.POINTER(FrameParams)]),
+    "vkgs_default_camera": (None, [C.POINTER(Camera)]),
+    "vkgs_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.POINTER(Outputs)]),
+    "vkgs_render_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams)]),
+    "vkgs_sync": (C.c_int, [C.c_void_p]),
+    "vkgs_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "vkgs_last_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(Outputs)]),
+    "vkgs_device_framebuffer": (C.c_void_p, [C.c_void_p]),
+    "vkgs_launch_count": (C.c_uint64, [C.c_void_p]),
+    "vkgs_sort_pairs": (C.c_int, [C.c_void_p, u32p, u32p, C.c_uint64, u32p, u32p, C.c_int, f32p]),
+    "vkgs_read_records": (C.c_int, [C.c_void_p, u32p, C.c_uint64, C.c_uint64]),
+    "vkgs_read_packed": (C.c_int, [C.c_void_p, f32p, f32p, f32p, f32p]),
+    "vkgs_synth_scene": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, f32p, f32p, f32p, f32p, f32p, f32p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libvkgs_b200.so (built in-tree by vk_gaussian_splatting_b200.build). Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m vk_gaussian_splatting_b200.build` "
+                               "(the CUDA extension is required; there is no CPU fallback)")
+        l = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib

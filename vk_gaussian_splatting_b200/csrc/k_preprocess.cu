@@ -1,0 +1,430 @@
+// k_preprocess.cu — fused per-splat front end (one pass over the splat arrays, in storage order).
+//
+// Replaces, for every splat i (reference file:line):
+//   dist.comp.slang:40-171       view/clip transform, NDC depth -> sortable key, frustum / size cull,
+//                                append (key, id)                       [K1]
+//   threedgs_raster.mesh.slang:161-289   alpha cull, SH colour, covariance projection, extent basis [K5]
+//   threedgs.h.slang:26-121, threedgs_particle_storage.h.slang:103-159
+// B200 design: the reference runs K5 after the sort and gathers 232 B/splat by sorted id. Here the
+// whole per-splat stage runs BEFORE the sort, in storage order, so every attribute array is
+// streamed exactly once with bulk async copies (TMA engine, cp.async.bulk -> shared memory, one
+// mbarrier per tile); the sort then only moves 8-byte (key,id) pairs and the raster stages gather
+// a compact 48-byte record per splat. The append is deterministic: a decoupled look-back prefix
+// over tiles replaces the reference's global atomic, so (key,id) pairs come out in ascending splat
+// id — one of the orders the reference's atomic can legally produce. The four 8-bit digit
+// histograms of the radix sort are accumulated here as well (no separate histogram pass).
+//
+// Arithmetic: this file is compiled with -fmad=false and evaluates every expression in the
+// operation order documented in oracle/vkgs_oracle.c, with IEEE division and square root, so keys
+// and records are bit-identical to the CPU oracle.
+#include <cuda_fp16.h>
+
+#include "device_common.cuh"
+#include "kernels.hpp"
+
+namespace vkgs {
+
+namespace {
+
+constexpr int NWARPS = PRE_TILE / 32;
+
+struct PreSmem
+{
+  // async-copy destinations first (16-byte aligned offsets)
+  float    sh[PRE_TILE * 45];   // 46080 B (fp32 worst case)
+  float    cov[PRE_TILE * 6];   //  6144 B
+  float    rgba[PRE_TILE * 4];  //  4096 B
+  float    center[PRE_TILE * 3];//  3072 B
+  float    scale[PRE_TILE * 3]; //  3072 B (size culling only)
+  uint64_t mbar;
+  uint32_t hist[4][256];
+  uint32_t warpScan[NWARPS + 1];
+  uint32_t tile;
+  uint32_t basePrefix;
+};
+
+__device__ __forceinline__ uint32_t encodeMinMaxFp32(float v)
+{
+  uint32_t bits = __float_as_uint(v);
+  bits ^= static_cast<uint32_t>(static_cast<int32_t>(bits) >> 31) | 0x80000000u;
+  return bits;
+}
+
+// mul(v, S) with Slang row-major S[i][j] = m[4*i+j]
+__device__ __forceinline__ void mulVecMat(const float v[4], const float* m, float out[4])
+{
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+    out[j] = ((v[0] * m[0 + j] + v[1] * m[4 + j]) + v[2] * m[8 + j]) + v[3] * m[12 + j];
+}
+
+template <int FMT>
+__device__ __forceinline__ float loadSh(const void* base, int idx)
+{
+  if constexpr(FMT == VKGS_FORMAT_FLOAT32)
+    return static_cast<const float*>(base)[idx];
+  else if constexpr(FMT == VKGS_FORMAT_FLOAT16)
+    return __half2float(static_cast<const __half*>(base)[idx]);
+  else  // threedgs_particle_buffers.h.slang:119-131: v / 255 * range - halfRange
+    return static_cast<float>(static_cast<const uint8_t*>(base)[idx]) / 255.0f * 2.0f - 1.0f;
+}
+
+__device__ __forceinline__ float4 loadRgba(const void* base, int t, uint32_t fmt)
+{
+  if(fmt == VKGS_FORMAT_FLOAT32)
+    return static_cast<const float4*>(base)[t];
+  if(fmt == VKGS_FORMAT_FLOAT16)
+  {
+    const __half* h = static_cast<const __half*>(base) + 4 * t;
+    return make_float4(__half2float(h[0]), __half2float(h[1]), __half2float(h[2]), __half2float(h[3]));
+  }
+  const uchar4 u = static_cast<const uchar4*>(base)[t];
+  return make_float4(static_cast<float>(u.x) / 255.0f, static_cast<float>(u.y) / 255.0f, static_cast<float>(u.z) / 255.0f,
+                     static_cast<float>(u.w) / 255.0f);
+}
+
+// fetchViewDependentRadiance, threedgs_particle_storage.h.slang:103-159
+template <int FMT>
+__device__ __forceinline__ void shRadiance(const void* row, int rowBase, uint32_t degree, float x, float y, float z, float rgb[3])
+{
+  const float C1    = 0.4886025119029199f;
+  const float C2[5] = {1.0925484f, -1.0925484f, 0.3153916f, -1.0925484f, 0.5462742f};
+  const float C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                       -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+#pragma unroll
+  for(int c = 0; c < 3; c++)
+  {
+#define S(k) loadSh<FMT>(row, rowBase + 3 * (k) + c)
+    float acc = 0.0f;
+    acc += C1 * (-S(0) * y + S(1) * z - S(2) * x);
+    if(degree >= 2)
+    {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      acc += (C2[0] * xy) * S(3) + (C2[1] * yz) * S(4) + (C2[2] * (2.0f * zz - xx - yy)) * S(5) + (C2[3] * xz) * S(6)
+             + (C2[4] * (xx - yy)) * S(7);
+      if(degree >= 3)
+      {
+        acc += C3[0] * S(8) * (3.0f * x * x - y * y) * y + C3[1] * S(9) * x * y * z
+               + C3[2] * S(10) * (4.0f * z * z - x * x - y * y) * y
+               + C3[3] * S(11) * z * (2.0f * z * z - 3.0f * x * x - 3.0f * y * y)
+               + C3[4] * S(12) * x * (4.0f * z * z - x * x - y * y) + C3[5] * S(13) * (x * x - y * y) * z
+               + C3[6] * S(14) * x * (x * x - 3.0f * y * y);
+      }
+    }
+#undef S
+    rgb[c] = acc;
+  }
+}
+
+template <int SHFMT>
+__global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__ PreprocessArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  PreSmem&       sm   = *reinterpret_cast<PreSmem*>(smemRaw);
+  const unsigned tid  = threadIdx.x;
+  const unsigned lane = tid & 31u, warp = tid >> 5;
+
+  // ---- claim a tile (ticket order == look-back order) and start the bulk copies ---------------
+  if(tid == 0)
+  {
+    sm.tile = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u);
+    mbar_init(&sm.mbar, 1);
+    mbar_fence_init();
+  }
+  for(int i = tid; i < 4 * 256; i += PRE_TILE)
+    (&sm.hist[0][0])[i] = 0u;
+  __syncthreads();
+  const uint32_t tile    = sm.tile;
+  const uint64_t first   = static_cast<uint64_t>(tile) * PRE_TILE;
+  const uint32_t shElem  = SHFMT == VKGS_FORMAT_FLOAT32 ? 4u : (SHFMT == VKGS_FORMAT_FLOAT16 ? 2u : 1u);
+  const uint32_t rgbaEl  = a.set.rgbaFormat == VKGS_FORMAT_FLOAT32 ? 4u : (a.set.rgbaFormat == VKGS_FORMAT_FLOAT16 ? 2u : 1u);
+  const bool     hasSh   = a.set.sh != nullptr && a.set.shDegree > 0 && a.fp.sh_degree > 0;
+  const bool     sizeCul = a.opt.size_culling_mode == VKGS_SIZE_CULLING_ENABLED;
+  if(tid == 0)
+  {
+    uint32_t bytes = PRE_TILE * (3 + 6) * 4 + PRE_TILE * 4 * rgbaEl;
+    if(hasSh)
+      bytes += PRE_TILE * 45 * shElem;
+    if(sizeCul)
+      bytes += PRE_TILE * 3 * 4;
+    mbar_arrive_expect_tx(&sm.mbar, bytes);
+    bulk_copy_g2s(sm.center, a.set.centers + first * 3, PRE_TILE * 3 * 4, &sm.mbar);
+    bulk_copy_g2s(sm.cov, a.set.cov6 + first * 6, PRE_TILE * 6 * 4, &sm.mbar);
+    bulk_copy_g2s(sm.rgba, static_cast<const unsigned char*>(a.set.rgba) + first * 4 * rgbaEl, PRE_TILE * 4 * rgbaEl, &sm.mbar);
+    if(hasSh)
+      bulk_copy_g2s(sm.sh, static_cast<const unsigned char*>(a.set.sh) + first * 45 * shElem, PRE_TILE * 45 * shElem, &sm.mbar);
+    if(sizeCul)
+      bulk_copy_g2s(sm.scale, a.set.scales + first * 3, PRE_TILE * 3 * 4, &sm.mbar);
+  }
+  mbar_wait(&sm.mbar, 0);
+
+  const uint64_t id    = first + tid;
+  const bool     inSet = id < a.set.count;
+
+  // ---- K1: dist.comp.slang:55-167 ------------------------------------------------------------
+  bool     keep = inSet;
+  uint32_t key  = 0;
+  float    c[4] = {sm.center[3 * tid + 0], sm.center[3 * tid + 1], sm.center[3 * tid + 2], 1.0f};
+  if(keep)
+  {
+    float t[4], view[4], ndc[4];
+    mulVecMat(c, a.fp.model, t);
+    mulVecMat(t, a.fp.view, view);
+    mulVecMat(view, a.fp.proj, ndc);
+    const float w = ndc[3];
+    ndc[0] = ndc[0] / w, ndc[1] = ndc[1] / w, ndc[2] = ndc[2] / w;
+    const float depth = ndc[2];
+    if(a.opt.frustum_culling_mode == VKGS_FRUSTUM_CULLING_AT_DIST)
+    {
+      const float clip = 1.0f + a.fp.frustum_dilation;
+      if(fabsf(ndc[0]) > clip || fabsf(ndc[1]) > clip || ndc[2] < 0.f - a.fp.frustum_dilation || ndc[2] > 1.0f)
+        keep = false;
+    }
+    if(keep && sizeCul)
+    {
+      const float sx = expf(sm.scale[3 * tid + 0]) * a.fp.splat_scale, sy = expf(sm.scale[3 * tid + 1]) * a.fp.splat_scale,
+                  sz = expf(sm.scale[3 * tid + 2]) * a.fp.splat_scale;
+      const float  radius = fmaxf(sx, fmaxf(sy, sz));
+      float        extent = radius * 2.8284271247f * 2.0f;
+      const float* m      = a.fp.model;
+      const float  l0 = sqrtf(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]), l1 = sqrtf(m[4] * m[4] + m[5] * m[5] + m[6] * m[6]),
+                  l2 = sqrtf(m[8] * m[8] + m[9] * m[9] + m[10] * m[10]);
+      extent *= fmaxf(l0, fmaxf(l1, l2));
+      const float viewDist = fabsf(view[2]);
+      if(viewDist > 0.0001f)
+      {
+        const float maxFocal        = fmaxf(fabsf(a.fp.focal[0]), fabsf(a.fp.focal[1]));
+        const float projectedPixels = (extent * maxFocal) / viewDist;
+        if(projectedPixels < a.fp.size_culling_min_pixels)
+          keep = false;
+      }
+    }
+    key = a.opt.front_to_back ? encodeMinMaxFp32(depth) : encodeMinMaxFp32(-depth);
+  }
+
+  // ---- K5: per-splat projection + colour (threedgs_raster.mesh.slang:161-289) -------------------
+  if(keep)
+  {
+    float4   col   = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
+    bool     valid = !(col.w < a.fp.alpha_cull_threshold);  // mesh.slang:165
+    float    cx = 0.f, cy = 0.f, w1x = 0.f, w1y = 0.f, w2x = 0.f, w2y = 0.f;
+    uint32_t bb0 = 1u, bb1 = 0u;  // empty: x1 < x0
+    if(valid)
+    {
+      float view[4], clip[4];
+      mulVecMat(c, a.mv, view);
+      mulVecMat(view, a.fp.proj, clip);
+      if(a.opt.frustum_culling_mode == VKGS_FRUSTUM_CULLING_AT_RASTER)
+      {
+        const float lim = (1.0f + a.fp.frustum_dilation) * clip[3];
+        if(fabsf(clip[0]) > lim || fabsf(clip[1]) > lim || clip[2] < (0.0f - a.fp.frustum_dilation) * clip[3] || clip[2] > clip[3])
+          valid = false;
+      }
+      if(valid)
+      {
+        if(a.opt.show_sh_only)
+          col.x = col.y = col.z = 0.5f;
+        if(hasSh)
+        {
+          float       d[3] = {c[0] - a.camModel[0], c[1] - a.camModel[1], c[2] - a.camModel[2]};
+          const float dinv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+          d[0] *= dinv, d[1] *= dinv, d[2] *= dinv;
+          const uint32_t degree = min(a.set.shDegree, a.fp.sh_degree);
+          float          rad[3];
+          shRadiance<SHFMT>(sm.sh, 45 * static_cast<int>(tid), degree, d[0], d[1], d[2], rad);
+          col.x += rad[0], col.y += rad[1], col.z += rad[2];
+        }
+        // threedgsCovarianceProjection, threedgs.h.slang:26-56
+        const float* s6      = sm.cov + 6 * tid;
+        const float  C[3][3] = {{s6[0], s6[1], s6[2]}, {s6[1], s6[3], s6[4]}, {s6[2], s6[4], s6[5]}};
+        const float  fx = a.fp.focal[0], fy = a.fp.focal[1];
+        const float  s   = 1.0f / (view[2] * view[2]);
+        const float  J00 = fx / view[2], J02 = -(fx * view[0]) * s;
+        const float  J11 = fy / view[2], J12 = -(fy * view[1]) * s;
+        float        T[2][3];
+#pragma unroll
+        for(int j = 0; j < 3; j++)
+        {
+          T[0][j] = J00 * a.mv[4 * j + 0] + J02 * a.mv[4 * j + 2];
+          T[1][j] = J11 * a.mv[4 * j + 1] + J12 * a.mv[4 * j + 2];
+        }
+        float TC[2][3];
+#pragma unroll
+        for(int i = 0; i < 2; i++)
+#pragma unroll
+          for(int j = 0; j < 3; j++)
+            TC[i][j] = (T[i][0] * C[0][j] + T[i][1] * C[1][j]) + T[i][2] * C[2][j];
+        float cov0 = (TC[0][0] * T[0][0] + TC[0][1] * T[0][1]) + TC[0][2] * T[0][2];
+        float cov1 = (TC[0][0] * T[1][0] + TC[0][1] * T[1][1]) + TC[0][2] * T[1][2];
+        float cov2 = (TC[1][0] * T[1][0] + TC[1][1] * T[1][1]) + TC[1][2] * T[1][2];
+
+        // threedgsProjectedExtentBasis, threedgs.h.slang:60-121
+        float detOrig = 0.0f;
+        if(a.opt.ms_antialiasing)
+          detOrig = cov0 * cov2 - cov1 * cov1;
+        cov0 += 0.3f;
+        cov2 += 0.3f;
+        if(a.opt.ms_antialiasing)
+        {
+          const float detBlur = cov0 * cov2 - cov1 * cov1;
+          col.w *= sqrtf(fmaxf(detOrig / detBlur, 0.0f));
+        }
+        const float D          = cov0 * cov2 - cov1 * cov1;
+        const float trace      = cov0 + cov2;
+        const float traceOver2 = 0.5f * trace;
+        const float term2      = sqrtf(fmaxf(0.1f, traceOver2 * traceOver2 - D));
+        float       ev1        = traceOver2 + term2;
+        float       ev2        = traceOver2 - term2;
+        if(ev2 <= 0.0f)
+          valid = false;
+        if(valid)
+        {
+          if(a.opt.point_cloud_mode)
+            ev1 = ev2 = 0.2f;
+          float       e1x  = (fabsf(cov1) < 0.001f) ? 1.0f : cov1;
+          float       e1y  = ev1 - cov0;
+          const float einv = 1.0f / sqrtf(e1x * e1x + e1y * e1y);
+          e1x *= einv, e1y *= einv;
+          const float e2x = e1y, e2y = -e1x;
+          const float sqrt8 = 2.8284271247461903f;
+          const float m1 = fminf(sqrt8 * sqrtf(ev1), 2048.0f), m2 = fminf(sqrt8 * sqrtf(ev2), 2048.0f);
+          const float b1x = e1x * a.fp.splat_scale * m1, b1y = e1y * a.fp.splat_scale * m1;
+          const float b2x = e2x * a.fp.splat_scale * m2, b2y = e2y * a.fp.splat_scale * m2;
+
+          // quad centre in pixels + affine fragPos basis (mesh.slang:201,276-289)
+          const float nz = clip[2] / clip[3];
+          cx             = ((clip[0] / clip[3]) * 0.5f + 0.5f) * a.fp.viewport[0];
+          cy             = ((clip[1] / clip[3]) * 0.5f + 0.5f) * a.fp.viewport[1];
+          const float n1 = b1x * b1x + b1y * b1y, n2 = b2x * b2x + b2y * b2y;
+          const float k1 = sqrt8 / n1, k2 = sqrt8 / n2;
+          w1x = b1x * k1, w1y = b1y * k1, w2x = b2x * k2, w2y = b2y * k2;
+          valid = (nz >= 0.0f && nz <= 1.0f);
+          if(!(n1 > 0.0f) || !(n2 > 0.0f) || !isfinite(k1) || !isfinite(k2) || !isfinite(cx) || !isfinite(cy))
+            valid = false;
+
+          if(valid)
+          {
+            // Conservative pixel bounding box of {A <= 8 and opacity > 1/255}: the ellipse with
+            // semi-axes b1,b2, shrunk when the splat's own alpha reaches 1/255 before A = 8.
+            float hx = sqrtf(b1x * b1x + b2x * b2x), hy = sqrtf(b1y * b1y + b2y * b2y);
+            if(!a.opt.disable_opacity_gaussian)
+            {
+              const float amax = 2.0f * logf(255.0f * col.w) * 1.00001f + 1e-4f;  // A < 2 ln(255 a)
+              if(!(amax > 0.0f))
+                valid = false;
+              else if(amax < 8.0f)
+              {
+                const float r = sqrtf(amax * 0.125f);
+                hx *= r, hy *= r;
+              }
+            }
+            hx = hx * 1.00001f + 0.01f, hy = hy * 1.00001f + 0.01f;
+            const float W = a.fp.viewport[0], H = a.fp.viewport[1];
+            const float fx0 = ceilf(cx - hx - 0.5f), fx1 = floorf(cx + hx - 0.5f);
+            const float fy0 = ceilf(cy - hy - 0.5f), fy1 = floorf(cy + hy - 0.5f);
+            if(!valid || fx1 < 0.0f || fy1 < 0.0f || fx0 > W - 1.0f || fy0 > H - 1.0f || fx1 < fx0 || fy1 < fy0)
+              valid = false;
+            else
+            {
+              const uint32_t x0 = static_cast<uint32_t>(fmaxf(fx0, 0.0f)), x1 = static_cast<uint32_t>(fminf(fx1, W - 1.0f));
+              const uint32_t y0 = static_cast<uint32_t>(fmaxf(fy0, 0.0f)), y1 = static_cast<uint32_t>(fminf(fy1, H - 1.0f));
+              bb0 = x0 | (y0 << 16);
+              bb1 = x1 | (y1 << 16);
+            }
+          }
+        }
+      }
+    }
+    if(!valid)
+      bb0 = 1u, bb1 = 0u;
+    float4* rec = reinterpret_cast<float4*>(a.records + id * RECORD_WORDS);
+    rec[0]      = make_float4(cx, cy, w1x, w1y);
+    rec[1]      = make_float4(w2x, w2y, col.x, col.y);
+    rec[2]      = make_float4(col.z, col.w, __uint_as_float(bb0), __uint_as_float(bb1));
+  }
+
+  // ---- deterministic append: block rank + decoupled look-back over tiles -----------------------
+  const unsigned ballot   = __ballot_sync(FULL_MASK, keep);
+  const uint32_t warpRank = __popc(ballot & ((1u << lane) - 1u));
+  if(lane == 0)
+    sm.warpScan[warp] = __popc(ballot);
+  if(keep)
+  {
+    atomicAdd(&sm.hist[0][key & 0xffu], 1u);
+    atomicAdd(&sm.hist[1][(key >> 8) & 0xffu], 1u);
+    atomicAdd(&sm.hist[2][(key >> 16) & 0xffu], 1u);
+    atomicAdd(&sm.hist[3][key >> 24], 1u);
+  }
+  __syncthreads();
+  if(warp == 0)
+  {
+    const uint32_t cnt = lane < NWARPS ? sm.warpScan[lane] : 0u;
+    const uint32_t inc = warp_inclusive_scan(cnt, lane);
+    if(lane < NWARPS)
+      sm.warpScan[lane] = inc - cnt;
+    const uint32_t total = __shfl_sync(FULL_MASK, inc, NWARPS - 1);
+    if(lane == 0)
+    {
+      uint64_t* st = a.status + tile;
+      if(tile == 0)
+      {
+        lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, total));
+        sm.basePrefix = 0;
+      }
+      else
+      {
+        lb_store(st, lb_pack(a.epoch, LB_AGGREGATE, total));
+        const uint32_t excl = lb_lookback(a.status, tile, 1, a.epoch);
+        lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, excl + total));
+        sm.basePrefix = excl;
+      }
+      // the tile holding the last splat knows V once its prefix is resolved
+      if(first + PRE_TILE >= a.set.count)
+        a.counters->visible = sm.basePrefix + total;
+    }
+  }
+  __syncthreads();
+  if(keep)
+  {
+    const uint32_t slot = sm.basePrefix + sm.warpScan[warp] + warpRank;
+    a.keys[slot]        = key;
+    a.ids[slot]         = static_cast<uint32_t>(id);
+  }
+  // flush the digit histograms (only bins this tile touched)
+  for(int i = tid; i < 4 * 256; i += PRE_TILE)
+  {
+    const uint32_t v = (&sm.hist[0][0])[i];
+    if(v)
+      atomicAdd(&a.counters->depthHist[0][0] + i, v);
+  }
+}
+
+}  // namespace
+
+void initPreprocessKernels()
+{
+  const int smem = static_cast<int>(sizeof(PreSmem));
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_UINT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream)
+{
+  const uint32_t tiles = (args.set.count + PRE_TILE - 1) / PRE_TILE;
+  const size_t   smem  = sizeof(PreSmem);
+  switch(args.set.shFormat)
+  {
+    case VKGS_FORMAT_FLOAT16:
+      k_preprocess<VKGS_FORMAT_FLOAT16><<<tiles, PRE_TILE, smem, stream>>>(args);
+      break;
+    case VKGS_FORMAT_UINT8:
+      k_preprocess<VKGS_FORMAT_UINT8><<<tiles, PRE_TILE, smem, stream>>>(args);
+      break;
+    default:
+      k_preprocess<VKGS_FORMAT_FLOAT32><<<tiles, PRE_TILE, smem, stream>>>(args);
+      break;
+  }
+}
+
+}  // namespace vkgs

@@ -1,0 +1,231 @@
+// k_radix_sort.cu — stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass.
+//
+// Replaces the vrdx key-value sort the reference records each frame
+// (vrdxCmdSortKeyValueIndirect, 3rdparty/vrdx/src/vk_radix_sort.cc:249-258,262-416; shaders
+// upsweep/spine/downsweep.slang). Same contract: ascending, stable, pair count read on the device.
+// vrdx is reduce-then-scan (3 dispatches and ~20 B/pair per pass). This is a single-pass
+// ("onesweep") design instead: the digit histograms of all passes are produced by whichever
+// kernel wrote the keys, and each pass is ONE kernel that ranks a 4096-pair partition in shared
+// memory, resolves its global digit offsets with a decoupled look-back over earlier partitions
+// (epoch-stamped 64-bit status words: nothing is cleared between passes or frames) and scatters
+// through shared memory so global writes leave in digit-contiguous runs. Traffic per pass is one
+// read + one write of the pairs (16 B/pair), i.e. 64 B/pair for 32-bit keys.
+//
+// Stability: a partition is ranked in (warp, item, lane) order, which is the input order because
+// each warp loads a contiguous chunk in a warp-striped arrangement; partitions are ordered by a
+// ticket taken at block start, which also guarantees the look-back never waits on a block that
+// has not been scheduled.
+#include "device_common.cuh"
+#include "kernels.hpp"
+
+namespace vkgs {
+
+namespace {
+
+constexpr int NWARPS = SORT_THREADS / 32;
+
+struct SortSmem
+{
+  union
+  {
+    uint32_t warpHist[NWARPS][256];  // per-warp digit counters, then per-warp exclusive offsets
+    uint32_t stageKeys[SORT_PART];   // (re-used after ranking) block-sorted keys
+  };
+  uint32_t stageVals[SORT_PART];
+  uint32_t digitStart[256];   // first block-local position of each digit
+  uint32_t globalBase[256];   // global position of the first key of each digit of this partition
+  uint32_t scan[NWARPS + 1];
+  uint32_t part;
+};
+static_assert(sizeof(uint32_t) * NWARPS * 256 <= sizeof(uint32_t) * SORT_PART, "warpHist must fit in the key staging area");
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constant__ SortPassArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  SortSmem&      sm   = *reinterpret_cast<SortSmem*>(smemRaw);
+  const unsigned tid  = threadIdx.x;
+  const unsigned lane = tid & 31u, warp = tid >> 5;
+
+  const uint32_t count = *a.countPtr;
+  const uint32_t parts = (count + SORT_PART - 1) / SORT_PART;
+  if(tid == 0)
+    sm.part = atomicAdd(a.ticket, 1u);
+  for(int i = tid; i < NWARPS * 256; i += SORT_THREADS)
+    (&sm.warpHist[0][0])[i] = 0u;
+  __syncthreads();
+  const uint32_t part = sm.part;
+  if(part >= parts)
+    return;
+
+  // ---- load (warp-striped: warp w owns SORT_ITEMS*32 consecutive pairs) ------------------------
+  const uint32_t partBase = part * SORT_PART;
+  const uint32_t warpBase = partBase + warp * (SORT_ITEMS * 32);
+  uint32_t       keys[SORT_ITEMS], vals[SORT_ITEMS];
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+  {
+    const uint32_t idx = warpBase + i * 32 + lane;
+    const bool     ok  = idx < count;
+    keys[i]            = ok ? a.keysIn[idx] : 0xffffffffu;  // padding sorts last, is never written back
+    vals[i]            = ok ? a.valsIn[idx] : 0u;
+  }
+
+  // ---- rank within the warp (match-any multi-split) --------------------------------------------
+  uint32_t rank[SORT_ITEMS];
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+  {
+    const uint32_t digit  = (keys[i] >> a.shift) & 0xffu;
+    const unsigned peers  = __match_any_sync(FULL_MASK, digit);
+    const unsigned leader = __ffs(peers) - 1;
+    uint32_t       before = 0;
+    if(lane == leader)
+    {
+      before                  = sm.warpHist[warp][digit];
+      sm.warpHist[warp][digit] = before + __popc(peers);
+    }
+    before  = __shfl_sync(FULL_MASK, before, leader);
+    rank[i] = before + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per-digit: exclusive scan over warps, block totals --------------------------------------
+  uint32_t digitCount = 0;
+  if(tid < 256)
+  {
+    uint32_t run = 0;
+#pragma unroll
+    for(int w = 0; w < NWARPS; w++)
+    {
+      const uint32_t c      = sm.warpHist[w][tid];
+      sm.warpHist[w][tid]   = run;
+      run += c;
+    }
+    digitCount = run;
+  }
+  // exclusive scan of the 256 digit totals -> block-local start of each digit
+  {
+    uint32_t       total;
+    const uint32_t excl = block_exclusive_scan<NWARPS>(tid < 256 ? digitCount : 0u, sm.scan, total);
+    if(tid < 256)
+      sm.digitStart[tid] = excl;
+  }
+
+  // ---- global digit offsets: decoupled look-back, one chain per digit --------------------------
+  if(tid < 256)
+  {
+    uint64_t* mine = a.status + static_cast<uint64_t>(part) * 256 + tid;
+    // padding keys (digit 0xff of the last partition) are not counted
+    uint32_t realCount = digitCount;
+    if(tid == 255 && partBase + SORT_PART > count)
+      realCount -= (partBase + SORT_PART - count);
+    uint32_t excl;
+    if(part == 0)
+    {
+      // exclusive scan of the global digit histogram = first global position of each digit.
+      // (only partition 0 needs it; everyone else inherits it through the look-back chain)
+      const uint32_t h   = a.histogram[tid];
+      uint32_t       inc = warp_inclusive_scan(h, lane);
+      __shared__ uint32_t warpTot[8];
+      if(lane == 31)
+        warpTot[warp] = inc;
+      asm volatile("bar.sync 1, 256;");
+      uint32_t add = 0;
+      for(unsigned w = 0; w < warp; w++)
+        add += warpTot[w];
+      excl = inc - h + add;
+      lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
+    }
+    else
+    {
+      lb_store(mine, lb_pack(a.epoch, LB_AGGREGATE, realCount));
+      excl = lb_lookback(a.status + tid, part, 256, a.epoch);
+      lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
+    }
+    sm.globalBase[tid] = excl;
+  }
+  __syncthreads();
+
+  // ---- block-local positions; stage pairs in sorted order --------------------------------------
+  uint32_t pos[SORT_ITEMS];
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+  {
+    const uint32_t digit = (keys[i] >> a.shift) & 0xffu;
+    pos[i]               = sm.digitStart[digit] + sm.warpHist[warp][digit] + rank[i];
+  }
+  __syncthreads();  // warpHist is dead from here: its storage becomes stageKeys
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+  {
+    sm.stageKeys[pos[i]] = keys[i];
+    sm.stageVals[pos[i]] = vals[i];
+  }
+  __syncthreads();
+
+  // ---- scatter: consecutive threads write consecutive positions of a digit run -----------------
+  const uint32_t valid = min(static_cast<uint32_t>(SORT_PART), count - partBase);
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+  {
+    const uint32_t j = i * SORT_THREADS + tid;
+    if(j < valid)
+    {
+      const uint32_t k     = sm.stageKeys[j];
+      const uint32_t digit = (k >> a.shift) & 0xffu;
+      const uint32_t dst   = sm.globalBase[digit] + (j - sm.digitStart[digit]);
+      a.keysOut[dst]       = k;
+      a.valsOut[dst]       = sm.stageVals[j];
+    }
+  }
+}
+
+// Stand-alone digit histograms (used by vkgs_sort_pairs; the frame pipeline fuses them upstream).
+__global__ void __launch_bounds__(256) k_histogram(const uint32_t* __restrict__ keys, const uint32_t* countPtr, uint32_t* hist,
+                                                   int firstShift, int passes)
+{
+  __shared__ uint32_t s[4][256];
+  for(int i = threadIdx.x; i < 4 * 256; i += 256)
+    (&s[0][0])[i] = 0u;
+  __syncthreads();
+  const uint32_t count = *countPtr;
+  for(uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x; i < count; i += static_cast<uint64_t>(gridDim.x) * 256)
+  {
+    const uint32_t k = keys[i];
+    for(int p = 0; p < passes; p++)
+      atomicAdd(&s[p][(k >> (firstShift + 8 * p)) & 0xffu], 1u);
+  }
+  __syncthreads();
+  for(int i = threadIdx.x; i < passes * 256; i += 256)
+  {
+    const uint32_t v = (&s[0][0])[i];
+    if(v)
+      atomicAdd(hist + i, v);
+  }
+}
+
+}  // namespace
+
+void launchSortPass(const SortPassArgs& args, cudaStream_t stream)
+{
+  const uint32_t parts = (args.maxCount + SORT_PART - 1) / SORT_PART;
+  if(parts == 0)
+    return;
+  k_sort_pass<<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
+}
+
+void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t maxCount, uint32_t* hist, int firstShift, int passes,
+                     cudaStream_t stream)
+{
+  uint32_t blocks = (maxCount + 256 * 16 - 1) / (256 * 16);
+  blocks          = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+  k_histogram<<<blocks, 256, 0, stream>>>(keys, countPtr, hist, firstShift, passes);
+}
+
+void initSortKernels()
+{
+  cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
+}
+
+}  // namespace vkgs

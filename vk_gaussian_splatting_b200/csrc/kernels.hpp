@@ -1,0 +1,120 @@
+// kernels.hpp — host-callable launchers of the sm_100a kernels (one translation unit per stage).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "vkgs_b200.h"
+
+namespace vkgs {
+
+// ---- geometry of the per-frame pipeline ------------------------------------------------------
+constexpr int      PRE_TILE        = 256;   // splats per preprocess tile (= block size)
+constexpr int      RECORD_WORDS    = 12;    // per-splat record, 48 B
+constexpr int      SORT_THREADS    = 512;
+constexpr int      SORT_ITEMS      = 8;     // keys per thread
+constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per partition
+constexpr int      BIN_THREADS     = 256;
+constexpr int      TILE_W          = 16;
+constexpr int      TILE_H          = 16;
+constexpr int      BLEND_THREADS   = TILE_W * TILE_H;
+
+// Small per-frame control block in HBM, cleared with one memset at the start of every frame.
+struct FrameCounters
+{
+  uint32_t visible;            // V: splats that passed the dist-stage cull (IndirectParams.instanceCount)
+  uint32_t tilePairs;          // D: (splat,tile) pairs the binning wanted to emit
+  uint32_t tilePairsClamped;   // min(D, capacity): what the tile sort actually processes
+  uint32_t overflow;           // set when D exceeded the tile-list capacity
+  uint32_t ticket[12];         // dynamic tile / partition tickets, one per kernel launch
+  uint32_t depthHist[4][256];  // digit histograms of the depth keys (filled by the preprocess kernel)
+  uint32_t tileHist[2][256];   // digit histograms of the tile ids (filled by the binning kernel)
+};
+
+struct DeviceSplatSet
+{
+  const float* centers;  // 3 x f32, padded to PRE_TILE rows
+  const float* cov6;     // 6 x f32
+  const float* scales;   // 3 x f32 (log), size culling only
+  const void*  rgba;     // 4 x {f32,f16,u8}
+  const void*  sh;       // 45 x {f32,f16,u8} or nullptr
+  uint32_t     count;
+  uint32_t     shDegree;
+  uint32_t     shFormat;
+  uint32_t     rgbaFormat;
+};
+
+struct PreprocessArgs
+{
+  DeviceSplatSet    set;
+  vkgs_frame_params fp;
+  vkgs_options      opt;
+  float             mv[16];      // mul(transform, viewMatrix), evaluated once per frame on the host
+  float             camModel[3]; // camera position in model space
+  uint32_t*         keys;        // [V] compacted, ascending splat id
+  uint32_t*         ids;         // [V]
+  uint32_t*         records;     // [N][RECORD_WORDS], indexed by splat id
+  FrameCounters*    counters;
+  uint64_t*         status;      // look-back chain, one word per tile
+  uint32_t          epoch;
+  uint32_t          ticketSlot;
+};
+
+void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream);
+
+struct SortPassArgs
+{
+  const uint32_t* keysIn;
+  const uint32_t* valsIn;
+  uint32_t*       keysOut;
+  uint32_t*       valsOut;
+  const uint32_t* countPtr;   // device-side number of pairs
+  uint32_t        maxCount;   // host-side upper bound (sizes the grid)
+  const uint32_t* histogram;  // 256 digit counts of this pass (not yet scanned)
+  uint64_t*       status;     // [partitions][256] look-back words
+  uint32_t*       ticket;
+  uint32_t        epoch;
+  int             shift;
+};
+
+void launchSortPass(const SortPassArgs& args, cudaStream_t stream);
+
+// Digit histograms for `passes` 8-bit digits starting at bit `firstShift` (stand-alone sort only;
+// the frame pipeline fuses its histograms into the producing kernels).
+void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t maxCount, uint32_t* hist /*[passes][256]*/,
+                     int firstShift, int passes, cudaStream_t stream);
+
+struct BinArgs
+{
+  const uint32_t* sortedIds;   // [V] depth-sorted splat ids
+  const uint32_t* records;
+  FrameCounters*  counters;
+  uint32_t*       tileKeys;    // [capacity]
+  uint32_t*       tileVals;    // [capacity] splat id
+  uint32_t        capacity;
+  uint32_t        maxCount;    // upper bound of V
+  uint32_t        tilesX, tilesY;
+  uint64_t*       status;
+  uint32_t        epoch;
+  uint32_t        ticketSlot;
+};
+
+void launchBinEmit(const BinArgs& args, cudaStream_t stream);
+
+void launchTileRanges(const uint32_t* tileKeys, const FrameCounters* counters, uint32_t capacity, uint2* ranges,
+                      cudaStream_t stream);
+
+struct BlendArgs
+{
+  const uint32_t* tileVals;  // tile-sorted splat ids
+  const uint2*    ranges;    // [tiles] (begin,end) into tileVals
+  const uint32_t* records;
+  float4*         image;     // [H][W] RGBA fp32
+  uint32_t        width, height, tilesX, tilesY;
+  uint32_t        frontToBack;
+  uint32_t        disableOpacityGaussian;
+  float           transmittanceEpsilon;
+};
+
+void launchBlend(const BlendArgs& args, cudaStream_t stream);
+
+}  // namespace vkgs
