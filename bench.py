@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the 3DGS forward raster path (dist/cull -> radix sort -> tile raster).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU sort path, host cores
+
+A "step" is one frame of the hot path. Workload at every N: BASELINE.json configs[1] — 1 M-splat
+synthetic scene, SH degree 3, 1920x1080, reference default camera, front-to-back compositing
+(north_star). Multi-GPU (N>1, launched by torch.distributed.run, one rank per GPU) is the
+embarrassingly parallel multi-view case: every rank holds the full scene and renders its own
+camera (rank r = default eye rotated r*45 deg about +Y); no data-path collective, NCCL only
+carries the barrier and the max-over-ranks timing ("weak" scaling: work per GPU is fixed).
+
+Prints ONE JSON line (rank 0). `value` = frames/s with the scene resident in HBM and the frame left
+in HBM; `e2e` = the same through the synchronous C-ABI call with host frame parameters in and the
+fp32 RGBA frame copied to pinned host memory every step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_SPLATS = 1_000_000
+SH_DEGREE = 3
+WIDTH, HEIGHT = 1920, 1080
+SEED = 0x3D650001  # 0x3D650000 + config index
+EPS = 2.0 ** -15   # front-to-back early-out; error bound eps*max|rgb| < 1e-4 (tests/test_gpu_parity.py)
+WORKLOAD = "configs[1]: 1M-splat synthetic scene, SH degree 3, 1920x1080, default camera, front-to-back"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+def cpu_sorter_baseline(scene, cam, budget_s=12.0, max_reps=20):
+    """The reference's CPU sorting path (splat_sorter_async restatement in oracle/) on all host cores."""
+    import numpy as np
+    from oracle import oracle as O
+    threads = O.hardware_concurrency()
+    eye = np.array(cam.eye, np.float32)
+    direction = np.array(cam.ctr, np.float32) - eye
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    best, t_start, reps = None, time.perf_counter(), 0
+    O.cpu_sort(scene.positions, ident, direction, eye, front_to_back=True, mode=1, threads=threads)  # warm-up
+    while reps < max_reps and (time.perf_counter() - t_start) < budget_s:
+        _, _, ms_d, ms_s = O.cpu_sort(scene.positions, ident, direction, eye, front_to_back=True, mode=1, threads=threads)
+        if best is None or ms_d + ms_s < best[0] + best[1]:
+            best = (ms_d, ms_s)
+        reps += 1
+    return {"ms_dist": best[0], "ms_sort": best[1], "cores": threads, "reps": reps}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its CPU sorting mode:
+    SplatSorterAsync::innerSort, all host threads). The reference has no CPU rasterizer, so a
+    reference 'frame' is CPU Dist + CPU Sort of all N splats; rank 0 alone runs it."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    import numpy as np
+    import vk_gaussian_splatting_b200 as g
+    from oracle import oracle as O
+    scene = g.synth_scene(N_SPLATS, SH_DEGREE, SEED)
+    cam = g.default_camera()
+    threads = O.hardware_concurrency()
+    eye = np.array(cam.eye, np.float32)
+    direction = np.array(cam.ctr, np.float32) - eye
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    for _ in range(args.warmup):
+        O.cpu_sort(scene.positions, ident, direction, eye, True, 1, threads)
+    t0 = time.perf_counter()
+    dsum = ssum = 0.0
+    for _ in range(args.steps):
+        _, _, md, ms = O.cpu_sort(scene.positions, ident, direction, eye, True, 1, threads)
+        dsum += md
+        ssum += ms
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "splats": N_SPLATS, "note": "CPU Dist + CPU Sort only; the reference has no CPU rasterizer"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"full sort of all {N_SPLATS} splats per step (splat_sorter_async restatement, "
+                                   f"__gnu_parallel::sort on {threads} threads); ms_dist={dsum / args.steps:.2f} ms_sort={ssum / args.steps:.2f}"},
+        "msplats_per_sec": fps * N_SPLATS / 1e6,
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import vk_gaussian_splatting_b200 as g
+    from vk_gaussian_splatting_b200 import _abi as A
+
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    scene = g.synth_scene(N_SPLATS, SH_DEGREE, SEED)  # every rank regenerates the scene from the seed
+    cam = g.orbit_camera(rank % 8, 8)                 # rank 0 = the reference default camera
+    fp = g.frame_params(cam, WIDTH, HEIGHT)
+    opt = g.default_options(front_to_back=1, transmittance_epsilon=EPS)
+
+    # a real (non-default) torch stream: the context launches on it, torch.cuda.Event times it
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    r = g.GaussianSplatting(local, stream=stream.cuda_stream)
+    r.upload(scene, opt)
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        r.render_async(fp)
+    r.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = r.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        r.render_async(fp)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    launches = r.launch_count() - l0
+    r.sync()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    st = r.last_frame_stats()
+    fps = world * args.steps / (ms_total / 1000.0)
+
+    # ---- end to end: host params in, RGBA frame to pinned host memory out, synchronous call ---------
+    host_img = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True)
+    host_np = host_img.numpy()
+    e2e_steps = max(10, min(args.steps, 100))
+    for _ in range(3):
+        r.render(fp, out=host_np)
+    barrier()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        r.render(fp, out=host_np)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    fps_e2e = world * e2e_steps / (ms_e2e / 1000.0)
+
+    # ---- per-kernel profile (separate frames, cudaEvents around every launch on the launch stream) --
+    r.set_profiling(True)
+    acc, nprof = {}, 10
+    for _ in range(nprof):
+        for _ in range(8):  # steady state: frames back to back, events of the last one are read
+            r.render_async(fp)
+        s = r.last_frame_stats()
+        for k, v in s.ms_kernel.items():
+            acc[k] = acc.get(k, 0.0) + v / nprof
+    r.set_profiling(False)
+    stage_ms = {"GPU Dist": acc["preprocess"], "GPU Sort": acc["sort_hist"] + sum(acc[f"sort_pass{i}"] for i in range(4)),
+                "Rasterization": acc["bin_emit"] + acc["tile_hist"] + acc["tile_sort0"] + acc["tile_sort1"] + acc["tile_ranges"] + acc["blend"]}
+    dominant = max(acc, key=acc.get)
+    n, v, p, d = N_SPLATS, st.visible_count, WIDTH * HEIGHT, st.tile_pairs
+    # algorithmic bytes per launch (SURVEY.md §8d per-unit figures; DESIGN.md "Kernels")
+    alg = {"preprocess": 12 * n + 8 * v + 236 * v, "sort_hist": 4 * v, "bin_emit": 4 * v + 8 * v, "tile_hist": 4 * d,
+           "tile_ranges": 4 * d, "blend": 16 * p, "tile_sort0": 16 * d, "tile_sort1": 16 * d}
+    for i in range(4):
+        alg[f"sort_pass{i}"] = 16 * v
+    peak, peak_src = peaks()
+    ach = alg[dominant] / (acc[dominant] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": acc[dominant],
+                "per_kernel_gbs": {k: alg[k] / (acc[k] * 1e-3) / 1e9 for k in alg if acc.get(k, 0) > 0}}
+    whole = st.bytes_algorithmic / (ms_total / args.steps * 1e-3) / 1e9
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "splats": N_SPLATS, "sh_degree": SH_DEGREE, "width": WIDTH, "height": HEIGHT,
+                       "views": "one camera per GPU (rank r: default eye rotated r*45deg about +Y)", "seed": hex(SEED),
+                       "transmittance_epsilon": EPS,
+                       "l2": "per-frame inputs (232 MB of splat attributes) exceed the 126 MB L2; no explicit flush"},
+            "msplats_per_sec": fps * N_SPLATS / 1e6, "visible_splats": v, "tile_pairs": d,
+            "stage_ms": stage_ms, "kernel_ms": acc,
+            "frame_algorithmic_bytes": st.bytes_algorithmic, "frame_hbm_gbs": whole, "frame_hbm_frac": whole / peak,
+            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": C.sizeof(A.FrameParams),
+                    "d2h_bytes_per_step": WIDTH * HEIGHT * 16 + 16, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_sorter_baseline(scene, cam)
+            f = 1000.0 / (cb["ms_dist"] + cb["ms_sort"])
+            line["cpu_baseline"] = {"value": f, "unit": "frames/s", "cores": cb["cores"], "kind": "port",
+                                    "sample": f"best of {cb['reps']} full sorts of all {N_SPLATS} splats (CPU Dist {cb['ms_dist']:.2f} ms + "
+                                              f"CPU Sort {cb['ms_sort']:.2f} ms, splat_sorter_async restatement, __gnu_parallel::sort); "
+                                              "raster excluded: the reference has no CPU rasterizer"}
+        else:
+            line["cpu_baseline"] = None
+    r.close()
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -147,10 +147,10 @@ typedef struct vkgs_outputs
 
 /* indices into vkgs_outputs.ms_kernel */
 #define VKGS_K_PREPROCESS 0   /* dist/cull + project + SH (one fused kernel) */
-#define VKGS_K_SORT_SCAN 1
+#define VKGS_K_SORT_SCAN 1    /* digit histograms of the depth keys */
 #define VKGS_K_SORT_PASS0 2   /* .. +3 = passes 0..3 */
 #define VKGS_K_BIN_EMIT 6
-#define VKGS_K_TILE_HIST 7
+#define VKGS_K_TILE_HIST 7    /* digit histograms of the tile ids */
 #define VKGS_K_TILE_SORT0 8   /* .. +1 */
 #define VKGS_K_TILE_RANGES 10
 #define VKGS_K_BLEND 11

@@ -25,7 +25,7 @@ FORMAT_FLOAT32, FORMAT_FLOAT16, FORMAT_UINT8 = 0, 1, 2
 FRUSTUM_CULLING_NONE, FRUSTUM_CULLING_AT_DIST, FRUSTUM_CULLING_AT_RASTER = 0, 1, 2
 SIZE_CULLING_DISABLED, SIZE_CULLING_ENABLED = 0, 1
 
-K_NAMES = ["preprocess", "sort_scan", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "bin_emit",
+K_NAMES = ["preprocess", "sort_hist", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "bin_emit",
            "tile_hist", "tile_sort0", "tile_sort1", "tile_ranges", "blend"]
 K_COUNT = 12
 

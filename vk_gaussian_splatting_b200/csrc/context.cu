@@ -203,16 +203,16 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp)
   launchPreprocess(pa, c->stream);
   c->launches++;
   mark(c, VKGS_K_PREPROCESS + 1);
-  mark(c, VKGS_K_SORT_SCAN + 1);  // (the histogram scan is folded into partition 0 of each pass)
+  mark(c, VKGS_K_SORT_SCAN + 1);  // (depth-key digit histograms are fused into the preprocess kernel)
 
   // ---- "GPU Sort": 4 x 8-bit stable passes over (key,id) ----------------------------------------
   for(int p = 0; p < 4; p++)
   {
     SortPassArgs sa{};
-    sa.keysIn    = c->dKeys[p & 1];
-    sa.valsIn    = c->dIds[p & 1];
-    sa.keysOut   = c->dKeys[(p + 1) & 1];
-    sa.valsOut   = c->dIds[(p + 1) & 1];
+    sa.keys[0] = c->dKeys[0], sa.keys[1] = c->dKeys[1];
+    sa.vals[0] = c->dIds[0], sa.vals[1] = c->dIds[1];
+    sa.srcSelIn  = p ? &c->dCounters->sortSrc[p - 1] : nullptr;
+    sa.srcSelOut = &c->dCounters->sortSrc[p];
     sa.countPtr  = &c->dCounters->visible;
     sa.maxCount  = n;
     sa.histogram = &c->dCounters->depthHist[p][0];
@@ -224,11 +224,12 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp)
     c->launches++;
     mark(c, VKGS_K_SORT_PASS0 + p + 1);
   }
-  // after 4 passes the sorted pairs are back in buffer 0
+  // the sorted pairs are in buffer sortSrc[3] (0 unless an odd number of passes was skipped)
 
   // ---- "Rasterization": binning, tile sort, blend -------------------------------------------------
   BinArgs ba{};
-  ba.sortedIds  = c->dIds[0];
+  ba.sortedIds[0] = c->dIds[0], ba.sortedIds[1] = c->dIds[1];
+  ba.sortedSel  = &c->dCounters->sortSrc[3];
   ba.records    = c->dRecords;
   ba.counters   = c->dCounters;
   ba.tileKeys   = c->dTileKeys[0];
@@ -240,18 +241,18 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp)
   ba.status     = c->dBinStatus;
   ba.epoch      = nextEpoch(c);
   ba.ticketSlot = 5;
+  ba.debugFlags = c->opt._reserved[5];
   launchBinEmit(ba, c->stream);
   c->launches++;
   mark(c, VKGS_K_BIN_EMIT + 1);
-  mark(c, VKGS_K_TILE_HIST + 1);  // (histograms are fused into the emit kernel)
+  mark(c, VKGS_K_TILE_HIST + 1);  // (tile-id digit histograms are fused into the emit kernel)
 
   for(int p = 0; p < 2; p++)
   {
     SortPassArgs sa{};
-    sa.keysIn    = c->dTileKeys[p & 1];
-    sa.valsIn    = c->dTileVals[p & 1];
-    sa.keysOut   = c->dTileKeys[(p + 1) & 1];
-    sa.valsOut   = c->dTileVals[(p + 1) & 1];
+    // fixed ping-pong (no pass skipping): pass 0 reads buffer 0, pass 1 reads buffer 1
+    sa.keys[0] = c->dTileKeys[p & 1], sa.keys[1] = c->dTileKeys[(p + 1) & 1];
+    sa.vals[0] = c->dTileVals[p & 1], sa.vals[1] = c->dTileVals[(p + 1) & 1];
     sa.countPtr  = &c->dCounters->tilePairsClamped;
     sa.maxCount  = static_cast<uint32_t>(c->tileCapacity);
     sa.histogram = &c->dCounters->tileHist[p][0];
@@ -285,7 +286,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp)
   mark(c, VKGS_K_BLEND + 1);
   c->evRecorded = c->profiling;
 
-  CU_TRY(c, cudaMemcpyAsync(c->hCounters, c->dCounters, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->hCounters, c->dCounters, 32, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaGetLastError());
   c->lastFp    = fp;
   c->haveFrame = true;
@@ -583,10 +584,11 @@ int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
       return rc;
     fillStats(c, out);
     const uint64_t v = std::min<uint64_t>(out->visible_count, out->sorted_ids_capacity);
+    const uint32_t sel = c->hCounters->sortSrc[3] & 1u;
     if(out->sorted_ids && v)
-      CU_TRY(c, cudaMemcpy(out->sorted_ids, c->dIds[0], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU_TRY(c, cudaMemcpy(out->sorted_ids, c->dIds[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if(out->sorted_keys && v)
-      CU_TRY(c, cudaMemcpy(out->sorted_keys, c->dKeys[0], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU_TRY(c, cudaMemcpy(out->sorted_keys, c->dKeys[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return VKGS_OK;
   }
   return fail(c, VKGS_ERR_OVERFLOW, "tile lists still overflow after regrowing");
@@ -690,10 +692,8 @@ int vkgs_sort_pairs(vkgs_ctx* c, const uint32_t* keys, const uint32_t* values, u
     for(int p = 0; p < 4; p++)
     {
       SortPassArgs sa{};
-      sa.keysIn    = dk[p & 1];
-      sa.valsIn    = dv[p & 1];
-      sa.keysOut   = dk[(p + 1) & 1];
-      sa.valsOut   = dv[(p + 1) & 1];
+      sa.keys[0] = dk[p & 1], sa.keys[1] = dk[(p + 1) & 1];
+      sa.vals[0] = dv[p & 1], sa.vals[1] = dv[(p + 1) & 1];
       sa.countPtr  = &dCtl->count;
       sa.maxCount  = static_cast<uint32_t>(n);
       sa.histogram = &dCtl->hist[p][0];

@@ -10,6 +10,20 @@ namespace vkgs {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+// Optional in-kernel timeline (tools/kbench.cu defines VKGS_TIMELINE): thread 0 of a block stamps
+// the SM clock at phase boundaries. Compiles to nothing in the product build.
+#ifdef VKGS_TIMELINE
+static __device__ long long* g_vkgsTimeline = nullptr;  // [block][16] (single-TU harness only)
+#define VKGS_TL(block, k)                                                                                                      \
+  do                                                                                                                           \
+  {                                                                                                                            \
+    if(threadIdx.x == 0 && g_vkgsTimeline)                                                                                     \
+      g_vkgsTimeline[(block)*16 + (k)] = clock64();                                                                            \
+  } while(0)
+#else
+#define VKGS_TL(block, k) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + cp.async.bulk (global -> shared::cta). Size and both addresses must be multiples of 16.
 
@@ -83,23 +97,100 @@ __device__ __forceinline__ uint64_t lb_load(const uint64_t* p)
   return v;
 }
 
-// Walk predecessors tile-1, tile-2, ... of a single scalar chain until an inclusive prefix is
-// found. `stride` is the distance in words between consecutive tiles of the same chain.
+// Per-thread look-back over one chain (tile-1, tile-2, ...; `stride` words between consecutive
+// tiles of the chain) until an inclusive prefix is found. Predecessors are fetched BATCH at a time
+// with independent loads, so the serial dependency is one L2 round trip per BATCH tiles instead of
+// one per tile (all resident tiles publish their aggregates at about the same time, so the walk
+// can be hundreds of tiles long in the first wave).
+template <int BATCH>
 __device__ __forceinline__ uint32_t lb_lookback(const uint64_t* status, int64_t tile, int64_t stride, uint32_t epoch)
 {
   uint32_t exclusive = 0;
-  for(int64_t p = tile - 1; p >= 0; --p)
+  int64_t  p         = tile - 1;
+  while(p >= 0)
   {
-    uint64_t w;
-    do
+    uint64_t w[BATCH];
+#pragma unroll
+    for(int b = 0; b < BATCH; b++)
+      w[b] = (p - b >= 0) ? lb_load(status + (p - b) * stride) : 0ull;
+#pragma unroll
+    for(int b = 0; b < BATCH; b++)
     {
-      w = lb_load(status + p * stride);
-    } while(static_cast<uint32_t>(w >> 34) != epoch);
-    exclusive += static_cast<uint32_t>(w);
-    if(((w >> 32) & 3ull) == LB_INCLUSIVE)
+      if(p - b < 0)
+        return exclusive;
+      while(static_cast<uint32_t>(w[b] >> 34) != epoch)
+        w[b] = lb_load(status + (p - b) * stride);
+      exclusive += static_cast<uint32_t>(w[b]);
+      if(((w[b] >> 32) & 3ull) == LB_INCLUSIVE)
+        return exclusive;
+    }
+    p -= BATCH;
+  }
+  return exclusive;
+}
+
+// Warp-cooperative look-back over a scalar chain (stride 1): each step inspects a window of
+// 32*W predecessors at once (W independent loads per lane). Must be called by all 32 lanes of one
+// warp; every lane gets the result.
+template <int W = 1>
+__device__ __forceinline__ uint32_t lb_lookback_warp(const uint64_t* status, int64_t tile, uint32_t epoch)
+{
+  const unsigned lane      = threadIdx.x & 31u;
+  uint32_t       exclusive = 0;
+  for(int64_t base = tile - 1; base >= 0; base -= 32 * W)
+  {
+    uint64_t w[W];
+#pragma unroll
+    for(int k = 0; k < W; k++)
+    {
+      const int64_t p = base - 32 * k - lane;
+      w[k]            = p >= 0 ? lb_load(status + p) : 0ull;
+    }
+    bool found = false;
+#pragma unroll
+    for(int k = 0; k < W; k++)
+    {
+      const int64_t p = base - 32 * k - lane;
+      if(p >= 0)
+        while(static_cast<uint32_t>(w[k] >> 34) != epoch)
+          w[k] = lb_load(status + p);
+      const bool     inclusive = p >= 0 && ((w[k] >> 32) & 3ull) == LB_INCLUSIVE;
+      const unsigned incMask   = __ballot_sync(FULL_MASK, inclusive);
+      // lanes up to and including the nearest inclusive predecessor contribute
+      const unsigned upto = incMask ? (__ffs(incMask) - 1) : 31u;
+      uint32_t       v    = (p >= 0 && lane <= upto) ? static_cast<uint32_t>(w[k]) : 0u;
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+      exclusive += v;
+      if(incMask)
+      {
+        found = true;
+        break;
+      }
+    }
+    if(found)
       break;
   }
   return exclusive;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lanes of `active` holding the same BITS-bit digit as the caller. MATCH.ANY is serviced once per
+// DISTINCT value in the warp (about 800 cycles for 32 random 8-bit digits, measured on B200), so
+// the peer mask is built from BITS ballots instead: cost independent of the digit distribution.
+template <int BITS>
+__device__ __forceinline__ unsigned match_digit(unsigned active, uint32_t digit)
+{
+  unsigned peers = active;
+#pragma unroll
+  for(int b = 0; b < BITS; b++)
+  {
+    const bool     bit = (digit >> b) & 1u;
+    const unsigned v   = __ballot_sync(active, bit);
+    peers &= bit ? v : ~v;
+  }
+  return peers;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -10,7 +10,8 @@
 //   a stable 2-pass (16-bit) radix sort on the tile id (k_radix_sort.cu) groups them per tile and
 //                keeps the depth order inside every tile;
 //   k_tile_ranges finds each tile's [begin,end) in the sorted list.
-// The digit histograms for the tile sort are accumulated by k_bin_emit.
+// The digit histograms for the tile sort are accumulated by k_bin_emit while it drains its staging
+// buffer.
 #include "device_common.cuh"
 #include "kernels.hpp"
 
@@ -18,100 +19,211 @@ namespace vkgs {
 
 namespace {
 
-constexpr int NWARPS = BIN_THREADS / 32;
+constexpr int BIN_WARPS    = BIN_THREADS / 32;
+constexpr int BIN_ITEMS = 4;                        // depth ranks per thread (one 16-byte id load)
+constexpr int BIN_PART  = BIN_THREADS * BIN_ITEMS;  // ranks per partition
+constexpr int BIN_CHUNK = 2048;                     // pairs staged in shared memory per round
 
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant__ BinArgs a)
 {
-  __shared__ uint32_t s_hist[2][256];
-  __shared__ uint32_t s_scan[NWARPS + 1];
+  __shared__ uint32_t s_keys[BIN_CHUNK];
+  __shared__ uint32_t s_vals[BIN_CHUNK];
+  __shared__ uint32_t s_whist[BIN_WARPS][2][256];  // warp-private digit tables of the tile ids
+  __shared__ uint32_t s_scan[BIN_WARPS + 1];
   __shared__ uint32_t s_part, s_base;
-  const unsigned      tid = threadIdx.x;
+  const unsigned      tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
   const uint32_t count = a.counters->visible;
-  const uint32_t parts = (count + BIN_THREADS - 1) / BIN_THREADS;
+  const uint32_t parts = (count + BIN_PART - 1) / BIN_PART;
+  const uint32_t* __restrict__ sortedIds = a.sortedIds[a.sortedSel ? *a.sortedSel : 0u];
   if(tid == 0)
     s_part = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u);
-  s_hist[0][tid] = 0u;
-  s_hist[1][tid] = 0u;
+  for(int i = tid; i < BIN_WARPS * 2 * 256; i += BIN_THREADS)
+    (&s_whist[0][0][0])[i] = 0u;
   __syncthreads();
   const uint32_t part = s_part;
   if(part >= parts)
     return;
+  VKGS_TL(part, 0);
 
-  const uint32_t r  = part * BIN_THREADS + tid;  // depth rank
-  uint32_t       id = 0, x0 = 1, x1 = 0, y0 = 1, y1 = 0;
-  if(r < count)
+  // thread t owns ranks r0 .. r0+3 (blocked: emission order == rank order)
+  const uint32_t r0 = part * BIN_PART + tid * BIN_ITEMS;
+  uint32_t       id[BIN_ITEMS];
+  if(r0 + BIN_ITEMS <= count)
   {
-    id             = a.sortedIds[r];
-    const uint2 bb = *reinterpret_cast<const uint2*>(a.records + static_cast<uint64_t>(id) * RECORD_WORDS + 10);
-    if((bb.y & 0xffffu) >= (bb.x & 0xffffu))
-    {
-      x0 = (bb.x & 0xffffu) / TILE_W, y0 = (bb.x >> 16) / TILE_H;
-      x1 = (bb.y & 0xffffu) / TILE_W, y1 = (bb.y >> 16) / TILE_H;
-    }
+    const uint4 v = *reinterpret_cast<const uint4*>(sortedIds + r0);
+    id[0] = v.x, id[1] = v.y, id[2] = v.z, id[3] = v.w;
   }
-  const uint32_t nTiles = (x1 >= x0 && y1 >= y0) ? (x1 - x0 + 1) * (y1 - y0 + 1) : 0u;
-
-  uint32_t       total;
-  const uint32_t local = block_exclusive_scan<NWARPS>(nTiles, s_scan, total);
-
-  if(tid == 0)
+  else
   {
-    uint64_t* st = a.status + part;
+#pragma unroll
+    for(int i = 0; i < BIN_ITEMS; i++)
+      id[i] = (r0 + i < count) ? sortedIds[r0 + i] : 0xffffffffu;
+  }
+  // four independent 8-byte gathers of the pixel bounding boxes
+  uint2 bb[BIN_ITEMS];
+#pragma unroll
+  for(int i = 0; i < BIN_ITEMS; i++)
+    bb[i] = (id[i] != 0xffffffffu) ? __ldg(reinterpret_cast<const uint2*>(a.records + static_cast<uint64_t>(id[i]) * RECORD_WORDS + 10))
+                                   : make_uint2(1u, 0u);
+  uint32_t x0[BIN_ITEMS], nx[BIN_ITEMS], y0[BIN_ITEMS], n[BIN_ITEMS], mine = 0;
+#pragma unroll
+  for(int i = 0; i < BIN_ITEMS; i++)
+  {
+    const uint32_t px0 = bb[i].x & 0xffffu, py0 = bb[i].x >> 16, px1 = bb[i].y & 0xffffu, py1 = bb[i].y >> 16;
+    const bool     ok  = px1 >= px0 && py1 >= py0;
+    x0[i]              = px0 / TILE_W;
+    y0[i]              = py0 / TILE_H;
+    nx[i]              = ok ? (px1 / TILE_W - x0[i] + 1) : 0u;
+    n[i]               = ok ? nx[i] * (py1 / TILE_H - y0[i] + 1) : 0u;
+    mine += n[i];
+  }
+
+  VKGS_TL(part, 1);
+  uint32_t       total;
+  const uint32_t local = block_exclusive_scan<BIN_WARPS>(mine, s_scan, total);
+  VKGS_TL(part, 2);
+
+  if(tid < 32)
+  {
+    uint64_t* st   = a.status + part;
     uint32_t  excl = 0;
     if(part == 0)
-      lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, total));
+    {
+      if(tid == 0)
+        lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, total));
+    }
     else
     {
-      lb_store(st, lb_pack(a.epoch, LB_AGGREGATE, total));
-      excl = lb_lookback(a.status, part, 1, a.epoch);
-      lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, excl + total));
+      if(tid == 0)
+        lb_store(st, lb_pack(a.epoch, LB_AGGREGATE, total));
+      if(a.debugFlags & 32u)
+      {
+        if(tid == 0)
+          excl = atomicAdd(&a.counters->tilePairs, total);
+        excl = __shfl_sync(FULL_MASK, excl, 0);
+      }
+      else
+      excl = lb_lookback_warp<4>(a.status, part, a.epoch);
+      if(tid == 0)
+        lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, excl + total));
     }
-    s_base = excl;
-    if(part == parts - 1)
+    if(tid == 0)
     {
-      const uint32_t d              = excl + total;
-      a.counters->tilePairs         = d;
-      a.counters->tilePairsClamped  = d < a.capacity ? d : a.capacity;
-      if(d > a.capacity)
-        a.counters->overflow = 1u;
+      s_base = excl;
+      if(part == parts - 1)
+      {
+        const uint32_t d             = excl + total;
+        a.counters->tilePairs        = d;
+        a.counters->tilePairsClamped = d < a.capacity ? d : a.capacity;
+        if(d > a.capacity)
+          a.counters->overflow = 1u;
+      }
     }
   }
   __syncthreads();
+  VKGS_TL(part, 3);
+  const uint32_t blockBase = s_base;
 
-  uint32_t off = s_base + local;
-  for(uint32_t ty = y0; ty <= y1 && nTiles; ty++)
-    for(uint32_t tx = x0; tx <= x1; tx++)
+  // Emit through shared memory so global writes are fully coalesced: every round stages up to
+  // BIN_CHUNK pairs of the block's contiguous output range, then drains them row by row; the drain
+  // also counts the two 8-bit digits of each tile id into warp-private tables (ballot multi-split).
+  for(uint32_t w = 0; w < total && !(a.debugFlags & 16u); w += BIN_CHUNK)
+  {
+    const uint32_t lim = min(total, w + BIN_CHUNK);
+    uint32_t       off = local;
+#pragma unroll
+    for(int i = 0; i < BIN_ITEMS; i++)
     {
-      const uint32_t key = ty * a.tilesX + tx;
-      if(off < a.capacity)
+      const uint32_t lo = max(off, w), hi = min(off + n[i], lim);
+      if(lo < hi)
       {
-        a.tileKeys[off] = key;
-        a.tileVals[off] = id;
-        atomicAdd(&s_hist[0][key & 0xffu], 1u);
-        atomicAdd(&s_hist[1][(key >> 8) & 0xffu], 1u);
+        const uint32_t j  = lo - off;
+        uint32_t       ty = j / nx[i];
+        uint32_t       tx = j - ty * nx[i];
+        for(uint32_t p = lo; p < hi; p++)
+        {
+          s_keys[p - w] = (y0[i] + ty) * a.tilesX + x0[i] + tx;
+          s_vals[p - w] = id[i];
+          if(++tx == nx[i])
+            tx = 0, ty++;
+        }
       }
-      off++;
+      off += n[i];
     }
-  __syncthreads();
+    __syncthreads();
+    const uint32_t cnt = lim - w;
+    for(uint32_t qb = warp * 32; qb < cnt; qb += BIN_THREADS)
+    {
+      const uint32_t q      = qb + lane;
+      const uint64_t g      = static_cast<uint64_t>(blockBase) + w + q;
+      const bool     ok     = q < cnt && g < a.capacity;
+      const unsigned active = __ballot_sync(FULL_MASK, ok);
+      if(ok)
+      {
+        const uint32_t key = s_keys[q];
+        a.tileKeys[g]      = key;
+        a.tileVals[g]      = s_vals[q];
+        if(a.debugFlags & 64u)
+          continue;
+        const unsigned p0  = match_digit<8>(active, key & 0xffu);
+        if(lane == static_cast<unsigned>(__ffs(p0) - 1))
+          s_whist[warp][0][key & 0xffu] += __popc(p0);
+        const unsigned p1 = match_digit<8>(active, (key >> 8) & 0xffu);
+        if(lane == static_cast<unsigned>(__ffs(p1) - 1))
+          s_whist[warp][1][(key >> 8) & 0xffu] += __popc(p1);
+      }
+    }
+    __syncthreads();
+  }
+  VKGS_TL(part, 4);
   for(int i = tid; i < 2 * 256; i += BIN_THREADS)
   {
-    const uint32_t v = (&s_hist[0][0])[i];
+    uint32_t v = 0;
+#pragma unroll
+    for(int wv = 0; wv < BIN_WARPS; wv++)
+      v += (&s_whist[wv][0][0])[i];
     if(v)
       atomicAdd(&a.counters->tileHist[0][0] + i, v);
   }
 }
 
+// [begin,end) of every tile in the tile-sorted pair list: one 16-byte load of 4 consecutive keys per
+// thread plus the key in front of them; a range boundary sits wherever two neighbours differ.
 __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ tileKeys, const FrameCounters* counters, uint2* ranges)
 {
-  const uint32_t count = counters->tilePairsClamped;
-  for(uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x; i < count; i += static_cast<uint64_t>(gridDim.x) * 256)
+  const uint32_t count  = counters->tilePairsClamped;
+  const uint32_t groups = (count + 3) / 4;
+  for(uint32_t g = blockIdx.x * 256 + threadIdx.x; g < groups; g += gridDim.x * 256)
   {
-    const uint32_t k = tileKeys[i];
-    if(i == 0 || tileKeys[i - 1] != k)
-      ranges[k].x = static_cast<uint32_t>(i);
-    if(i + 1 == count || tileKeys[i + 1] != k)
-      ranges[k].y = static_cast<uint32_t>(i + 1);
+    const uint32_t i0 = g * 4;
+    uint32_t       k[4];
+    if(i0 + 4 <= count)
+    {
+      const uint4 v = *reinterpret_cast<const uint4*>(tileKeys + i0);
+      k[0] = v.x, k[1] = v.y, k[2] = v.z, k[3] = v.w;
+    }
+    else
+    {
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+        k[j] = (i0 + j < count) ? tileKeys[i0 + j] : 0xffffffffu;
+    }
+    uint32_t prev = i0 ? tileKeys[i0 - 1] : 0xffffffffu;
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+    {
+      const uint32_t i = i0 + j;
+      if(i < count && k[j] != prev)
+      {
+        ranges[k[j]].x = i;
+        if(i)
+          ranges[prev].y = i;
+      }
+      if(i + 1 == count)
+        ranges[k[j]].y = count;
+      prev = k[j];
+    }
   }
 }
 
@@ -119,7 +231,7 @@ __global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict_
 
 void launchBinEmit(const BinArgs& args, cudaStream_t stream)
 {
-  const uint32_t parts = (args.maxCount + BIN_THREADS - 1) / BIN_THREADS;
+  const uint32_t parts = (args.maxCount + BIN_PART - 1) / BIN_PART;
   if(parts == 0)
     return;
   k_bin_emit<<<parts, BIN_THREADS, 0, stream>>>(args);
@@ -127,8 +239,8 @@ void launchBinEmit(const BinArgs& args, cudaStream_t stream)
 
 void launchTileRanges(const uint32_t* tileKeys, const FrameCounters* counters, uint32_t capacity, uint2* ranges, cudaStream_t stream)
 {
-  uint32_t blocks = (capacity + 256 * 8 - 1) / (256 * 8);
-  blocks          = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
+  uint32_t blocks = (capacity + 256 * 16 - 1) / (256 * 16);
+  blocks          = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
   k_tile_ranges<<<blocks, 256, 0, stream>>>(tileKeys, counters, ranges);
 }
 

@@ -8,9 +8,10 @@
 //   colour target cleared to 0 (src/gaussian_splatting.cpp:582), fp32 RGBA here.
 // One CTA per 16x16 tile, one thread per pixel, a warp covers an 8x4 pixel block. The tile's
 // depth-ordered splat list is consumed in batches of 256: each thread gathers one 48-byte record
-// into shared memory, then every warp ballots which of the batch's splats overlap its 8x4 block
-// (bounding-box test) and evaluates only those, in list order — per-pixel blend order is exactly
-// the sorted order, like the ROP.
+// (prefetched into registers one batch ahead), computes which of the 8 warp blocks the splat's
+// pixel bounding box touches, and parks both in shared memory; every warp then ballots the batch
+// 32 entries at a time and evaluates only the splats that touch its block, in list order — the
+// per-pixel blend order is exactly the sorted order, like the ROP.
 //
 // Exactness: fragPos / A are evaluated with explicit fp32 mul/fma in the oracle's operation order,
 // so the `A > 8` discard is bit-exact. opacity uses the SFU ex2 for speed; whenever that value is
@@ -24,7 +25,7 @@ namespace vkgs {
 namespace {
 
 // Same operation sequence as orc_expf (oracle/vkgs_oracle.c): Cody-Waite + Cephes polynomial.
-__device__ __forceinline__ float expfExact(float x)
+__device__ __noinline__ float expfExact(float x)
 {
   x              = fminf(fmaxf(x, -87.0f), 88.0f);
   const float kf = rintf(__fmul_rn(x, 1.44269504088896341f));
@@ -50,92 +51,142 @@ __device__ __forceinline__ float ex2Approx(float x)
   return y;
 }
 
+// shared-memory accesses through explicit 32-bit addresses (keeps address arithmetic out of the
+// inner loop: one IMAD per splat)
+__device__ __forceinline__ float4 ldsV4(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 ldsV2(uint32_t addr)
+{
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldsU32(uint32_t addr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void stsV4(uint32_t addr, float4 v)
+{
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr uint32_t REC_BYTES = RECORD_WORDS * 4;  // 48: cx cy w1x w1y | w2x w2y r g | b a mask -
+
 template <bool FTB>
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
 {
-  __shared__ float4 s_a[BLEND_THREADS];  // cx, cy, w1x, w1y
-  __shared__ float4 s_b[BLEND_THREADS];  // w2x, w2y, r, g
-  __shared__ float4 s_c[BLEND_THREADS];  // b, a, bbox0, bbox1
+  __shared__ __align__(16) float s_rec[BLEND_THREADS * RECORD_WORDS];
+  const uint32_t sbase = smem_u32(s_rec);
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t tile = blockIdx.x;
   const uint32_t tx = tile % a.tilesX, ty = tile / a.tilesX;
-  const uint32_t wx0 = tx * TILE_W + (warp & 1u) * 8u, wy0 = ty * TILE_H + (warp >> 1) * 4u;
-  const uint32_t px = wx0 + (lane & 7u), py = wy0 + (lane >> 3);
+  const uint32_t tileX0 = tx * TILE_W, tileY0 = ty * TILE_H;
+  const uint32_t px = tileX0 + (warp & 1u) * 8u + (lane & 7u), py = tileY0 + (warp >> 1) * 4u + (lane >> 3);
   const bool     inside = px < a.width && py < a.height;
   const float    fx = static_cast<float>(px) + 0.5f, fy = static_cast<float>(py) + 0.5f;
 
   const uint2 range = a.ranges[tile];
-  float       c0 = 0.f, c1 = 0.f, c2 = 0.f, alpha = 0.f;
+  float       c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  float       acc = FTB ? 1.0f : 0.0f;  // FTB: transmittance T = 1 - A_dst;  BTF: sum of alphas
   bool        done = !inside;
   const float THRESHOLD = 1.0f / 255.0f;
-  const float GUARD     = THRESHOLD * 4e-6f;
+  const float THR_HI    = THRESHOLD * (1.0f + 4e-6f);
+  const float THR_LO    = THRESHOLD * (1.0f - 4e-6f);
+  const float eps       = a.transmittanceEpsilon;
+
+  // gather of this thread's entry of a batch: record + warp-block mask
+  float4 r0, r1, r2;
+  auto   fetch = [&](uint32_t base) {
+    if(base + tid < range.y)
+    {
+      const uint32_t id  = a.tileVals[base + tid];
+      const float4*  rec = reinterpret_cast<const float4*>(a.records + static_cast<uint64_t>(id) * RECORD_WORDS);
+      r0                 = __ldg(rec + 0);
+      r1                 = __ldg(rec + 1);
+      r2                 = __ldg(rec + 2);
+    }
+  };
+  fetch(range.x);
 
   for(uint32_t base = range.x; base < range.y; base += BLEND_THREADS)
   {
     const uint32_t n = min(static_cast<uint32_t>(BLEND_THREADS), range.y - base);
-    // all pixels of the tile saturated (front-to-back only) -> stop reading the list
+    // all pixels of the tile saturated (front-to-back only) -> stop reading the list.
+    // (the barrier also protects the shared batch against the previous round's readers)
     const int active = __syncthreads_count(!done);
     if(FTB && active == 0)
       break;
     if(tid < n)
     {
-      const uint32_t id  = a.tileVals[base + tid];
-      const float4*  rec = reinterpret_cast<const float4*>(a.records + static_cast<uint64_t>(id) * RECORD_WORDS);
-      s_a[tid]           = __ldg(rec + 0);
-      s_b[tid]           = __ldg(rec + 1);
-      s_c[tid]           = __ldg(rec + 2);
+      // which of the 8 warp blocks (2 columns x 4 rows of 8x4 pixels) does the pixel bbox touch?
+      const uint32_t bb0 = __float_as_uint(r2.z), bb1 = __float_as_uint(r2.w);
+      const uint32_t x0 = bb0 & 0xffffu, y0 = bb0 >> 16, x1 = bb1 & 0xffffu, y1 = bb1 >> 16;
+      const uint32_t colL = (x0 <= tileX0 + 7u && x1 >= tileX0) ? 0x55u : 0u;       // warps 0,2,4,6
+      const uint32_t colR = (x0 <= tileX0 + 15u && x1 >= tileX0 + 8u) ? 0xaau : 0u;  // warps 1,3,5,7
+      uint32_t       rows = 0;
+#pragma unroll
+      for(uint32_t r = 0; r < 4; r++)
+        rows |= (y0 <= tileY0 + 4u * r + 3u && y1 >= tileY0 + 4u * r) ? (3u << (2u * r)) : 0u;
+      r2.z = __uint_as_float((colL | colR) & rows);
+      const uint32_t dst = sbase + tid * REC_BYTES;
+      stsV4(dst, r0);
+      stsV4(dst + 16, r1);
+      stsV4(dst + 32, r2);
     }
     __syncthreads();
+    fetch(base + BLEND_THREADS);  // prefetch the next batch while this one is blended
     if(__all_sync(FULL_MASK, done))
       continue;
 
     for(uint32_t chunk = 0; chunk < n; chunk += 32)
     {
       const uint32_t j   = chunk + lane;
-      bool           hit = false;
-      if(j < n)
-      {
-        const uint32_t bb0 = __float_as_uint(s_c[j].z), bb1 = __float_as_uint(s_c[j].w);
-        hit = (bb0 & 0xffffu) <= wx0 + 7u && (bb1 & 0xffffu) >= wx0 && (bb0 >> 16) <= wy0 + 3u && (bb1 >> 16) >= wy0;
-      }
-      unsigned m = __ballot_sync(FULL_MASK, hit);
+      const bool     hit = j < n && ((ldsU32(sbase + j * REC_BYTES + 40) >> warp) & 1u);
+      unsigned       m   = __ballot_sync(FULL_MASK, hit);
+      const uint32_t chunkAddr = sbase + chunk * REC_BYTES;
       while(m)
       {
-        const uint32_t jj = chunk + __ffs(m) - 1;
+        const uint32_t addr = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
         m &= m - 1;
-        if(done)
-          continue;
-        const float4 ra = s_a[jj];
+        const float4 ra = ldsV4(addr);
+        const float4 rb = ldsV4(addr + 16);
         const float  dx = __fsub_rn(fx, ra.x), dy = __fsub_rn(fy, ra.y);
-        const float4 rb = s_b[jj];
         const float  fpx = __fmaf_rn(dy, ra.w, __fmul_rn(dx, ra.z));
         const float  fpy = __fmaf_rn(dy, rb.y, __fmul_rn(dx, rb.x));
         const float  A   = __fmaf_rn(fpy, fpy, __fmul_rn(fpx, fpx));
-        if(A > 8.0f)
+        if(A > 8.0f || done)
           continue;
-        const float4 rc = s_c[jj];
+        const float2 rc = ldsV2(addr + 32);
         float        op;
         if(a.disableOpacityGaussian)
           op = 1.0f;
         else
         {
           op = ex2Approx(A * -0.72134752044448170368f) * rc.y;  // exp(-A/2) = 2^(-A/2 * log2 e)
-          if(fabsf(op - THRESHOLD) <= GUARD)
-            op = __fmul_rn(expfExact(__fmul_rn(-0.5f, A)), rc.y);
+          if(op <= THR_HI)
+          {
+            if(op < THR_LO)
+              continue;
+            op = __fmul_rn(expfExact(__fmul_rn(-0.5f, A)), rc.y);  // within the guard band: decide exactly
+            if(op <= THRESHOLD)
+              continue;
+          }
         }
-        if(op <= THRESHOLD)
-          continue;
         if(FTB)
         {
-          const float t = 1.0f - alpha;
-          const float w = op * t;
+          const float w = op * acc;
           c0            = fmaf(rb.z, w, c0);
           c1            = fmaf(rb.w, w, c1);
           c2            = fmaf(rc.x, w, c2);
-          alpha += w;
-          if(1.0f - alpha < a.transmittanceEpsilon)
-            done = true;
+          acc -= w;
+          done = acc < eps;
         }
         else
         {
@@ -143,7 +194,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
           c0            = fmaf(rb.z, op, c0 * t);
           c1            = fmaf(rb.w, op, c1 * t);
           c2            = fmaf(rc.x, op, c2 * t);
-          alpha += op;
+          acc += op;
         }
       }
       if(FTB && __all_sync(FULL_MASK, done))
@@ -151,7 +202,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
     }
   }
   if(inside)
-    a.image[static_cast<uint64_t>(py) * a.width + px] = make_float4(c0, c1, c2, alpha);
+    a.image[static_cast<uint64_t>(py) * a.width + px] = make_float4(c0, c1, c2, FTB ? 1.0f - acc : acc);
 }
 
 }  // namespace

@@ -12,7 +12,7 @@
 // a compact 48-byte record per splat. The append is deterministic: a decoupled look-back prefix
 // over tiles replaces the reference's global atomic, so (key,id) pairs come out in ascending splat
 // id — one of the orders the reference's atomic can legally produce. The four 8-bit digit
-// histograms of the radix sort are accumulated here as well (no separate histogram pass).
+// histograms the radix sort needs are accumulated here as well (no separate histogram pass).
 //
 // Arithmetic: this file is compiled with -fmad=false and evaluates every expression in the
 // operation order documented in oracle/vkgs_oracle.c, with IEEE division and square root, so keys
@@ -36,8 +36,9 @@ struct PreSmem
   float    rgba[PRE_TILE * 4];  //  4096 B
   float    center[PRE_TILE * 3];//  3072 B
   float    scale[PRE_TILE * 3]; //  3072 B (size culling only)
-  uint64_t mbar;
-  uint32_t hist[4][256];
+  uint64_t mbarA;  // centers (+ scales): all the dist/cull stage needs
+  uint64_t mbarB;  // cov6, rgba, SH: the per-splat projection stage
+  uint32_t hist[4][256];  // digit histograms of this tile's keys (all four sort passes)
   uint32_t warpScan[NWARPS + 1];
   uint32_t tile;
   uint32_t basePrefix;
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   if(tid == 0)
   {
     sm.tile = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u);
-    mbar_init(&sm.mbar, 1);
+    mbar_init(&sm.mbarA, 1);
+    mbar_init(&sm.mbarB, 1);
     mbar_fence_init();
   }
   for(int i = tid; i < 4 * 256; i += PRE_TILE)
@@ -142,21 +144,20 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   const bool     sizeCul = a.opt.size_culling_mode == VKGS_SIZE_CULLING_ENABLED;
   if(tid == 0)
   {
-    uint32_t bytes = PRE_TILE * (3 + 6) * 4 + PRE_TILE * 4 * rgbaEl;
-    if(hasSh)
-      bytes += PRE_TILE * 45 * shElem;
+    // stage A: what the cull needs; stage B: everything else. Two barriers so the cull (and the
+    // early publication of this tile's visible count) does not wait for the 46 KB of SH.
+    mbar_arrive_expect_tx(&sm.mbarA, PRE_TILE * 3 * 4 * (sizeCul ? 2u : 1u));
+    bulk_copy_g2s(sm.center, a.set.centers + first * 3, PRE_TILE * 3 * 4, &sm.mbarA);
     if(sizeCul)
-      bytes += PRE_TILE * 3 * 4;
-    mbar_arrive_expect_tx(&sm.mbar, bytes);
-    bulk_copy_g2s(sm.center, a.set.centers + first * 3, PRE_TILE * 3 * 4, &sm.mbar);
-    bulk_copy_g2s(sm.cov, a.set.cov6 + first * 6, PRE_TILE * 6 * 4, &sm.mbar);
-    bulk_copy_g2s(sm.rgba, static_cast<const unsigned char*>(a.set.rgba) + first * 4 * rgbaEl, PRE_TILE * 4 * rgbaEl, &sm.mbar);
+      bulk_copy_g2s(sm.scale, a.set.scales + first * 3, PRE_TILE * 3 * 4, &sm.mbarA);
+    mbar_arrive_expect_tx(&sm.mbarB, PRE_TILE * 6 * 4 + PRE_TILE * 4 * rgbaEl + (hasSh ? PRE_TILE * 45 * shElem : 0u));
+    bulk_copy_g2s(sm.cov, a.set.cov6 + first * 6, PRE_TILE * 6 * 4, &sm.mbarB);
+    bulk_copy_g2s(sm.rgba, static_cast<const unsigned char*>(a.set.rgba) + first * 4 * rgbaEl, PRE_TILE * 4 * rgbaEl, &sm.mbarB);
     if(hasSh)
-      bulk_copy_g2s(sm.sh, static_cast<const unsigned char*>(a.set.sh) + first * 45 * shElem, PRE_TILE * 45 * shElem, &sm.mbar);
-    if(sizeCul)
-      bulk_copy_g2s(sm.scale, a.set.scales + first * 3, PRE_TILE * 3 * 4, &sm.mbar);
+      bulk_copy_g2s(sm.sh, static_cast<const unsigned char*>(a.set.sh) + first * 45 * shElem, PRE_TILE * 45 * shElem, &sm.mbarB);
   }
-  mbar_wait(&sm.mbar, 0);
+  mbar_wait(&sm.mbarA, 0);
+  const uint32_t ablate = a.opt._reserved[5];
 
   const uint64_t id    = first + tid;
   const bool     inSet = id < a.set.count;
@@ -202,7 +203,35 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     key = a.opt.front_to_back ? encodeMinMaxFp32(depth) : encodeMinMaxFp32(-depth);
   }
 
+  // ---- deterministic append, part 1: publish this tile's visible count as early as possible ----
+  // (decoupled look-back: successors only need the aggregate; publishing it before the heavy
+  // per-splat stage means nobody ever waits on this tile's projection / SH work)
+  const unsigned ballot   = __ballot_sync(FULL_MASK, keep);
+  const uint32_t warpRank = __popc(ballot & ((1u << lane) - 1u));
+  if(lane == 0)
+    sm.warpScan[warp] = __popc(ballot);
+  if(keep)
+  {
+    atomicAdd(&sm.hist[0][key & 0xffu], 1u);
+    atomicAdd(&sm.hist[1][(key >> 8) & 0xffu], 1u);
+    atomicAdd(&sm.hist[2][(key >> 16) & 0xffu], 1u);
+    atomicAdd(&sm.hist[3][key >> 24], 1u);
+  }
+  __syncthreads();
+  uint32_t tileTotal = 0;
+  if(warp == 0)
+  {
+    const uint32_t cnt = lane < NWARPS ? sm.warpScan[lane] : 0u;
+    const uint32_t inc = warp_inclusive_scan(cnt, lane);
+    if(lane < NWARPS)
+      sm.warpScan[lane] = inc - cnt;
+    tileTotal = __shfl_sync(FULL_MASK, inc, NWARPS - 1);
+    if(lane == 0 && !(ablate & 1u))
+      lb_store(a.status + tile, lb_pack(a.epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, tileTotal));
+  }
+
   // ---- K5: per-splat projection + colour (threedgs_raster.mesh.slang:161-289) -------------------
+  mbar_wait(&sm.mbarB, 0);
   if(keep)
   {
     float4   col   = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
@@ -224,7 +253,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
       {
         if(a.opt.show_sh_only)
           col.x = col.y = col.z = 0.5f;
-        if(hasSh)
+        if(hasSh && !(ablate & 8u))
         {
           float       d[3] = {c[0] - a.camModel[0], c[1] - a.camModel[1], c[2] - a.camModel[2]};
           const float dinv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -338,49 +367,36 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     if(!valid)
       bb0 = 1u, bb1 = 0u;
     float4* rec = reinterpret_cast<float4*>(a.records + id * RECORD_WORDS);
+    if(!(ablate & 4u))
+    {
     rec[0]      = make_float4(cx, cy, w1x, w1y);
     rec[1]      = make_float4(w2x, w2y, col.x, col.y);
     rec[2]      = make_float4(col.z, col.w, __uint_as_float(bb0), __uint_as_float(bb1));
+    }
   }
 
-  // ---- deterministic append: block rank + decoupled look-back over tiles -----------------------
-  const unsigned ballot   = __ballot_sync(FULL_MASK, keep);
-  const uint32_t warpRank = __popc(ballot & ((1u << lane) - 1u));
-  if(lane == 0)
-    sm.warpScan[warp] = __popc(ballot);
-  if(keep)
-  {
-    atomicAdd(&sm.hist[0][key & 0xffu], 1u);
-    atomicAdd(&sm.hist[1][(key >> 8) & 0xffu], 1u);
-    atomicAdd(&sm.hist[2][(key >> 16) & 0xffu], 1u);
-    atomicAdd(&sm.hist[3][key >> 24], 1u);
-  }
-  __syncthreads();
+
+  // ---- deterministic append, part 2: resolve the exclusive prefix (predecessors published long ago)
   if(warp == 0)
   {
-    const uint32_t cnt = lane < NWARPS ? sm.warpScan[lane] : 0u;
-    const uint32_t inc = warp_inclusive_scan(cnt, lane);
-    if(lane < NWARPS)
-      sm.warpScan[lane] = inc - cnt;
-    const uint32_t total = __shfl_sync(FULL_MASK, inc, NWARPS - 1);
+    uint32_t excl = 0;
+    if(ablate & 1u)
+    {
+      if(lane == 0)
+        excl = atomicAdd(&a.counters->visible, tileTotal);
+    }
+    else if(tile != 0)
+    {
+      excl = lb_lookback_warp(a.status, tile, a.epoch);
+      if(lane == 0)
+        lb_store(a.status + tile, lb_pack(a.epoch, LB_INCLUSIVE, excl + tileTotal));
+    }
     if(lane == 0)
     {
-      uint64_t* st = a.status + tile;
-      if(tile == 0)
-      {
-        lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, total));
-        sm.basePrefix = 0;
-      }
-      else
-      {
-        lb_store(st, lb_pack(a.epoch, LB_AGGREGATE, total));
-        const uint32_t excl = lb_lookback(a.status, tile, 1, a.epoch);
-        lb_store(st, lb_pack(a.epoch, LB_INCLUSIVE, excl + total));
-        sm.basePrefix = excl;
-      }
+      sm.basePrefix = excl;
       // the tile holding the last splat knows V once its prefix is resolved
-      if(first + PRE_TILE >= a.set.count)
-        a.counters->visible = sm.basePrefix + total;
+      if(first + PRE_TILE >= a.set.count && !(ablate & 1u))
+        a.counters->visible = excl + tileTotal;
     }
   }
   __syncthreads();
@@ -390,11 +406,11 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     a.keys[slot]        = key;
     a.ids[slot]         = static_cast<uint32_t>(id);
   }
-  // flush the digit histograms (only bins this tile touched)
+  // flush the digit histograms of the four sort passes (only bins this tile touched)
   for(int i = tid; i < 4 * 256; i += PRE_TILE)
   {
     const uint32_t v = (&sm.hist[0][0])[i];
-    if(v)
+    if(v && !(ablate & 2u))
       atomicAdd(&a.counters->depthHist[0][0] + i, v);
   }
 }

@@ -46,8 +46,27 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
   const unsigned tid  = threadIdx.x;
   const unsigned lane = tid & 31u, warp = tid >> 5;
 
+#ifdef VKGS_TIMELINE
+  const long long tl0 = clock64();
+#endif
   const uint32_t count = *a.countPtr;
   const uint32_t parts = (count + SORT_PART - 1) / SORT_PART;
+  uint32_t       cur   = a.srcSelIn ? *a.srcSelIn : 0u;
+  if(a.srcSelOut)
+  {
+    // identity pass (every key has the same digit, e.g. the exponent byte of NDC depths): skip it
+    const int same = __syncthreads_or(count == 0u || a.histogram[tid & 255u] == count);
+    if(same)
+    {
+      if(blockIdx.x == 0 && tid == 0)
+        *a.srcSelOut = cur;
+      return;
+    }
+  }
+  const uint32_t* __restrict__ keysIn  = a.keys[cur];
+  const uint32_t* __restrict__ valsIn  = a.vals[cur];
+  uint32_t* __restrict__       keysOut = a.keys[cur ^ 1u];
+  uint32_t* __restrict__       valsOut = a.vals[cur ^ 1u];
   if(tid == 0)
     sm.part = atomicAdd(a.ticket, 1u);
   for(int i = tid; i < NWARPS * 256; i += SORT_THREADS)
@@ -56,71 +75,77 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
   const uint32_t part = sm.part;
   if(part >= parts)
     return;
+#ifdef VKGS_TIMELINE
+  if(tid == 0 && g_vkgsTimeline)
+    g_vkgsTimeline[part * 16 + 0] = tl0;
+#endif
+  VKGS_TL(part, 1);
 
-  // ---- load (warp-striped: warp w owns SORT_ITEMS*32 consecutive pairs) ------------------------
+  // ---- load keys (warp-striped: warp w owns SORT_ITEMS*32 consecutive pairs) ------------------
   const uint32_t partBase = part * SORT_PART;
   const uint32_t warpBase = partBase + warp * (SORT_ITEMS * 32);
-  uint32_t       keys[SORT_ITEMS], vals[SORT_ITEMS];
+  uint32_t       keys[SORT_ITEMS];
 #pragma unroll
   for(int i = 0; i < SORT_ITEMS; i++)
   {
     const uint32_t idx = warpBase + i * 32 + lane;
-    const bool     ok  = idx < count;
-    keys[i]            = ok ? a.keysIn[idx] : 0xffffffffu;  // padding sorts last, is never written back
-    vals[i]            = ok ? a.valsIn[idx] : 0u;
+    keys[i]            = idx < count ? keysIn[idx] : 0xffffffffu;  // padding sorts last, is never written back
   }
+  VKGS_TL(part, 2);
 
-  // ---- rank within the warp (match-any multi-split) --------------------------------------------
+  // ---- rank within the warp (ballot multi-split) ------------------------------------------------
+  // peer masks first (see match_digit), then the dependent counter updates
   uint32_t rank[SORT_ITEMS];
+  {
+    unsigned peers[SORT_ITEMS];
+#pragma unroll
+    for(int i = 0; i < SORT_ITEMS; i++)
+      peers[i] = match_digit<8>(FULL_MASK, (keys[i] >> a.shift) & 0xffu);
+#pragma unroll
+    for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      const uint32_t digit  = (keys[i] >> a.shift) & 0xffu;
+      const unsigned leader = __ffs(peers[i]) - 1;
+      uint32_t       before = 0;
+      if(lane == leader)
+      {
+        before                   = sm.warpHist[warp][digit];
+        sm.warpHist[warp][digit] = before + __popc(peers[i]);
+      }
+      before  = __shfl_sync(FULL_MASK, before, leader);
+      rank[i] = before + __popc(peers[i] & ((1u << lane) - 1u));
+      __syncwarp();
+    }
+  }
+  // values are only needed for staging: issue their loads now so the latency hides behind the scans
+  uint32_t vals[SORT_ITEMS];
 #pragma unroll
   for(int i = 0; i < SORT_ITEMS; i++)
   {
-    const uint32_t digit  = (keys[i] >> a.shift) & 0xffu;
-    const unsigned peers  = __match_any_sync(FULL_MASK, digit);
-    const unsigned leader = __ffs(peers) - 1;
-    uint32_t       before = 0;
-    if(lane == leader)
-    {
-      before                  = sm.warpHist[warp][digit];
-      sm.warpHist[warp][digit] = before + __popc(peers);
-    }
-    before  = __shfl_sync(FULL_MASK, before, leader);
-    rank[i] = before + __popc(peers & ((1u << lane) - 1u));
-    __syncwarp();
+    const uint32_t idx = warpBase + i * 32 + lane;
+    vals[i]            = idx < count ? valsIn[idx] : 0u;
   }
   __syncthreads();
+  VKGS_TL(part, 3);
 
-  // ---- per-digit: exclusive scan over warps, block totals --------------------------------------
-  uint32_t digitCount = 0;
+  // ---- per-digit: exclusive scan over warps, block totals; publish the aggregate at once -------
+  uint32_t  digitCount = 0, realCount = 0;
+  uint64_t* mine       = a.status + static_cast<uint64_t>(part) * 256 + (tid & 255u);
   if(tid < 256)
   {
     uint32_t run = 0;
 #pragma unroll
     for(int w = 0; w < NWARPS; w++)
     {
-      const uint32_t c      = sm.warpHist[w][tid];
-      sm.warpHist[w][tid]   = run;
+      const uint32_t c    = sm.warpHist[w][tid];
+      sm.warpHist[w][tid] = run;
       run += c;
     }
     digitCount = run;
-  }
-  // exclusive scan of the 256 digit totals -> block-local start of each digit
-  {
-    uint32_t       total;
-    const uint32_t excl = block_exclusive_scan<NWARPS>(tid < 256 ? digitCount : 0u, sm.scan, total);
-    if(tid < 256)
-      sm.digitStart[tid] = excl;
-  }
-
-  // ---- global digit offsets: decoupled look-back, one chain per digit --------------------------
-  if(tid < 256)
-  {
-    uint64_t* mine = a.status + static_cast<uint64_t>(part) * 256 + tid;
     // padding keys (digit 0xff of the last partition) are not counted
-    uint32_t realCount = digitCount;
+    realCount = digitCount;
     if(tid == 255 && partBase + SORT_PART > count)
       realCount -= (partBase + SORT_PART - count);
-    uint32_t excl;
     if(part == 0)
     {
       // exclusive scan of the global digit histogram = first global position of each digit.
@@ -134,18 +159,24 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
       uint32_t add = 0;
       for(unsigned w = 0; w < warp; w++)
         add += warpTot[w];
-      excl = inc - h + add;
+      const uint32_t excl = inc - h + add;
       lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
+      sm.globalBase[tid] = excl;
+      if(tid == 0 && a.srcSelOut)
+        *a.srcSelOut = cur ^ 1u;
     }
     else
-    {
-      lb_store(mine, lb_pack(a.epoch, LB_AGGREGATE, realCount));
-      excl = lb_lookback(a.status + tid, part, 256, a.epoch);
-      lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
-    }
-    sm.globalBase[tid] = excl;
+      lb_store(mine, lb_pack(a.epoch, LB_AGGREGATE, realCount));  // successors never wait on our staging
+  }
+  // exclusive scan of the 256 digit totals -> block-local start of each digit
+  {
+    uint32_t       total;
+    const uint32_t excl = block_exclusive_scan<NWARPS>(tid < 256 ? digitCount : 0u, sm.scan, total);
+    if(tid < 256)
+      sm.digitStart[tid] = excl;
   }
   __syncthreads();
+  VKGS_TL(part, 4);
 
   // ---- block-local positions; stage pairs in sorted order --------------------------------------
   uint32_t pos[SORT_ITEMS];
@@ -162,7 +193,18 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
     sm.stageKeys[pos[i]] = keys[i];
     sm.stageVals[pos[i]] = vals[i];
   }
+  VKGS_TL(part, 5);
+
+  // ---- global digit offsets: decoupled look-back, one chain per digit --------------------------
+  if(tid < 256 && part != 0)
+  {
+    const uint32_t excl = lb_lookback<16>(a.status + tid, part, 256, a.epoch);
+    lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
+    sm.globalBase[tid] = excl;
+  }
+  VKGS_TL(part, 6);
   __syncthreads();
+  VKGS_TL(part, 7);
 
   // ---- scatter: consecutive threads write consecutive positions of a digit run -----------------
   const uint32_t valid = min(static_cast<uint32_t>(SORT_PART), count - partBase);
@@ -175,31 +217,70 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
       const uint32_t k     = sm.stageKeys[j];
       const uint32_t digit = (k >> a.shift) & 0xffu;
       const uint32_t dst   = sm.globalBase[digit] + (j - sm.digitStart[digit]);
-      a.keysOut[dst]       = k;
-      a.valsOut[dst]       = sm.stageVals[j];
+      keysOut[dst]         = k;
+      valsOut[dst]         = sm.stageVals[j];
     }
   }
+  VKGS_TL(part, 8);
 }
 
-// Stand-alone digit histograms (used by vkgs_sort_pairs; the frame pipeline fuses them upstream).
-__global__ void __launch_bounds__(256) k_histogram(const uint32_t* __restrict__ keys, const uint32_t* countPtr, uint32_t* hist,
-                                                   int firstShift, int passes)
+// Digit histograms of all passes in one sweep over the keys. No shared-memory atomics (2 cycles
+// per lane on this part): every warp owns a private 256-bin table per pass and counts a row of 32
+// keys with eight ballots (match_digit) — the lowest lane of each group of equal digits adds the group size with a
+// plain read-modify-write. Tables are reduced per block and flushed with one global atomic per
+// non-empty bin (a few hundred blocks at most).
+constexpr int HIST_THREADS = 256;
+constexpr int HIST_WARPS   = HIST_THREADS / 32;
+
+template <int PASSES>
+__global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t* __restrict__ keys, const uint32_t* countPtr,
+                                                            uint32_t* hist, int firstShift)
 {
-  __shared__ uint32_t s[4][256];
-  for(int i = threadIdx.x; i < 4 * 256; i += 256)
-    (&s[0][0])[i] = 0u;
+  __shared__ uint32_t s[HIST_WARPS][PASSES][256];
+  const unsigned      tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  for(int i = tid; i < HIST_WARPS * PASSES * 256; i += HIST_THREADS)
+    (&s[0][0][0])[i] = 0u;
   __syncthreads();
   const uint32_t count = *countPtr;
-  for(uint64_t i = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x; i < count; i += static_cast<uint64_t>(gridDim.x) * 256)
+  // each warp walks rows of 32 keys, 4 rows per trip for memory-level parallelism
+  const uint64_t warpsTotal = static_cast<uint64_t>(gridDim.x) * HIST_WARPS;
+  const uint64_t warpId     = static_cast<uint64_t>(blockIdx.x) * HIST_WARPS + warp;
+  for(uint64_t base = warpId * 128; base < count; base += warpsTotal * 128)
   {
-    const uint32_t k = keys[i];
-    for(int p = 0; p < passes; p++)
-      atomicAdd(&s[p][(k >> (firstShift + 8 * p)) & 0xffu], 1u);
+    uint32_t k[4];
+    bool     ok[4];
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+    {
+      const uint64_t i = base + r * 32 + lane;
+      ok[r]            = i < count;
+      k[r]             = ok[r] ? keys[i] : 0u;
+    }
+#pragma unroll
+    for(int r = 0; r < 4; r++)
+    {
+      // all 32 lanes take part in the ballots (full-mask votes are the fast path); lanes past the
+      // end of the input are masked out of the peer sets afterwards
+      const unsigned active = __ballot_sync(FULL_MASK, ok[r]);
+      if(active == 0u)
+        break;
+#pragma unroll
+      for(int p = 0; p < PASSES; p++)
+      {
+        const uint32_t d     = (k[r] >> (firstShift + 8 * p)) & 0xffu;
+        const unsigned peers = match_digit<8>(FULL_MASK, d) & active;
+        if(ok[r] && lane == static_cast<unsigned>(__ffs(peers) - 1))
+          s[warp][p][d] += __popc(peers);
+      }
+    }
   }
   __syncthreads();
-  for(int i = threadIdx.x; i < passes * 256; i += 256)
+  for(int i = tid; i < PASSES * 256; i += HIST_THREADS)
   {
-    const uint32_t v = (&s[0][0])[i];
+    uint32_t v = 0;
+#pragma unroll
+    for(int w = 0; w < HIST_WARPS; w++)
+      v += (&s[w][0][0])[i];
     if(v)
       atomicAdd(hist + i, v);
   }
@@ -218,9 +299,14 @@ void launchSortPass(const SortPassArgs& args, cudaStream_t stream)
 void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t maxCount, uint32_t* hist, int firstShift, int passes,
                      cudaStream_t stream)
 {
-  uint32_t blocks = (maxCount + 256 * 16 - 1) / (256 * 16);
-  blocks          = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
-  k_histogram<<<blocks, 256, 0, stream>>>(keys, countPtr, hist, firstShift, passes);
+  uint32_t blocks = (maxCount + HIST_THREADS * 16 - 1) / (HIST_THREADS * 16);
+  blocks          = blocks < 1 ? 1 : (blocks > 148 * 2 ? 148 * 2 : blocks);
+  if(passes == 4)
+    k_histogram<4><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, hist, firstShift);
+  else if(passes == 2)
+    k_histogram<2><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, hist, firstShift);
+  else
+    k_histogram<1><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, hist, firstShift);
 }
 
 void initSortKernels()

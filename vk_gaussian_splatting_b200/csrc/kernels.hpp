@@ -25,6 +25,8 @@ struct FrameCounters
   uint32_t tilePairs;          // D: (splat,tile) pairs the binning wanted to emit
   uint32_t tilePairsClamped;   // min(D, capacity): what the tile sort actually processes
   uint32_t overflow;           // set when D exceeded the tile-list capacity
+  uint32_t sortSrc[4];         // [p]: which (key,id) buffer holds the output of depth-sort pass p (a pass
+                               // whose digit is constant over all keys is skipped and does not flip it)
   uint32_t ticket[12];         // dynamic tile / partition tickets, one per kernel launch
   uint32_t depthHist[4][256];  // digit histograms of the depth keys (filled by the preprocess kernel)
   uint32_t tileHist[2][256];   // digit histograms of the tile ids (filled by the binning kernel)
@@ -63,10 +65,14 @@ void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream);
 
 struct SortPassArgs
 {
-  const uint32_t* keysIn;
-  const uint32_t* valsIn;
-  uint32_t*       keysOut;
-  uint32_t*       valsOut;
+  // ping-pong buffers; the pass reads buffer `cur` and writes buffer `cur^1`, where cur = *srcSelIn
+  // (0 when srcSelIn is null). With srcSelOut set, a pass whose digit histogram has a single
+  // non-empty bin is skipped (it would be the identity) and *srcSelOut tells later kernels where
+  // the data is.
+  uint32_t*       keys[2];
+  uint32_t*       vals[2];
+  const uint32_t* srcSelIn;
+  uint32_t*       srcSelOut;
   const uint32_t* countPtr;   // device-side number of pairs
   uint32_t        maxCount;   // host-side upper bound (sizes the grid)
   const uint32_t* histogram;  // 256 digit counts of this pass (not yet scanned)
@@ -85,7 +91,8 @@ void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t ma
 
 struct BinArgs
 {
-  const uint32_t* sortedIds;   // [V] depth-sorted splat ids
+  const uint32_t* sortedIds[2];  // [V] depth-sorted splat ids: buffer *sortedSel holds them
+  const uint32_t* sortedSel;
   const uint32_t* records;
   FrameCounters*  counters;
   uint32_t*       tileKeys;    // [capacity]
@@ -96,6 +103,7 @@ struct BinArgs
   uint64_t*       status;
   uint32_t        epoch;
   uint32_t        ticketSlot;
+  uint32_t        debugFlags;  // profiling ablations (0 in production)
 };
 
 void launchBinEmit(const BinArgs& args, cudaStream_t stream);
