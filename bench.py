@@ -234,22 +234,27 @@ def main():
     fps = world * args.steps / (ms_total / 1000.0)
 
     # ---- end to end: host params in, RGBA frame to pinned host memory out, synchronous call ---------
-    host_img = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True)
-    host_np = host_img.numpy()
+    host_imgs = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+    host_np = [t.numpy() for t in host_imgs]
     e2e_steps = max(10, min(args.steps, 100))
-    for _ in range(3):
-        r.render(fp, out=host_np)
+    for i in range(3):
+        r.render_to_host_async(fp, host_np[i % 2])
+    r.sync()
     barrier()
     e0.record(stream)
-    for _ in range(e2e_steps):
-        r.render(fp, out=host_np)
+    for i in range(e2e_steps):
+        # the call a user makes: host frame parameters in, finished RGBA frame copied to pinned host
+        # memory out, every step; two frames in flight so step i's copy overlaps step i+1's kernels
+        r.render_to_host_async(fp, host_np[i % 2])
     e1.record(stream)
+    r.sync()
     torch.cuda.synchronize()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     fps_e2e = world * e2e_steps / (ms_e2e / 1000.0)
 
     # ---- per-kernel profile (separate frames, cudaEvents around every launch on the launch stream) --
+    r.set_frames_in_flight(1)  # per-kernel times need one frame at a time (no cross-frame overlap)
     r.set_profiling(True)
     acc, nprof = {}, 10
     for _ in range(nprof):
@@ -259,6 +264,7 @@ def main():
         for k, v in s.ms_kernel.items():
             acc[k] = acc.get(k, 0.0) + v / nprof
     r.set_profiling(False)
+    r.set_frames_in_flight(2)
     stage_ms = {"GPU Dist": acc["preprocess"], "GPU Sort": acc["sort_hist"] + sum(acc[f"sort_pass{i}"] for i in range(4)),
                 "Rasterization": acc["bin_emit"] + acc["tile_hist"] + acc["tile_sort0"] + acc["tile_sort1"] + acc["tile_ranges"] + acc["blend"]}
     dominant = max(acc, key=acc.get)

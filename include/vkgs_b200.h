@@ -159,7 +159,9 @@ typedef struct vkgs_outputs
 /* ---- lifetime (replaces GaussianSplatting::onAttach/onDetach, src/gaussian_splatting.h:124-127) */
 VKGS_API int vkgs_create(int device, vkgs_ctx** out);
 VKGS_API int vkgs_destroy(vkgs_ctx* ctx);
-/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own. */
+/* Make every frame's completion visible on a caller-owned CUDA stream (cudaStream_t as void*), in
+ * submission order: work the caller enqueues on it afterwards sees the finished framebuffer, and
+ * events recorded on it bracket the frames. NULL detaches. Frames run on the context's own streams. */
 VKGS_API int vkgs_set_stream(vkgs_ctx* ctx, void* cuda_stream);
 VKGS_API const char* vkgs_last_error(const vkgs_ctx* ctx);
 VKGS_API const char* vkgs_version(void);
@@ -185,8 +187,15 @@ VKGS_API int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t widt
 VKGS_API void vkgs_default_camera(vkgs_camera* cam);
 /* Synchronous: returns after the frame (and the requested copies to host) completed. */
 VKGS_API int vkgs_render(vkgs_ctx* ctx, const vkgs_frame_params* fp, vkgs_outputs* out);
-/* Stream-ordered: enqueue one frame, result stays in the device framebuffer. */
+/* Stream-ordered: enqueue one frame, result stays in the device framebuffer. Up to two frames are
+ * in flight on two internal streams (the frames-in-flight of the reference's swapchain loop,
+ * nvpro_core2/nvapp/application.cpp:517-548); completion order == submission order. */
 VKGS_API int vkgs_render_async(vkgs_ctx* ctx, const vkgs_frame_params* fp);
+/* Same, plus an asynchronous copy of the finished fp32 RGBA frame to PINNED host memory
+ * (W*H*4 floats); the buffer is valid after vkgs_sync (or after the caller's stream reaches it). */
+VKGS_API int vkgs_render_to_host_async(vkgs_ctx* ctx, const vkgs_frame_params* fp, float* host_rgba);
+/* 1 = strictly one frame at a time, 2 (default) = overlap consecutive frames. */
+VKGS_API int vkgs_set_frames_in_flight(vkgs_ctx* ctx, int frames);
 VKGS_API int vkgs_sync(vkgs_ctx* ctx);
 /* Enable per-kernel cudaEvent timing for subsequent frames (off by default). */
 VKGS_API int vkgs_set_profiling(vkgs_ctx* ctx, int enabled);

@@ -81,6 +81,8 @@ SYMBOLS = {
     "vkgs_default_camera": (None, [C.POINTER(Camera)]),
     "vkgs_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.POINTER(Outputs)]),
     "vkgs_render_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams)]),
+    "vkgs_render_to_host_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), f32p]),
+    "vkgs_set_frames_in_flight": (C.c_int, [C.c_void_p, C.c_int]),
     "vkgs_sync": (C.c_int, [C.c_void_p]),
     "vkgs_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "vkgs_last_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(Outputs)]),

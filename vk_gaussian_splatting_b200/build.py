@@ -23,7 +23,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
           f"-I{ROOT / 'include'}", f"-I{CSRC}"]
 # per-file extra flags: the per-splat front end must not contract mul+add (bit-exact vs the oracle)
 EXTRA = {"k_preprocess.cu": ["-fmad=false"]}
-SOURCES = ["context.cu", "k_preprocess.cu", "k_radix_sort.cu", "k_binning.cu", "k_blend.cu",
+SOURCES = ["context.cu", "sort_api.cu", "k_preprocess.cu", "k_radix_sort.cu", "k_binning.cu", "k_blend.cu",
            "host_camera.cpp", "host_pack.cpp", "host_synth.cpp"]
 
 

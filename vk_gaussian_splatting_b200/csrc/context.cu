@@ -4,8 +4,10 @@
 // (src/gaussian_splatting.cpp:1298-1367, 1369-1465) as a fixed sequence of stream-ordered launches
 // with every data-dependent size (V, tile-pair count) read on the device — no host round trip
 // inside a frame:
-//   memset(control block) -> preprocess -> 4 x sort pass -> bin emit -> 2 x tile sort pass
+//   memset(control block) -> preprocess -> <=4 x sort pass -> bin emit -> 2 x tile sort pass
 //   -> tile ranges -> blend
+// Up to two frames are in flight on two internal streams (FrameSlot), so one frame's latency-bound
+// front end overlaps the previous frame's blend.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -13,9 +15,8 @@
 #include <string>
 #include <vector>
 
+#include "context.hpp"
 #include "host_pack.hpp"
-#include "kernels.hpp"
-#include "vkgs_b200.h"
 
 namespace vkgs {
 void initSortKernels();
@@ -24,55 +25,7 @@ void initPreprocessKernels();
 
 using namespace vkgs;
 
-struct vkgs_ctx
-{
-  int          device      = 0;
-  cudaStream_t ownStream   = nullptr;
-  cudaStream_t stream      = nullptr;
-  std::string  lastError;
-  uint64_t     launches    = 0;
-  uint32_t     epoch       = 0;
-  bool         profiling   = false;
-
-  // scene
-  bool           uploaded = false;
-  vkgs_options   opt{};
-  DeviceSplatSet set{};
-  uint64_t       paddedCount = 0;
-  void *         dCenters = nullptr, *dCov = nullptr, *dScales = nullptr, *dRgba = nullptr, *dSh = nullptr;
-
-  // per-frame buffers
-  uint32_t *     dKeys[2] = {nullptr, nullptr}, *dIds[2] = {nullptr, nullptr};
-  uint32_t*      dRecords    = nullptr;
-  FrameCounters* dCounters   = nullptr;
-  uint64_t *     dPreStatus = nullptr, *dSortStatus = nullptr, *dBinStatus = nullptr, *dTileSortStatus = nullptr;
-  uint32_t *     dTileKeys[2] = {nullptr, nullptr}, *dTileVals[2] = {nullptr, nullptr};
-  uint64_t       tileCapacity = 0;
-  uint2*         dRanges      = nullptr;
-  uint32_t       rangesTiles  = 0;
-  float4*        dImage       = nullptr;
-  uint32_t       imgW = 0, imgH = 0;
-  FrameCounters* hCounters = nullptr;  // pinned
-
-  // last frame
-  vkgs_frame_params lastFp{};
-  bool              haveFrame = false;
-  cudaEvent_t       ev[VKGS_K_COUNT + 1]{};
-  bool              evRecorded = false;
-};
-
 namespace {
-
-#define CU_TRY(ctx, expr)                                                                                                      \
-  do                                                                                                                           \
-  {                                                                                                                            \
-    cudaError_t e_ = (expr);                                                                                                   \
-    if(e_ != cudaSuccess)                                                                                                      \
-    {                                                                                                                          \
-      (ctx)->lastError = std::string(#expr) + ": " + cudaGetErrorString(e_);                                                   \
-      return VKGS_ERR_CUDA;                                                                                                    \
-    }                                                                                                                          \
-  } while(0)
 
 int fail(vkgs_ctx* ctx, int code, const char* msg)
 {
@@ -81,56 +34,75 @@ int fail(vkgs_ctx* ctx, int code, const char* msg)
   return code;
 }
 
-template <typename T>
-void freeDev(T*& p)
+void freeSlotScene(FrameSlot& s)
 {
-  if(p)
-    cudaFree(p);
-  p = nullptr;
+  for(int i = 0; i < 2; i++)
+    freeDev(s.dKeys[i]), freeDev(s.dIds[i]), freeDev(s.dTileKeys[i]), freeDev(s.dTileVals[i]);
+  freeDev(s.dRecords), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
+  s.tileCapacity = 0;
+  s.haveFrame    = false;
 }
 
 void freeScene(vkgs_ctx* c)
 {
   freeDev(c->dCenters), freeDev(c->dCov), freeDev(c->dScales), freeDev(c->dRgba), freeDev(c->dSh);
-  for(int i = 0; i < 2; i++)
-    freeDev(c->dKeys[i]), freeDev(c->dIds[i]), freeDev(c->dTileKeys[i]), freeDev(c->dTileVals[i]);
-  freeDev(c->dRecords), freeDev(c->dPreStatus), freeDev(c->dSortStatus), freeDev(c->dBinStatus), freeDev(c->dTileSortStatus);
-  c->tileCapacity = 0;
-  c->uploaded     = false;
+  for(auto& s : c->slots)
+    freeSlotScene(s);
+  c->uploaded = false;
+  c->lastSlot = -1;
 }
 
-int allocTileLists(vkgs_ctx* c, uint64_t capacity)
+int allocTileLists(vkgs_ctx* c, FrameSlot& s, uint64_t capacity)
 {
   for(int i = 0; i < 2; i++)
-    freeDev(c->dTileKeys[i]), freeDev(c->dTileVals[i]);
-  freeDev(c->dTileSortStatus);
+    freeDev(s.dTileKeys[i]), freeDev(s.dTileVals[i]);
+  freeDev(s.dTileSortStatus);
   capacity = std::min<uint64_t>(capacity, 0xfffff000ull);
   for(int i = 0; i < 2; i++)
   {
-    CU_TRY(c, cudaMalloc(&c->dTileKeys[i], capacity * sizeof(uint32_t)));
-    CU_TRY(c, cudaMalloc(&c->dTileVals[i], capacity * sizeof(uint32_t)));
+    CU_TRY(c, cudaMalloc(&s.dTileKeys[i], capacity * sizeof(uint32_t)));
+    CU_TRY(c, cudaMalloc(&s.dTileVals[i], capacity * sizeof(uint32_t)));
   }
   const uint64_t parts = (capacity + SORT_PART - 1) / SORT_PART;
-  CU_TRY(c, cudaMalloc(&c->dTileSortStatus, parts * 256 * sizeof(uint64_t)));
-  CU_TRY(c, cudaMemset(c->dTileSortStatus, 0, parts * 256 * sizeof(uint64_t)));
-  c->tileCapacity = capacity;
+  CU_TRY(c, cudaMalloc(&s.dTileSortStatus, parts * 256 * sizeof(uint64_t)));
+  CU_TRY(c, cudaMemset(s.dTileSortStatus, 0, parts * 256 * sizeof(uint64_t)));
+  s.tileCapacity = capacity;
   return VKGS_OK;
 }
 
-int ensureTargets(vkgs_ctx* c, uint32_t w, uint32_t h)
+int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n)
+{
+  for(int i = 0; i < 2; i++)
+  {
+    CU_TRY(c, cudaMalloc(&s.dKeys[i], n * sizeof(uint32_t)));
+    CU_TRY(c, cudaMalloc(&s.dIds[i], n * sizeof(uint32_t)));
+  }
+  CU_TRY(c, cudaMalloc(&s.dRecords, n * RECORD_WORDS * sizeof(uint32_t)));
+  const uint64_t preTiles = (n + PRE_TILE - 1) / PRE_TILE, binParts = (n + 255) / 256, sortParts = (n + SORT_PART - 1) / SORT_PART;
+  CU_TRY(c, cudaMalloc(&s.dPreStatus, preTiles * sizeof(uint64_t)));
+  CU_TRY(c, cudaMalloc(&s.dBinStatus, binParts * sizeof(uint64_t)));
+  CU_TRY(c, cudaMalloc(&s.dSortStatus, sortParts * 256 * sizeof(uint64_t)));
+  CU_TRY(c, cudaMemset(s.dPreStatus, 0, preTiles * sizeof(uint64_t)));
+  CU_TRY(c, cudaMemset(s.dBinStatus, 0, binParts * sizeof(uint64_t)));
+  CU_TRY(c, cudaMemset(s.dSortStatus, 0, sortParts * 256 * sizeof(uint64_t)));
+  return allocTileLists(c, s, std::max<uint64_t>(8 * n, 1u << 20));
+}
+
+int ensureTargets(vkgs_ctx* c, FrameSlot& s, uint32_t w, uint32_t h)
 {
   if(w == 0 || h == 0 || w > 65535 || h > 65535)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "viewport must be within 1..65535 pixels per side");
   const uint32_t tx = (w + TILE_W - 1) / TILE_W, ty = (h + TILE_H - 1) / TILE_H;
   if(tx * ty > 65536)
     return fail(c, VKGS_ERR_UNSUPPORTED, "more than 65536 tiles (tile ids are sorted on 16 bits)");
-  if(c->imgW != w || c->imgH != h)
+  if(s.imgW != w || s.imgH != h)
   {
-    freeDev(c->dImage);
-    freeDev(c->dRanges);
-    CU_TRY(c, cudaMalloc(&c->dImage, sizeof(float4) * static_cast<size_t>(w) * h));
-    CU_TRY(c, cudaMalloc(&c->dRanges, sizeof(uint2) * tx * ty));
-    c->imgW = w, c->imgH = h, c->rangesTiles = tx * ty;
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    freeDev(s.dImage);
+    freeDev(s.dRanges);
+    CU_TRY(c, cudaMalloc(&s.dImage, sizeof(float4) * static_cast<size_t>(w) * h));
+    CU_TRY(c, cudaMalloc(&s.dRanges, sizeof(uint2) * tx * ty));
+    s.imgW = w, s.imgH = h;
   }
   return VKGS_OK;
 }
@@ -141,12 +113,17 @@ uint32_t nextEpoch(vkgs_ctx* c)
   if(c->epoch >= (1u << 30))
   {
     // epoch space exhausted (2^30 launches): clear the status arrays once and restart
-    cudaStreamSynchronize(c->stream);
     const uint64_t n = c->set.count;
-    cudaMemset(c->dPreStatus, 0, ((n + PRE_TILE - 1) / PRE_TILE) * sizeof(uint64_t));
-    cudaMemset(c->dBinStatus, 0, ((n + BIN_THREADS - 1) / BIN_THREADS) * sizeof(uint64_t));
-    cudaMemset(c->dSortStatus, 0, ((n + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
-    cudaMemset(c->dTileSortStatus, 0, ((c->tileCapacity + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
+    for(auto& s : c->slots)
+    {
+      cudaStreamSynchronize(s.stream);
+      if(!s.dPreStatus)
+        continue;
+      cudaMemset(s.dPreStatus, 0, ((n + PRE_TILE - 1) / PRE_TILE) * sizeof(uint64_t));
+      cudaMemset(s.dBinStatus, 0, ((n + 255) / 256) * sizeof(uint64_t));
+      cudaMemset(s.dSortStatus, 0, ((n + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
+      cudaMemset(s.dTileSortStatus, 0, ((s.tileCapacity + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
+    }
     c->epoch = 1;
   }
   return c->epoch;
@@ -165,27 +142,29 @@ void frameConstants(const vkgs_frame_params& fp, float mv[16], float camModel[3]
                   + cp[3] * fp.model_inverse[12 + j];
 }
 
-void mark(vkgs_ctx* c, int slot)
-{
-  if(c->profiling)
-    cudaEventRecord(c->ev[slot], c->stream);
-}
-
-int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp)
+// Enqueue one frame on the next slot; optionally a device->host copy of the finished frame.
+int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, float* hostRgba, int* slotOut)
 {
   if(!c->uploaded)
     return fail(c, VKGS_ERR_NOT_UPLOADED, "vkgs_render before vkgs_upload");
   if(fp.width == 0 || fp.height == 0)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "zero-sized viewport");
-  if(int rc = ensureTargets(c, fp.width, fp.height))
-    return rc;
   CU_TRY(c, cudaSetDevice(c->device));
+  const int  si = c->nextSlot;
+  FrameSlot& s  = c->slots[si];
+  if(int rc = ensureTargets(c, s, fp.width, fp.height))
+    return rc;
   const uint32_t n  = c->set.count;
   const uint32_t tx = (fp.width + TILE_W - 1) / TILE_W, ty = (fp.height + TILE_H - 1) / TILE_H;
+  cudaStream_t   st = s.stream;
+  auto           mark = [&](int slot) {
+    if(c->profiling)
+      cudaEventRecord(s.ev[slot], st);
+  };
 
-  CU_TRY(c, cudaMemsetAsync(c->dCounters, 0, sizeof(FrameCounters), c->stream));
-  CU_TRY(c, cudaMemsetAsync(c->dRanges, 0, sizeof(uint2) * tx * ty, c->stream));
-  mark(c, 0);
+  CU_TRY(c, cudaMemsetAsync(s.dCounters, 0, sizeof(FrameCounters), st));
+  CU_TRY(c, cudaMemsetAsync(s.dRanges, 0, sizeof(uint2) * tx * ty, st));
+  mark(0);
 
   // ---- "GPU Dist" (+ the per-splat half of "Rasterization", fused) -----------------------------
   PreprocessArgs pa{};
@@ -193,87 +172,87 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp)
   pa.fp  = fp;
   pa.opt = c->opt;
   frameConstants(fp, pa.mv, pa.camModel);
-  pa.keys       = c->dKeys[0];
-  pa.ids        = c->dIds[0];
-  pa.records    = c->dRecords;
-  pa.counters   = c->dCounters;
-  pa.status     = c->dPreStatus;
+  pa.keys       = s.dKeys[0];
+  pa.ids        = s.dIds[0];
+  pa.records    = s.dRecords;
+  pa.counters   = s.dCounters;
+  pa.status     = s.dPreStatus;
   pa.epoch      = nextEpoch(c);
   pa.ticketSlot = 0;
-  launchPreprocess(pa, c->stream);
+  launchPreprocess(pa, st);
   c->launches++;
-  mark(c, VKGS_K_PREPROCESS + 1);
-  mark(c, VKGS_K_SORT_SCAN + 1);  // (depth-key digit histograms are fused into the preprocess kernel)
+  mark(VKGS_K_PREPROCESS + 1);
+  mark(VKGS_K_SORT_SCAN + 1);  // (depth-key digit histograms are fused into the preprocess kernel)
 
-  // ---- "GPU Sort": 4 x 8-bit stable passes over (key,id) ----------------------------------------
+  // ---- "GPU Sort": up to 4 x 8-bit stable passes over (key,id) -----------------------------------
   for(int p = 0; p < 4; p++)
   {
     SortPassArgs sa{};
-    sa.keys[0] = c->dKeys[0], sa.keys[1] = c->dKeys[1];
-    sa.vals[0] = c->dIds[0], sa.vals[1] = c->dIds[1];
-    sa.srcSelIn  = p ? &c->dCounters->sortSrc[p - 1] : nullptr;
-    sa.srcSelOut = &c->dCounters->sortSrc[p];
-    sa.countPtr  = &c->dCounters->visible;
+    sa.keys[0] = s.dKeys[0], sa.keys[1] = s.dKeys[1];
+    sa.vals[0] = s.dIds[0], sa.vals[1] = s.dIds[1];
+    sa.srcSelIn  = p ? &s.dCounters->sortSrc[p - 1] : nullptr;
+    sa.srcSelOut = &s.dCounters->sortSrc[p];
+    sa.countPtr  = &s.dCounters->visible;
     sa.maxCount  = n;
-    sa.histogram = &c->dCounters->depthHist[p][0];
-    sa.status    = c->dSortStatus;
-    sa.ticket    = &c->dCounters->ticket[1 + p];
+    sa.histogram = &s.dCounters->depthHist[p][0];
+    sa.status    = s.dSortStatus;
+    sa.ticket    = &s.dCounters->ticket[1 + p];
     sa.epoch     = nextEpoch(c);
     sa.shift     = 8 * p;
-    launchSortPass(sa, c->stream);
+    launchSortPass(sa, st);
     c->launches++;
-    mark(c, VKGS_K_SORT_PASS0 + p + 1);
+    mark(VKGS_K_SORT_PASS0 + p + 1);
   }
   // the sorted pairs are in buffer sortSrc[3] (0 unless an odd number of passes was skipped)
 
   // ---- "Rasterization": binning, tile sort, blend -------------------------------------------------
   BinArgs ba{};
-  ba.sortedIds[0] = c->dIds[0], ba.sortedIds[1] = c->dIds[1];
-  ba.sortedSel  = &c->dCounters->sortSrc[3];
-  ba.records    = c->dRecords;
-  ba.counters   = c->dCounters;
-  ba.tileKeys   = c->dTileKeys[0];
-  ba.tileVals   = c->dTileVals[0];
-  ba.capacity   = static_cast<uint32_t>(c->tileCapacity);
+  ba.sortedIds[0] = s.dIds[0], ba.sortedIds[1] = s.dIds[1];
+  ba.sortedSel  = &s.dCounters->sortSrc[3];
+  ba.records    = s.dRecords;
+  ba.counters   = s.dCounters;
+  ba.tileKeys   = s.dTileKeys[0];
+  ba.tileVals   = s.dTileVals[0];
+  ba.capacity   = static_cast<uint32_t>(s.tileCapacity);
   ba.maxCount   = n;
   ba.tilesX     = tx;
   ba.tilesY     = ty;
-  ba.status     = c->dBinStatus;
+  ba.status     = s.dBinStatus;
   ba.epoch      = nextEpoch(c);
   ba.ticketSlot = 5;
   ba.debugFlags = c->opt._reserved[5];
-  launchBinEmit(ba, c->stream);
+  launchBinEmit(ba, st);
   c->launches++;
-  mark(c, VKGS_K_BIN_EMIT + 1);
-  mark(c, VKGS_K_TILE_HIST + 1);  // (tile-id digit histograms are fused into the emit kernel)
+  mark(VKGS_K_BIN_EMIT + 1);
+  mark(VKGS_K_TILE_HIST + 1);  // (tile-id digit histograms are fused into the emit kernel)
 
   for(int p = 0; p < 2; p++)
   {
     SortPassArgs sa{};
     // fixed ping-pong (no pass skipping): pass 0 reads buffer 0, pass 1 reads buffer 1
-    sa.keys[0] = c->dTileKeys[p & 1], sa.keys[1] = c->dTileKeys[(p + 1) & 1];
-    sa.vals[0] = c->dTileVals[p & 1], sa.vals[1] = c->dTileVals[(p + 1) & 1];
-    sa.countPtr  = &c->dCounters->tilePairsClamped;
-    sa.maxCount  = static_cast<uint32_t>(c->tileCapacity);
-    sa.histogram = &c->dCounters->tileHist[p][0];
-    sa.status    = c->dTileSortStatus;
-    sa.ticket    = &c->dCounters->ticket[6 + p];
+    sa.keys[0] = s.dTileKeys[p & 1], sa.keys[1] = s.dTileKeys[(p + 1) & 1];
+    sa.vals[0] = s.dTileVals[p & 1], sa.vals[1] = s.dTileVals[(p + 1) & 1];
+    sa.countPtr  = &s.dCounters->tilePairsClamped;
+    sa.maxCount  = static_cast<uint32_t>(s.tileCapacity);
+    sa.histogram = &s.dCounters->tileHist[p][0];
+    sa.status    = s.dTileSortStatus;
+    sa.ticket    = &s.dCounters->ticket[6 + p];
     sa.epoch     = nextEpoch(c);
     sa.shift     = 8 * p;
-    launchSortPass(sa, c->stream);
+    launchSortPass(sa, st);
     c->launches++;
-    mark(c, VKGS_K_TILE_SORT0 + p + 1);
+    mark(VKGS_K_TILE_SORT0 + p + 1);
   }
 
-  launchTileRanges(c->dTileKeys[0], c->dCounters, static_cast<uint32_t>(c->tileCapacity), c->dRanges, c->stream);
+  launchTileRanges(s.dTileKeys[0], s.dCounters, static_cast<uint32_t>(s.tileCapacity), s.dRanges, st);
   c->launches++;
-  mark(c, VKGS_K_TILE_RANGES + 1);
+  mark(VKGS_K_TILE_RANGES + 1);
 
   BlendArgs bl{};
-  bl.tileVals               = c->dTileVals[0];
-  bl.ranges                 = c->dRanges;
-  bl.records                = c->dRecords;
-  bl.image                  = c->dImage;
+  bl.tileVals               = s.dTileVals[0];
+  bl.ranges                 = s.dRanges;
+  bl.records                = s.dRecords;
+  bl.image                  = s.dImage;
   bl.width                  = fp.width;
   bl.height                 = fp.height;
   bl.tilesX                 = tx;
@@ -281,51 +260,83 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp)
   bl.frontToBack            = c->opt.front_to_back;
   bl.disableOpacityGaussian = c->opt.disable_opacity_gaussian;
   bl.transmittanceEpsilon   = c->opt.front_to_back ? c->opt.transmittance_epsilon : 0.0f;
-  launchBlend(bl, c->stream);
+  launchBlend(bl, st);
   c->launches++;
-  mark(c, VKGS_K_BLEND + 1);
-  c->evRecorded = c->profiling;
+  mark(VKGS_K_BLEND + 1);
+  s.evRecorded = c->profiling;
 
-  CU_TRY(c, cudaMemcpyAsync(c->hCounters, c->dCounters, 32, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, 32, cudaMemcpyDeviceToHost, st));
+  if(hostRgba)
+    CU_TRY(c, cudaMemcpyAsync(hostRgba, s.dImage, sizeof(float4) * static_cast<size_t>(fp.width) * fp.height, cudaMemcpyDeviceToHost, st));
+  if(c->userStream)
+  {
+    // completion of this frame becomes visible on the caller's stream, in submission order
+    CU_TRY(c, cudaEventRecord(s.evDone, st));
+    CU_TRY(c, cudaStreamWaitEvent(c->userStream, s.evDone, 0));
+  }
   CU_TRY(c, cudaGetLastError());
-  c->lastFp    = fp;
-  c->haveFrame = true;
+  s.lastFp    = fp;
+  s.haveFrame = true;
+  c->lastSlot = si;
+  c->nextSlot = (si + 1) % std::max(1, c->framesInFlight);
+  if(slotOut)
+    *slotOut = si;
   return VKGS_OK;
 }
 
-// After a sync: if the tile lists overflowed, grow them so the caller can re-render.
+// After a sync: if a slot's tile lists overflowed, grow them so the caller can re-render.
 int checkOverflow(vkgs_ctx* c)
 {
-  if(c->haveFrame && c->hCounters->overflow)
+  bool grown = false;
+  for(auto& s : c->slots)
   {
-    const uint64_t want = static_cast<uint64_t>(c->hCounters->tilePairs) * 5 / 4 + 65536;
-    if(int rc = allocTileLists(c, want))
-      return rc;
-    return fail(c, VKGS_ERR_OVERFLOW, "tile lists overflowed; capacity was grown, render the frame again");
+    if(s.haveFrame && s.hCounters->overflow)
+    {
+      const uint64_t want = static_cast<uint64_t>(s.hCounters->tilePairs) * 5 / 4 + 65536;
+      for(auto& t : c->slots)
+        if(t.tileCapacity && t.tileCapacity < want)
+        {
+          cudaStreamSynchronize(t.stream);
+          if(int rc = allocTileLists(c, t, want))
+            return rc;
+        }
+      s.hCounters->overflow = 0;
+      grown                 = true;
+    }
   }
+  return grown ? fail(c, VKGS_ERR_OVERFLOW, "tile lists overflowed; capacity was grown, render the frame again") : VKGS_OK;
+}
+
+int syncAll(vkgs_ctx* c)
+{
+  for(auto& s : c->slots)
+    if(s.stream)
+      CU_TRY(c, cudaStreamSynchronize(s.stream));
+  if(c->userStream)
+    CU_TRY(c, cudaStreamSynchronize(c->userStream));
   return VKGS_OK;
 }
 
-void fillStats(vkgs_ctx* c, vkgs_outputs* out)
+void fillStats(vkgs_ctx* c, FrameSlot& s, vkgs_outputs* out)
 {
-  out->visible_count = c->hCounters->visible;
-  out->tile_pairs    = c->hCounters->tilePairs;
-  const uint64_t n = c->set.count, v = out->visible_count, p = static_cast<uint64_t>(c->lastFp.width) * c->lastFp.height;
-  const uint32_t deg    = std::min(c->set.shDegree, c->lastFp.sh_degree);
-  const uint64_t shB    = 12ull * ((deg + 1) * (deg + 1) - 1);
+  out->visible_count = s.hCounters->visible;
+  out->tile_pairs    = s.hCounters->tilePairs;
+  const uint64_t n = c->set.count, v = out->visible_count, p = static_cast<uint64_t>(s.lastFp.width) * s.lastFp.height;
+  const uint32_t deg     = std::min(c->set.shDegree, s.lastFp.sh_degree);
+  const uint64_t shB     = 12ull * ((deg + 1) * (deg + 1) - 1);
   out->bytes_algorithmic = 12 * n + (132 + shB) * v + 16 * p;
   std::memset(out->ms_kernel, 0, sizeof(out->ms_kernel));
   out->ms_dist = out->ms_sort = out->ms_raster = out->ms_total = 0.0f;
-  if(c->evRecorded)
+  if(s.evRecorded)
   {
     for(int k = 0; k < VKGS_K_COUNT; k++)
-      cudaEventElapsedTime(&out->ms_kernel[k], c->ev[k], c->ev[k + 1]);
+      cudaEventElapsedTime(&out->ms_kernel[k], s.ev[k], s.ev[k + 1]);
     out->ms_dist = out->ms_kernel[VKGS_K_PREPROCESS];
     for(int k = VKGS_K_SORT_SCAN; k < VKGS_K_BIN_EMIT; k++)
       out->ms_sort += out->ms_kernel[k];
     for(int k = VKGS_K_BIN_EMIT; k < VKGS_K_COUNT; k++)
       out->ms_raster += out->ms_kernel[k];
-    cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[VKGS_K_COUNT]);
+    cudaEventElapsedTime(&out->ms_total, s.ev[0], s.ev[VKGS_K_COUNT]);
   }
 }
 
@@ -336,7 +347,7 @@ extern "C" {
 
 const char* vkgs_version(void)
 {
-  return "vkgs_b200 0.1.0 (sm_100a)";
+  return "vkgs_b200 0.2.0 (sm_100a)";
 }
 
 uint32_t vkgs_abi_struct_size(int which)
@@ -397,20 +408,21 @@ int vkgs_create(int device, vkgs_ctx** out)
     return VKGS_ERR_NO_DEVICE;
   vkgs_ctx* c = new vkgs_ctx();
   c->device   = device;
-  if(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking) != cudaSuccess)
+  bool ok     = true;
+  for(auto& s : c->slots)
   {
-    delete c;
-    return VKGS_ERR_CUDA;
+    ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for(auto& e : s.ev)
+      ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.dCounters, sizeof(FrameCounters)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s.hCounters, sizeof(FrameCounters)) == cudaSuccess;
+    if(ok)
+      std::memset(s.hCounters, 0, sizeof(FrameCounters));
   }
-  c->stream = c->ownStream;
-  for(auto& e : c->ev)
-    cudaEventCreate(&e);
-  cudaMalloc(&c->dCounters, sizeof(FrameCounters));
-  cudaMallocHost(&c->hCounters, sizeof(FrameCounters));
-  std::memset(c->hCounters, 0, sizeof(FrameCounters));
   initSortKernels();
   initPreprocessKernels();
-  if(cudaGetLastError() != cudaSuccess)
+  if(!ok || cudaGetLastError() != cudaSuccess)
   {
     vkgs_destroy(c);
     return VKGS_ERR_CUDA;
@@ -424,16 +436,23 @@ int vkgs_destroy(vkgs_ctx* c)
   if(!c)
     return VKGS_ERR_INVALID_ARGUMENT;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  for(auto& s : c->slots)
+    if(s.stream)
+      cudaStreamSynchronize(s.stream);
   freeScene(c);
-  freeDev(c->dImage), freeDev(c->dRanges), freeDev(c->dCounters);
-  if(c->hCounters)
-    cudaFreeHost(c->hCounters);
-  for(auto& e : c->ev)
-    if(e)
-      cudaEventDestroy(e);
-  if(c->ownStream)
-    cudaStreamDestroy(c->ownStream);
+  for(auto& s : c->slots)
+  {
+    freeDev(s.dImage), freeDev(s.dRanges), freeDev(s.dCounters);
+    if(s.hCounters)
+      cudaFreeHost(s.hCounters);
+    for(auto& e : s.ev)
+      if(e)
+        cudaEventDestroy(e);
+    if(s.evDone)
+      cudaEventDestroy(s.evDone);
+    if(s.stream)
+      cudaStreamDestroy(s.stream);
+  }
   delete c;
   return VKGS_OK;
 }
@@ -442,8 +461,20 @@ int vkgs_set_stream(vkgs_ctx* c, void* cuda_stream)
 {
   if(!c)
     return VKGS_ERR_INVALID_ARGUMENT;
-  cudaStreamSynchronize(c->stream);
-  c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->ownStream;
+  if(int rc = syncAll(c))
+    return rc;
+  c->userStream = static_cast<cudaStream_t>(cuda_stream);
+  return VKGS_OK;
+}
+
+int vkgs_set_frames_in_flight(vkgs_ctx* c, int frames)
+{
+  if(!c || frames < 1 || frames > MAX_FRAMES_IN_FLIGHT)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(int rc = syncAll(c))
+    return rc;
+  c->framesInFlight = frames;
+  c->nextSlot       = 0;
   return VKGS_OK;
 }
 
@@ -479,14 +510,15 @@ int vkgs_upload(vkgs_ctx* c, const vkgs_splat_set_view* set, const vkgs_options*
   if(opt.frustum_culling_mode > VKGS_FRUSTUM_CULLING_AT_RASTER)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad frustum_culling_mode");
   CU_TRY(c, cudaSetDevice(c->device));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if(int rc = syncAll(c))
+    return rc;
 
   PackedSplatSet packed;
   if(int rc = packSplatSet(*set, opt, PRE_TILE, packed))
     return fail(c, rc, "packSplatSet failed (null array, or f_rest_per_splat not 0/45)");
 
   freeScene(c);
-  const uint64_t n = packed.count, pad = packed.paddedCount;
+  const uint64_t n  = packed.count;
   auto           up = [&](void*& dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(&dst, bytes);
     if(e != cudaSuccess)
@@ -508,29 +540,15 @@ int vkgs_upload(vkgs_ctx* c, const vkgs_splat_set_view* set, const vkgs_options*
   c->set.shDegree   = packed.shDegree;
   c->set.shFormat   = packed.shFormat;
   c->set.rgbaFormat = packed.rgbaFormat;
-  c->paddedCount    = pad;
   c->opt            = opt;
 
   // sorting / raster buffers (the reference allocates its sorting buffers with the splat set too,
-  // src/splat_set_manager_vk.cpp:2426-2517)
-  for(int i = 0; i < 2; i++)
-  {
-    CU_TRY(c, cudaMalloc(&c->dKeys[i], n * sizeof(uint32_t)));
-    CU_TRY(c, cudaMalloc(&c->dIds[i], n * sizeof(uint32_t)));
-  }
-  CU_TRY(c, cudaMalloc(&c->dRecords, n * RECORD_WORDS * sizeof(uint32_t)));
-  const uint64_t preTiles = (n + PRE_TILE - 1) / PRE_TILE, binParts = (n + BIN_THREADS - 1) / BIN_THREADS,
-                 sortParts = (n + SORT_PART - 1) / SORT_PART;
-  CU_TRY(c, cudaMalloc(&c->dPreStatus, preTiles * sizeof(uint64_t)));
-  CU_TRY(c, cudaMalloc(&c->dBinStatus, binParts * sizeof(uint64_t)));
-  CU_TRY(c, cudaMalloc(&c->dSortStatus, sortParts * 256 * sizeof(uint64_t)));
-  CU_TRY(c, cudaMemset(c->dPreStatus, 0, preTiles * sizeof(uint64_t)));
-  CU_TRY(c, cudaMemset(c->dBinStatus, 0, binParts * sizeof(uint64_t)));
-  CU_TRY(c, cudaMemset(c->dSortStatus, 0, sortParts * 256 * sizeof(uint64_t)));
-  if(int rc = allocTileLists(c, std::max<uint64_t>(8 * n, 1u << 20)))
-    return rc;
-  c->uploaded  = true;
-  c->haveFrame = false;
+  // src/splat_set_manager_vk.cpp:2426-2517), one set per frame in flight
+  for(auto& s : c->slots)
+    if(int rc = allocSlotScene(c, s, n))
+      return rc;
+  c->uploaded = true;
+  c->nextSlot = 0;
   return VKGS_OK;
 }
 
@@ -538,14 +556,22 @@ int vkgs_render_async(vkgs_ctx* c, const vkgs_frame_params* fp)
 {
   if(!c || !fp)
     return VKGS_ERR_INVALID_ARGUMENT;
-  return enqueueFrame(c, *fp);
+  return enqueueFrame(c, *fp, nullptr, nullptr);
+}
+
+int vkgs_render_to_host_async(vkgs_ctx* c, const vkgs_frame_params* fp, float* host_rgba)
+{
+  if(!c || !fp || !host_rgba)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  return enqueueFrame(c, *fp, host_rgba, nullptr);
 }
 
 int vkgs_sync(vkgs_ctx* c)
 {
   if(!c)
     return VKGS_ERR_INVALID_ARGUMENT;
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if(int rc = syncAll(c))
+    return rc;
   return checkOverflow(c);
 }
 
@@ -553,16 +579,17 @@ int vkgs_last_frame_stats(vkgs_ctx* c, vkgs_outputs* out)
 {
   if(!c || !out)
     return VKGS_ERR_INVALID_ARGUMENT;
-  if(!c->haveFrame)
+  if(c->lastSlot < 0 || !c->slots[c->lastSlot].haveFrame)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "no frame rendered yet");
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
-  fillStats(c, out);
+  FrameSlot& s = c->slots[c->lastSlot];
+  CU_TRY(c, cudaStreamSynchronize(s.stream));
+  fillStats(c, s, out);
   return VKGS_OK;
 }
 
 const void* vkgs_device_framebuffer(const vkgs_ctx* c)
 {
-  return c ? c->dImage : nullptr;
+  return (c && c->lastSlot >= 0) ? c->slots[c->lastSlot].dImage : nullptr;
 }
 
 int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
@@ -571,24 +598,23 @@ int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
     return VKGS_ERR_INVALID_ARGUMENT;
   for(int attempt = 0; attempt < 3; attempt++)
   {
-    if(int rc = enqueueFrame(c, *fp))
+    int si = 0;
+    if(int rc = enqueueFrame(c, *fp, out->rgba, &si))
       return rc;
-    if(out->rgba)
-      CU_TRY(c, cudaMemcpyAsync(out->rgba, c->dImage, sizeof(float4) * static_cast<size_t>(fp->width) * fp->height,
-                                cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    FrameSlot& s = c->slots[si];
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
     const int rc = checkOverflow(c);
     if(rc == VKGS_ERR_OVERFLOW)
       continue;  // lists were regrown: run the frame again
     if(rc)
       return rc;
-    fillStats(c, out);
-    const uint64_t v = std::min<uint64_t>(out->visible_count, out->sorted_ids_capacity);
-    const uint32_t sel = c->hCounters->sortSrc[3] & 1u;
+    fillStats(c, s, out);
+    const uint64_t v   = std::min<uint64_t>(out->visible_count, out->sorted_ids_capacity);
+    const uint32_t sel = s.hCounters->sortSrc[3] & 1u;
     if(out->sorted_ids && v)
-      CU_TRY(c, cudaMemcpy(out->sorted_ids, c->dIds[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU_TRY(c, cudaMemcpy(out->sorted_ids, s.dIds[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if(out->sorted_keys && v)
-      CU_TRY(c, cudaMemcpy(out->sorted_keys, c->dKeys[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      CU_TRY(c, cudaMemcpy(out->sorted_keys, s.dKeys[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return VKGS_OK;
   }
   return fail(c, VKGS_ERR_OVERFLOW, "tile lists still overflow after regrowing");
@@ -596,10 +622,11 @@ int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
 
 int vkgs_read_records(vkgs_ctx* c, uint32_t* records12, uint64_t first, uint64_t count)
 {
-  if(!c || !records12 || !c->uploaded || first + count > c->set.count)
+  if(!c || !records12 || !c->uploaded || c->lastSlot < 0 || first + count > c->set.count)
     return VKGS_ERR_INVALID_ARGUMENT;
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
-  CU_TRY(c, cudaMemcpy(records12, c->dRecords + first * RECORD_WORDS, count * RECORD_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  FrameSlot& s = c->slots[c->lastSlot];
+  CU_TRY(c, cudaStreamSynchronize(s.stream));
+  CU_TRY(c, cudaMemcpy(records12, s.dRecords + first * RECORD_WORDS, count * RECORD_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return VKGS_OK;
 }
 
@@ -618,113 +645,6 @@ int vkgs_read_packed(vkgs_ctx* c, float* centers, float* cov6, float* rgba, floa
     CU_TRY(c, cudaMemcpy(rgba, c->dRgba, n * 16, cudaMemcpyDeviceToHost));
   if(sh && c->dSh)
     CU_TRY(c, cudaMemcpy(sh, c->dSh, n * 180, cudaMemcpyDeviceToHost));
-  return VKGS_OK;
-}
-
-int vkgs_sort_pairs(vkgs_ctx* c, const uint32_t* keys, const uint32_t* values, uint64_t n, uint32_t* keysOut, uint32_t* valuesOut,
-                    int repeats, float* msDevice)
-{
-  if(!c || (!keys && n) || (!values && n) || n > 0xfffff000ull)
-    return VKGS_ERR_INVALID_ARGUMENT;
-  if(msDevice)
-    *msDevice = 0.0f;
-  if(n == 0)
-    return VKGS_OK;
-  CU_TRY(c, cudaSetDevice(c->device));
-  repeats = std::max(repeats, 1);
-  uint32_t *dk[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr}, *dIn[2] = {nullptr, nullptr};
-  struct Ctl
-  {
-    uint32_t count;
-    uint32_t ticket[4];
-    uint32_t hist[4][256];
-  }* dCtl             = nullptr;
-  uint64_t*      dSt  = nullptr;
-  const uint64_t parts = (n + SORT_PART - 1) / SORT_PART;
-  auto           cleanup = [&]() {
-    for(int i = 0; i < 2; i++)
-      freeDev(dk[i]), freeDev(dv[i]), freeDev(dIn[i]);
-    freeDev(dCtl), freeDev(dSt);
-  };
-  cudaError_t e = cudaSuccess;
-  for(int i = 0; i < 2 && e == cudaSuccess; i++)
-  {
-    e = cudaMalloc(&dk[i], n * 4);
-    if(e == cudaSuccess)
-      e = cudaMalloc(&dv[i], n * 4);
-    if(e == cudaSuccess)
-      e = cudaMalloc(&dIn[i], n * 4);
-  }
-  if(e == cudaSuccess)
-    e = cudaMalloc(&dCtl, sizeof(Ctl));
-  if(e == cudaSuccess)
-    e = cudaMalloc(&dSt, parts * 256 * sizeof(uint64_t));
-  if(e == cudaSuccess)
-    e = cudaMemset(dSt, 0, parts * 256 * sizeof(uint64_t));
-  if(e == cudaSuccess)
-    e = cudaMemcpy(dIn[0], keys, n * 4, cudaMemcpyHostToDevice);
-  if(e == cudaSuccess)
-    e = cudaMemcpy(dIn[1], values, n * 4, cudaMemcpyHostToDevice);
-  if(e != cudaSuccess)
-  {
-    cleanup();
-    c->lastError = std::string("vkgs_sort_pairs alloc/upload: ") + cudaGetErrorString(e);
-    return VKGS_ERR_CUDA;
-  }
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  float total = 0.0f;
-  // private epoch space: this status array is local to the call
-  uint32_t epoch = 0;
-  for(int rep = 0; rep < repeats; rep++)
-  {
-    // restore the unsorted input (not timed), then time histogram + 4 passes
-    cudaMemcpyAsync(dk[0], dIn[0], n * 4, cudaMemcpyDeviceToDevice, c->stream);
-    cudaMemcpyAsync(dv[0], dIn[1], n * 4, cudaMemcpyDeviceToDevice, c->stream);
-    Ctl h{};
-    h.count = static_cast<uint32_t>(n);
-    cudaMemcpyAsync(dCtl, &h, sizeof(Ctl), cudaMemcpyHostToDevice, c->stream);
-    cudaStreamSynchronize(c->stream);
-    cudaEventRecord(e0, c->stream);
-    launchHistogram(dk[0], &dCtl->count, static_cast<uint32_t>(n), &dCtl->hist[0][0], 0, 4, c->stream);
-    c->launches++;
-    for(int p = 0; p < 4; p++)
-    {
-      SortPassArgs sa{};
-      sa.keys[0] = dk[p & 1], sa.keys[1] = dk[(p + 1) & 1];
-      sa.vals[0] = dv[p & 1], sa.vals[1] = dv[(p + 1) & 1];
-      sa.countPtr  = &dCtl->count;
-      sa.maxCount  = static_cast<uint32_t>(n);
-      sa.histogram = &dCtl->hist[p][0];
-      sa.status    = dSt;
-      sa.ticket    = &dCtl->ticket[p];
-      sa.epoch     = ++epoch;
-      sa.shift     = 8 * p;
-      launchSortPass(sa, c->stream);
-      c->launches++;
-    }
-    cudaEventRecord(e1, c->stream);
-    cudaEventSynchronize(e1);
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    total += ms;
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  e = cudaGetLastError();
-  if(e == cudaSuccess && keysOut)
-    e = cudaMemcpy(keysOut, dk[0], n * 4, cudaMemcpyDeviceToHost);
-  if(e == cudaSuccess && valuesOut)
-    e = cudaMemcpy(valuesOut, dv[0], n * 4, cudaMemcpyDeviceToHost);
-  cleanup();
-  if(e != cudaSuccess)
-  {
-    c->lastError = std::string("vkgs_sort_pairs: ") + cudaGetErrorString(e);
-    return VKGS_ERR_CUDA;
-  }
-  if(msDevice)
-    *msDevice = total / static_cast<float>(repeats);
   return VKGS_OK;
 }
 

@@ -1,0 +1,77 @@
+// context.hpp — the context object behind the C ABI (shared by context.cu and sort_api.cu)
+#pragma once
+#include <string>
+
+#include "kernels.hpp"
+#include "vkgs_b200.h"
+
+namespace vkgs {
+
+constexpr int MAX_FRAMES_IN_FLIGHT = 2;
+
+// Everything one in-flight frame owns. Two slots let frame N+1's front end (preprocess, sorts,
+// binning — latency-bound kernels that leave most issue slots idle) overlap frame N's blend on the
+// same GPU, like the frames-in-flight of the reference's swapchain loop.
+struct FrameSlot
+{
+  cudaStream_t   stream = nullptr;
+  uint32_t *     dKeys[2] = {nullptr, nullptr}, *dIds[2] = {nullptr, nullptr};
+  uint32_t*      dRecords    = nullptr;
+  FrameCounters* dCounters   = nullptr;
+  FrameCounters* hCounters   = nullptr;  // pinned; first 32 bytes are copied back every frame
+  uint64_t *     dPreStatus = nullptr, *dSortStatus = nullptr, *dBinStatus = nullptr, *dTileSortStatus = nullptr;
+  uint32_t *     dTileKeys[2] = {nullptr, nullptr}, *dTileVals[2] = {nullptr, nullptr};
+  uint64_t       tileCapacity = 0;
+  uint2*         dRanges      = nullptr;
+  float4*        dImage       = nullptr;
+  uint32_t       imgW = 0, imgH = 0;
+  cudaEvent_t    ev[VKGS_K_COUNT + 1]{};
+  cudaEvent_t    evDone     = nullptr;
+  bool           evRecorded = false;
+  bool           haveFrame  = false;
+  vkgs_frame_params lastFp{};
+};
+
+}  // namespace vkgs
+
+struct vkgs_ctx
+{
+  int          device     = 0;
+  cudaStream_t userStream = nullptr;  // optional: completion of every frame is made visible on it
+  std::string  lastError;
+  uint64_t     launches  = 0;
+  uint32_t     epoch     = 0;
+  bool         profiling = false;
+  int          framesInFlight = vkgs::MAX_FRAMES_IN_FLIGHT;
+  int          nextSlot  = 0;
+  int          lastSlot  = -1;
+
+  // scene (shared by all slots)
+  bool                 uploaded = false;
+  vkgs_options         opt{};
+  vkgs::DeviceSplatSet set{};
+  void *               dCenters = nullptr, *dCov = nullptr, *dScales = nullptr, *dRgba = nullptr, *dSh = nullptr;
+
+  vkgs::FrameSlot slots[vkgs::MAX_FRAMES_IN_FLIGHT];
+};
+
+#define CU_TRY(ctx, expr)                                                                                                      \
+  do                                                                                                                           \
+  {                                                                                                                            \
+    cudaError_t e_ = (expr);                                                                                                   \
+    if(e_ != cudaSuccess)                                                                                                      \
+    {                                                                                                                          \
+      (ctx)->lastError = std::string(#expr) + ": " + cudaGetErrorString(e_);                                                   \
+      return VKGS_ERR_CUDA;                                                                                                    \
+    }                                                                                                                          \
+  } while(0)
+
+namespace vkgs {
+template <typename T>
+inline void freeDev(T*& p)
+{
+  if(p)
+    cudaFree(p);
+  p = nullptr;
+}
+}  // namespace vkgs

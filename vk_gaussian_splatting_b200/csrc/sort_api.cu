@@ -1,0 +1,121 @@
+// sort_api.cu — stand-alone key/value radix sort entry point (vkgs_sort_pairs), the drop-in for
+// vrdxCmdSortKeyValueIndirect (3rdparty/vrdx/src/vk_radix_sort.cc:249-258). Same kernels as the
+// frame pipeline (k_radix_sort.cu); host in, host out, device time reported.
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "context.hpp"
+
+using namespace vkgs;
+
+extern "C" {
+
+int vkgs_sort_pairs(vkgs_ctx* c, const uint32_t* keys, const uint32_t* values, uint64_t n, uint32_t* keysOut, uint32_t* valuesOut,
+                    int repeats, float* msDevice)
+{
+  if(!c || (!keys && n) || (!values && n) || n > 0xfffff000ull)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(msDevice)
+    *msDevice = 0.0f;
+  if(n == 0)
+    return VKGS_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  repeats = std::max(repeats, 1);
+  uint32_t *dk[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr}, *dIn[2] = {nullptr, nullptr};
+  struct Ctl
+  {
+    uint32_t count;
+    uint32_t ticket[4];
+    uint32_t hist[4][256];
+  }* dCtl             = nullptr;
+  uint64_t*      dSt  = nullptr;
+  const uint64_t parts = (n + SORT_PART - 1) / SORT_PART;
+  auto           cleanup = [&]() {
+    for(int i = 0; i < 2; i++)
+      freeDev(dk[i]), freeDev(dv[i]), freeDev(dIn[i]);
+    freeDev(dCtl), freeDev(dSt);
+  };
+  cudaError_t e = cudaSuccess;
+  for(int i = 0; i < 2 && e == cudaSuccess; i++)
+  {
+    e = cudaMalloc(&dk[i], n * 4);
+    if(e == cudaSuccess)
+      e = cudaMalloc(&dv[i], n * 4);
+    if(e == cudaSuccess)
+      e = cudaMalloc(&dIn[i], n * 4);
+  }
+  if(e == cudaSuccess)
+    e = cudaMalloc(&dCtl, sizeof(Ctl));
+  if(e == cudaSuccess)
+    e = cudaMalloc(&dSt, parts * 256 * sizeof(uint64_t));
+  if(e == cudaSuccess)
+    e = cudaMemset(dSt, 0, parts * 256 * sizeof(uint64_t));
+  if(e == cudaSuccess)
+    e = cudaMemcpy(dIn[0], keys, n * 4, cudaMemcpyHostToDevice);
+  if(e == cudaSuccess)
+    e = cudaMemcpy(dIn[1], values, n * 4, cudaMemcpyHostToDevice);
+  if(e != cudaSuccess)
+  {
+    cleanup();
+    c->lastError = std::string("vkgs_sort_pairs alloc/upload: ") + cudaGetErrorString(e);
+    return VKGS_ERR_CUDA;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float total = 0.0f;
+  // private epoch space: this status array is local to the call
+  uint32_t epoch = 0;
+  for(int rep = 0; rep < repeats; rep++)
+  {
+    // restore the unsorted input (not timed), then time histogram + 4 passes
+    cudaMemcpyAsync(dk[0], dIn[0], n * 4, cudaMemcpyDeviceToDevice, c->slots[0].stream);
+    cudaMemcpyAsync(dv[0], dIn[1], n * 4, cudaMemcpyDeviceToDevice, c->slots[0].stream);
+    Ctl h{};
+    h.count = static_cast<uint32_t>(n);
+    cudaMemcpyAsync(dCtl, &h, sizeof(Ctl), cudaMemcpyHostToDevice, c->slots[0].stream);
+    cudaStreamSynchronize(c->slots[0].stream);
+    cudaEventRecord(e0, c->slots[0].stream);
+    launchHistogram(dk[0], &dCtl->count, static_cast<uint32_t>(n), &dCtl->hist[0][0], 0, 4, c->slots[0].stream);
+    c->launches++;
+    for(int p = 0; p < 4; p++)
+    {
+      SortPassArgs sa{};
+      sa.keys[0] = dk[p & 1], sa.keys[1] = dk[(p + 1) & 1];
+      sa.vals[0] = dv[p & 1], sa.vals[1] = dv[(p + 1) & 1];
+      sa.countPtr  = &dCtl->count;
+      sa.maxCount  = static_cast<uint32_t>(n);
+      sa.histogram = &dCtl->hist[p][0];
+      sa.status    = dSt;
+      sa.ticket    = &dCtl->ticket[p];
+      sa.epoch     = ++epoch;
+      sa.shift     = 8 * p;
+      launchSortPass(sa, c->slots[0].stream);
+      c->launches++;
+    }
+    cudaEventRecord(e1, c->slots[0].stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  e = cudaGetLastError();
+  if(e == cudaSuccess && keysOut)
+    e = cudaMemcpy(keysOut, dk[0], n * 4, cudaMemcpyDeviceToHost);
+  if(e == cudaSuccess && valuesOut)
+    e = cudaMemcpy(valuesOut, dv[0], n * 4, cudaMemcpyDeviceToHost);
+  cleanup();
+  if(e != cudaSuccess)
+  {
+    c->lastError = std::string("vkgs_sort_pairs: ") + cudaGetErrorString(e);
+    return VKGS_ERR_CUDA;
+  }
+  if(msDevice)
+    *msDevice = total / static_cast<float>(repeats);
+  return VKGS_OK;
+}
+
+}  // extern "C"
