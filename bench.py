@@ -177,29 +177,17 @@ def main():
     import vk_gaussian_splatting_b200 as g
     from vk_gaussian_splatting_b200 import _abi as A
 
-    rank, local, world = dist_env()
+    from vk_gaussian_splatting_b200 import farm as F
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    rank, local, world = dist_env()
     torch.cuda.set_device(local)
-    use_dist = world > 1
-    if use_dist:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if use_dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if not use_dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    farm = F.Farm(backend="nccl", device="cuda")  # no-op control plane when world == 1
+    barrier, max_over_ranks = farm.barrier, farm.max_over_ranks
 
     scene = g.synth_scene(N_SPLATS, SH_DEGREE, SEED)  # every rank regenerates the scene from the seed
-    cam = g.orbit_camera(rank % 8, 8)                 # rank 0 = the reference default camera
+    cam = F.view_for_rank(rank, 8)                    # rank 0 = the reference default camera
     fp = g.frame_params(cam, WIDTH, HEIGHT)
     opt = g.default_options(front_to_back=1, transmittance_epsilon=EPS)
 
@@ -308,9 +296,7 @@ def main():
         else:
             line["cpu_baseline"] = None
     r.close()
-    if use_dist:
-        dist.barrier()
-        dist.destroy_process_group()
+    farm.close()
     if line is not None:
         print(json.dumps(line), flush=True)
     return 0
