@@ -7,7 +7,7 @@
 
 namespace vkgs {
 
-constexpr int MAX_FRAMES_IN_FLIGHT = 2;
+constexpr int MAX_FRAMES_IN_FLIGHT = 4;
 
 // Everything one in-flight frame owns. Two slots let frame N+1's front end (preprocess, sorts,
 // binning — latency-bound kernels that leave most issue slots idle) overlap frame N's blend on the

@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
   const uint32_t px = tileX0 + (warp & 1u) * 8u + (lane & 7u), py = tileY0 + (warp >> 1) * 4u + (lane >> 3);
   const bool     inside = px < a.width && py < a.height;
   const float    fx = static_cast<float>(px) + 0.5f, fy = static_cast<float>(py) + 0.5f;
+  // centre of this warp's 8x4 block of pixel centres (half extents 3.5 x 1.5)
+  const float    blockCx = static_cast<float>(tileX0 + (warp & 1u) * 8u) + 4.0f, blockCy = static_cast<float>(tileY0 + (warp >> 1) * 4u) + 2.0f;
 
   const uint2 range = a.ranges[tile];
   float       c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -147,8 +149,21 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
 
     for(uint32_t chunk = 0; chunk < n; chunk += 32)
     {
+      // Lane l tests splat chunk+l against THIS warp's 8x4 pixel block: first the precomputed bbox
+      // mask, then a separating-axis test along the splat's own axes — over the block the
+      // interpolated fragPos component f_i = dot(p - c, w_i) stays within f_i(centre) +- e_i, and
+      // |f_i| > sqrt(8) everywhere means A > 8 everywhere. Conservative, and amortised 32x.
       const uint32_t j   = chunk + lane;
-      const bool     hit = j < n && ((ldsU32(sbase + j * REC_BYTES + 40) >> warp) & 1u);
+      bool           hit = j < n && ((ldsU32(sbase + j * REC_BYTES + 40) >> warp) & 1u);
+      if(hit)
+      {
+        const float4 qa = ldsV4(sbase + j * REC_BYTES);
+        const float2 qb = ldsV2(sbase + j * REC_BYTES + 16);
+        const float  ddx = blockCx - qa.x, ddy = blockCy - qa.y;
+        const float  f1 = fabsf(ddx * qa.z + ddy * qa.w) - (3.5f * fabsf(qa.z) + 1.5f * fabsf(qa.w));
+        const float  f2 = fabsf(ddx * qb.x + ddy * qb.y) - (3.5f * fabsf(qb.x) + 1.5f * fabsf(qb.y));
+        hit = fmaxf(f1, f2) <= 2.829f;  // sqrt(8) = 2.82843 plus a safety margin for rounding
+      }
       unsigned       m   = __ballot_sync(FULL_MASK, hit);
       const uint32_t chunkAddr = sbase + chunk * REC_BYTES;
       while(m)
