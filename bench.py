@@ -222,24 +222,30 @@ def main():
     fps = world * args.steps / (ms_total / 1000.0)
 
     # ---- end to end: host params in, RGBA frame to pinned host memory out, synchronous call ---------
-    host_imgs = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    host_np = [t.numpy() for t in host_imgs]
-    e2e_steps = max(10, min(args.steps, 100))
-    for i in range(3):
-        r.render_to_host_async(fp, host_np[i % 2])
-    r.sync()
-    barrier()
-    e0.record(stream)
-    for i in range(e2e_steps):
-        # the call a user makes: host frame parameters in, finished RGBA frame copied to pinned host
-        # memory out, every step; two frames in flight so step i's copy overlaps step i+1's kernels
-        r.render_to_host_async(fp, host_np[i % 2])
-    e1.record(stream)
-    r.sync()
-    torch.cuda.synchronize()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    fps_e2e = world * e2e_steps / (ms_e2e / 1000.0)
+    def e2e_run(target_fmt, torch_dtype):
+        r.set_target_format(target_fmt)
+        host_imgs = [torch.empty((HEIGHT, WIDTH, 4), dtype=torch_dtype, pin_memory=True) for _ in range(2)]
+        host_np = [t.numpy() for t in host_imgs]
+        steps = max(10, min(args.steps, 100))
+        for i in range(3):
+            r.render_to_host_async(fp, host_np[i % 2])
+        r.sync()
+        barrier()
+        e0.record(stream)
+        for i in range(steps):
+            # the call a user makes: host frame parameters in, finished RGBA frame copied to pinned host
+            # memory out, every step; two frames in flight so step i's copy overlaps step i+1's kernels
+            r.render_to_host_async(fp, host_np[i % 2])
+        e1.record(stream)
+        r.sync()
+        torch.cuda.synchronize()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        return world * steps / (ms / 1000.0), ms / steps, steps, host_imgs[0].element_size() * WIDTH * HEIGHT * 4
+
+    # headline e2e: the reference's default colour target (COLOR_MAIN = R16G16B16A16_SFLOAT); fp32 target alongside
+    fps_e2e, ms_e2e_step, e2e_steps, d2h_bytes = e2e_run(A.FORMAT_FLOAT16, torch.float16)
+    fps_e2e32, ms_e2e32_step, _, d2h_bytes32 = e2e_run(A.FORMAT_FLOAT32, torch.float32)
 
     # ---- per-kernel profile (separate frames, cudaEvents around every launch on the launch stream) --
     r.set_frames_in_flight(1)  # per-kernel times need one frame at a time (no cross-frame overlap)
@@ -284,7 +290,9 @@ def main():
             "frame_algorithmic_bytes": st.bytes_algorithmic, "frame_hbm_gbs": whole, "frame_hbm_frac": whole / peak,
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": C.sizeof(A.FrameParams),
-                    "d2h_bytes_per_step": WIDTH * HEIGHT * 16 + 16, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+                    "d2h_bytes_per_step": d2h_bytes + 32, "steps": e2e_steps, "ms_per_step": ms_e2e_step,
+                    "target": "RGBA16F (reference default COLOR_MAIN format), pinned host buffer, 2 frames in flight",
+                    "fp32_target": {"value": fps_e2e32, "ms_per_step": ms_e2e32_step, "d2h_bytes_per_step": d2h_bytes32 + 32}},
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_sorter_baseline(scene, cam)

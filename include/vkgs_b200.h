@@ -89,7 +89,11 @@ typedef struct vkgs_options
   float    transmittance_epsilon;    /* front_to_back only: stop compositing a pixel once the
                                         remaining transmittance 1-A drops below this (0 = never,
                                         the reference's exact behaviour). Error bound: eps*max|rgb|. */
-  uint32_t _reserved[6];
+  uint32_t target_format;            /* colour target of the frame: VKGS_FORMAT_FLOAT32 (default; parity tests),
+                                        VKGS_FORMAT_FLOAT16 (the reference's default COLOR_MAIN format,
+                                        R16G16B16A16_SFLOAT, src/gaussian_splatting.h:338) or VKGS_FORMAT_UINT8
+                                        (R8G8B8A8_UNORM). Blending is always fp32; the target is rounded once. */
+  uint32_t _reserved[5];             /* [4]: profiling ablation flags (0 in production) */
 } vkgs_options;
 
 /* Per-frame parameters: the fields of shaderio::FrameInfo the path reads
@@ -130,7 +134,8 @@ typedef struct vkgs_camera
  * "Rasterization" (src/gaussian_splatting.cpp:1324,1346,567). */
 typedef struct vkgs_outputs
 {
-  float*    rgba;       /* HOST, W*H*4 fp32, row 0 = top; may be NULL (frame stays on the device) */
+  float*    rgba;       /* HOST, W*H*4 elements of the target format (fp32 by default; fp16/u8 bit
+                           patterns when options.target_format says so), row 0 = top; may be NULL */
   uint32_t* sorted_ids; /* HOST, optional, capacity sorted_ids_capacity */
   uint32_t* sorted_keys;/* HOST, optional, same capacity */
   uint64_t  sorted_ids_capacity;
@@ -191,9 +196,11 @@ VKGS_API int vkgs_render(vkgs_ctx* ctx, const vkgs_frame_params* fp, vkgs_output
  * in flight on two internal streams (the frames-in-flight of the reference's swapchain loop,
  * nvpro_core2/nvapp/application.cpp:517-548); completion order == submission order. */
 VKGS_API int vkgs_render_async(vkgs_ctx* ctx, const vkgs_frame_params* fp);
-/* Same, plus an asynchronous copy of the finished fp32 RGBA frame to PINNED host memory
- * (W*H*4 floats); the buffer is valid after vkgs_sync (or after the caller's stream reaches it). */
-VKGS_API int vkgs_render_to_host_async(vkgs_ctx* ctx, const vkgs_frame_params* fp, float* host_rgba);
+/* Same, plus an asynchronous copy of the finished RGBA frame (W*H*4 elements of the target
+ * format) to PINNED host memory; valid after vkgs_sync (or once the caller's stream reaches it). */
+VKGS_API int vkgs_render_to_host_async(vkgs_ctx* ctx, const vkgs_frame_params* fp, void* host_rgba);
+/* Change the colour target format (VKGS_FORMAT_*) for subsequent frames without re-uploading. */
+VKGS_API int vkgs_set_target_format(vkgs_ctx* ctx, uint32_t target_format);
 /* 1 = strictly one frame at a time, 2 (default) = overlap consecutive frames. */
 VKGS_API int vkgs_set_frames_in_flight(vkgs_ctx* ctx, int frames);
 VKGS_API int vkgs_sync(vkgs_ctx* ctx);

@@ -289,3 +289,29 @@ def test_caller_stream_sees_finished_frames(gpu_renderer):
     st = r.last_frame_stats()
     assert st.visible_count > 40_000
     r.close()
+
+
+def test_colour_target_formats(gpu_renderer):
+    """RGBA16F (the reference's default COLOR_MAIN format) and RGBA8_UNORM targets: blended in fp32,
+    rounded once. fp16: within one half-precision ulp of the oracle's fp32 frame; unorm8: within 1 LSB."""
+    s = g.synth_scene(80_000, 3, 0x3D65000E)
+    cam = g.default_camera()
+    r = gpu_renderer
+    r.upload(s, g.default_options(front_to_back=1))
+    fp = g.frame_params(cam, 640, 360)
+    ref32, _, _, _ = r.render(fp)
+    oimg, _, _, _ = O.render(O.Packed(s), O.frame_params(cam, 640, 360), O.default_options(front_to_back=1))
+    assert np.abs(ref32 - oimg).max() <= RGBA_TOL
+    r.set_target_format(A.FORMAT_FLOAT16)
+    h, _, _, _ = r.render(fp)
+    assert h.dtype == np.float16 and np.array_equal(h, ref32.astype(np.float16))  # exactly the RN rounding of the fp32 frame
+    want = oimg.astype(np.float16)
+    ulp = np.abs(h.view(np.int16).astype(np.int32) - want.view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1
+    r.set_target_format(A.FORMAT_UINT8)
+    u, _, _, _ = r.render(fp)
+    want8 = np.rint(np.clip(oimg, 0, 1) * 255.0)
+    assert u.dtype == np.uint8 and np.abs(u.astype(np.int32) - want8).max() <= 1
+    r.set_target_format(A.FORMAT_FLOAT32)
+    again, _, _, _ = r.render(fp)
+    assert np.array_equal(again, ref32)

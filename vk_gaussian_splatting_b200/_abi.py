@@ -42,7 +42,7 @@ class Options(C.Structure):
     _fields_ = [("frustum_culling_mode", C.c_uint32), ("size_culling_mode", C.c_uint32), ("front_to_back", C.c_uint32),
                 ("ms_antialiasing", C.c_uint32), ("sh_format", C.c_uint32), ("rgba_format", C.c_uint32),
                 ("point_cloud_mode", C.c_uint32), ("show_sh_only", C.c_uint32), ("disable_opacity_gaussian", C.c_uint32),
-                ("transmittance_epsilon", C.c_float), ("_reserved", C.c_uint32 * 6)]
+                ("transmittance_epsilon", C.c_float), ("target_format", C.c_uint32), ("_reserved", C.c_uint32 * 5)]
 
 
 class FrameParams(C.Structure):
@@ -81,8 +81,9 @@ SYMBOLS = {
     "vkgs_default_camera": (None, [C.POINTER(Camera)]),
     "vkgs_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.POINTER(Outputs)]),
     "vkgs_render_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams)]),
-    "vkgs_render_to_host_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), f32p]),
+    "vkgs_render_to_host_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_void_p]),
     "vkgs_set_frames_in_flight": (C.c_int, [C.c_void_p, C.c_int]),
+    "vkgs_set_target_format": (C.c_int, [C.c_void_p, C.c_uint32]),
     "vkgs_sync": (C.c_int, [C.c_void_p]),
     "vkgs_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "vkgs_last_frame_stats": (C.c_int, [C.c_void_p, C.POINTER(Outputs)]),

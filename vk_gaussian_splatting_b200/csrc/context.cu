@@ -143,7 +143,7 @@ void frameConstants(const vkgs_frame_params& fp, float mv[16], float camModel[3]
 }
 
 // Enqueue one frame on the next slot; optionally a device->host copy of the finished frame.
-int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, float* hostRgba, int* slotOut)
+int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* slotOut)
 {
   if(!c->uploaded)
     return fail(c, VKGS_ERR_NOT_UPLOADED, "vkgs_render before vkgs_upload");
@@ -220,7 +220,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, float* hostRgba, int*
   ba.status     = s.dBinStatus;
   ba.epoch      = nextEpoch(c);
   ba.ticketSlot = 5;
-  ba.debugFlags = c->opt._reserved[5];
+  ba.debugFlags = c->opt._reserved[4];
   launchBinEmit(ba, st);
   c->launches++;
   mark(VKGS_K_BIN_EMIT + 1);
@@ -253,6 +253,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, float* hostRgba, int*
   bl.ranges                 = s.dRanges;
   bl.records                = s.dRecords;
   bl.image                  = s.dImage;
+  bl.targetFormat           = c->opt.target_format;
   bl.width                  = fp.width;
   bl.height                 = fp.height;
   bl.tilesX                 = tx;
@@ -267,7 +268,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, float* hostRgba, int*
 
   CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, 32, cudaMemcpyDeviceToHost, st));
   if(hostRgba)
-    CU_TRY(c, cudaMemcpyAsync(hostRgba, s.dImage, sizeof(float4) * static_cast<size_t>(fp.width) * fp.height, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaMemcpyAsync(hostRgba, s.dImage, 4ull * formatSize(c->opt.target_format) * fp.width * fp.height, cudaMemcpyDeviceToHost, st));
   if(c->userStream)
   {
     // completion of this frame becomes visible on the caller's stream, in submission order
@@ -467,6 +468,16 @@ int vkgs_set_stream(vkgs_ctx* c, void* cuda_stream)
   return VKGS_OK;
 }
 
+int vkgs_set_target_format(vkgs_ctx* c, uint32_t target_format)
+{
+  if(!c || target_format > VKGS_FORMAT_UINT8)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(int rc = syncAll(c))
+    return rc;
+  c->opt.target_format = target_format;
+  return VKGS_OK;
+}
+
 int vkgs_set_frames_in_flight(vkgs_ctx* c, int frames)
 {
   if(!c || frames < 1 || frames > MAX_FRAMES_IN_FLIGHT)
@@ -509,6 +520,8 @@ int vkgs_upload(vkgs_ctx* c, const vkgs_splat_set_view* set, const vkgs_options*
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "splat count must be in 1..2^31-1");
   if(opt.frustum_culling_mode > VKGS_FRUSTUM_CULLING_AT_RASTER)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad frustum_culling_mode");
+  if(opt.target_format > VKGS_FORMAT_UINT8)
+    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad target_format");
   CU_TRY(c, cudaSetDevice(c->device));
   if(int rc = syncAll(c))
     return rc;
@@ -559,7 +572,7 @@ int vkgs_render_async(vkgs_ctx* c, const vkgs_frame_params* fp)
   return enqueueFrame(c, *fp, nullptr, nullptr);
 }
 
-int vkgs_render_to_host_async(vkgs_ctx* c, const vkgs_frame_params* fp, float* host_rgba)
+int vkgs_render_to_host_async(vkgs_ctx* c, const vkgs_frame_params* fp, void* host_rgba)
 {
   if(!c || !fp || !host_rgba)
     return VKGS_ERR_INVALID_ARGUMENT;

@@ -23,7 +23,7 @@ struct FrameSlot
   uint32_t *     dTileKeys[2] = {nullptr, nullptr}, *dTileVals[2] = {nullptr, nullptr};
   uint64_t       tileCapacity = 0;
   uint2*         dRanges      = nullptr;
-  float4*        dImage       = nullptr;
+  void*          dImage       = nullptr;  // [H][W] RGBA in the target format (allocated for fp32, the largest)
   uint32_t       imgW = 0, imgH = 0;
   cudaEvent_t    ev[VKGS_K_COUNT + 1]{};
   cudaEvent_t    evDone     = nullptr;

@@ -17,6 +17,8 @@
 // so the `A > 8` discard is bit-exact. opacity uses the SFU ex2 for speed; whenever that value is
 // within a guard band of the 1/255 discard threshold it is recomputed with the same fixed-sequence
 // expf the oracle uses, so the discard decision is exact too and values differ by a few ulp only.
+#include <cuda_fp16.h>
+
 #include "device_common.cuh"
 #include "kernels.hpp"
 
@@ -217,7 +219,26 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
     }
   }
   if(inside)
-    a.image[static_cast<uint64_t>(py) * a.width + px] = make_float4(c0, c1, c2, FTB ? 1.0f - acc : acc);
+  {
+    // the colour target is rounded ONCE from the fp32 accumulators (the reference's ROP rounds after
+    // every blend in the target format)
+    const uint64_t o  = static_cast<uint64_t>(py) * a.width + px;
+    const float    al = FTB ? 1.0f - acc : acc;
+    if(a.targetFormat == VKGS_FORMAT_FLOAT32)
+      static_cast<float4*>(a.image)[o] = make_float4(c0, c1, c2, al);
+    else if(a.targetFormat == VKGS_FORMAT_FLOAT16)
+    {
+      const __half2 lo = __floats2half2_rn(c0, c1), hi = __floats2half2_rn(c2, al);
+      static_cast<uint2*>(a.image)[o] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+    else
+    {
+      // R8G8B8A8_UNORM: clamp to [0,1], scale, round to nearest
+      const uint32_t r = __float2uint_rn(__saturatef(c0) * 255.0f), gch = __float2uint_rn(__saturatef(c1) * 255.0f),
+                     b = __float2uint_rn(__saturatef(c2) * 255.0f), aa = __float2uint_rn(__saturatef(al) * 255.0f);
+      static_cast<uint32_t*>(a.image)[o] = r | (gch << 8) | (b << 16) | (aa << 24);
+    }
+  }
 }
 
 }  // namespace

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
       bulk_copy_g2s(sm.sh, static_cast<const unsigned char*>(a.set.sh) + first * 45 * shElem, PRE_TILE * 45 * shElem, &sm.mbarB);
   }
   mbar_wait(&sm.mbarA, 0);
-  const uint32_t ablate = a.opt._reserved[5];
+  const uint32_t ablate = a.opt._reserved[4];
 
   const uint64_t id    = first + tid;
   const bool     inSet = id < a.set.count;

@@ -116,7 +116,8 @@ struct BlendArgs
   const uint32_t* tileVals;  // tile-sorted splat ids
   const uint2*    ranges;    // [tiles] (begin,end) into tileVals
   const uint32_t* records;
-  float4*         image;     // [H][W] RGBA fp32
+  void*           image;     // [H][W] RGBA in targetFormat (float4 / half4 / uchar4)
+  uint32_t        targetFormat;
   uint32_t        width, height, tilesX, tilesY;
   uint32_t        frontToBack;
   uint32_t        disableOpacityGaussian;
