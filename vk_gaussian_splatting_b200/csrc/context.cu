@@ -5,7 +5,7 @@
 // with every data-dependent size (V, tile-pair count) read on the device — no host round trip
 // inside a frame:
 //   memset(control block) -> preprocess -> <=4 x sort pass -> bin emit -> 2 x tile sort pass
-//   -> tile ranges -> blend
+//   (the second also records the per-tile list ranges) -> blend
 // Up to two frames are in flight on two internal streams (FrameSlot), so one frame's latency-bound
 // front end overlaps the previous frame's blend.
 #include <algorithm>
@@ -101,7 +101,7 @@ int ensureTargets(vkgs_ctx* c, FrameSlot& s, uint32_t w, uint32_t h)
     freeDev(s.dImage);
     freeDev(s.dRanges);
     CU_TRY(c, cudaMalloc(&s.dImage, sizeof(float4) * static_cast<size_t>(w) * h));
-    CU_TRY(c, cudaMalloc(&s.dRanges, sizeof(uint2) * tx * ty));
+    CU_TRY(c, cudaMalloc(&s.dRanges, 2 * sizeof(uint32_t) * tx * ty));
     s.imgW = w, s.imgH = h;
   }
   return VKGS_OK;
@@ -163,7 +163,9 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   };
 
   CU_TRY(c, cudaMemsetAsync(s.dCounters, 0, sizeof(FrameCounters), st));
-  CU_TRY(c, cudaMemsetAsync(s.dRanges, 0, sizeof(uint2) * tx * ty, st));
+  // tile list ranges: begin = 0xffffffff, end = 0 (two arrays, two byte-pattern memsets)
+  CU_TRY(c, cudaMemsetAsync(s.dRanges, 0xff, sizeof(uint32_t) * tx * ty, st));
+  CU_TRY(c, cudaMemsetAsync(s.dRanges + tx * ty, 0, sizeof(uint32_t) * tx * ty, st));
   mark(0);
 
   // ---- "GPU Dist" (+ the per-splat half of "Rasterization", fused) -----------------------------
@@ -239,18 +241,22 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     sa.ticket    = &s.dCounters->ticket[6 + p];
     sa.epoch     = nextEpoch(c);
     sa.shift     = 8 * p;
+    if(p == 1)
+    {
+      sa.rangeBegin = s.dRanges;
+      sa.rangeEnd   = s.dRanges + tx * ty;
+    }
     launchSortPass(sa, st);
     c->launches++;
     mark(VKGS_K_TILE_SORT0 + p + 1);
   }
 
-  launchTileRanges(s.dTileKeys[0], s.dCounters, static_cast<uint32_t>(s.tileCapacity), s.dRanges, st);
-  c->launches++;
-  mark(VKGS_K_TILE_RANGES + 1);
+  mark(VKGS_K_TILE_RANGES + 1);  // (tile ranges are recorded by the last tile-sort pass)
 
   BlendArgs bl{};
   bl.tileVals               = s.dTileVals[0];
-  bl.ranges                 = s.dRanges;
+  bl.rangeBegin             = s.dRanges;
+  bl.rangeEnd               = s.dRanges + tx * ty;
   bl.records                = s.dRecords;
   bl.image                  = s.dImage;
   bl.targetFormat           = c->opt.target_format;

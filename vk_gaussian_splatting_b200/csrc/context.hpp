@@ -22,7 +22,7 @@ struct FrameSlot
   uint64_t *     dPreStatus = nullptr, *dSortStatus = nullptr, *dBinStatus = nullptr, *dTileSortStatus = nullptr;
   uint32_t *     dTileKeys[2] = {nullptr, nullptr}, *dTileVals[2] = {nullptr, nullptr};
   uint64_t       tileCapacity = 0;
-  uint2*         dRanges      = nullptr;
+  uint32_t*      dRanges      = nullptr;  // [2][tiles]: list begin, list end
   void*          dImage       = nullptr;  // [H][W] RGBA in the target format (allocated for fp32, the largest)
   uint32_t       imgW = 0, imgH = 0;
   cudaEvent_t    ev[VKGS_K_COUNT + 1]{};

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
   // centre of this warp's 8x4 block of pixel centres (half extents 3.5 x 1.5)
   const float    blockCx = static_cast<float>(tileX0 + (warp & 1u) * 8u) + 4.0f, blockCy = static_cast<float>(tileY0 + (warp >> 1) * 4u) + 2.0f;
 
-  const uint2 range = a.ranges[tile];
+  const uint2 range = make_uint2(a.rangeBegin[tile], a.rangeEnd[tile]);  // empty tile: begin > end
   float       c0 = 0.f, c1 = 0.f, c2 = 0.f;
   float       acc = FTB ? 1.0f : 0.0f;  // FTB: transmittance T = 1 - A_dst;  BTF: sum of alphas
   bool        done = !inside;

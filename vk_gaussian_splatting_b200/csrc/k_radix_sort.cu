@@ -219,68 +219,64 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
       const uint32_t dst   = sm.globalBase[digit] + (j - sm.digitStart[digit]);
       keysOut[dst]         = k;
       valsOut[dst]         = sm.stageVals[j];
+      if(a.rangeBegin)
+      {
+        // equal keys are contiguous in the staged (block-sorted) order: the input of the last pass is
+        // ordered by the low digit, so inside every high-digit run the full key is non-decreasing
+        if(j == 0 || sm.stageKeys[j - 1] != k)
+          atomicMin(a.rangeBegin + k, dst);
+        if(j + 1 == valid || sm.stageKeys[j + 1] != k)
+          atomicMax(a.rangeEnd + k, dst + 1u);
+      }
     }
   }
   VKGS_TL(part, 8);
 }
 
-// Digit histograms of all passes in one sweep over the keys. No shared-memory atomics (2 cycles
-// per lane on this part): every warp owns a private 256-bin table per pass and counts a row of 32
-// keys with eight ballots (match_digit) — the lowest lane of each group of equal digits adds the group size with a
-// plain read-modify-write. Tables are reduced per block and flushed with one global atomic per
-// non-empty bin (a few hundred blocks at most).
-constexpr int HIST_THREADS = 256;
-constexpr int HIST_WARPS   = HIST_THREADS / 32;
+// Digit histograms of all passes in one sweep over the keys (stand-alone sort only: the frame
+// pipeline produces its histograms inside the kernels that write the keys). Each thread reads 16
+// keys with 16-byte loads and counts every digit with a shared-memory atomic into one of
+// HIST_COPIES block-private copies of the table (lane-interleaved, which spreads same-digit
+// collisions); copies are reduced at the end and flushed with one global atomic per non-empty bin.
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_COPIES  = 4;
 
 template <int PASSES>
 __global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t* __restrict__ keys, const uint32_t* countPtr,
                                                             uint32_t* hist, int firstShift)
 {
-  __shared__ uint32_t s[HIST_WARPS][PASSES][256];
-  const unsigned      tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  for(int i = tid; i < HIST_WARPS * PASSES * 256; i += HIST_THREADS)
+  __shared__ uint32_t s[HIST_COPIES][PASSES][256];
+  const unsigned      tid = threadIdx.x;
+  for(int i = tid; i < HIST_COPIES * PASSES * 256; i += HIST_THREADS)
     (&s[0][0][0])[i] = 0u;
   __syncthreads();
   const uint32_t count = *countPtr;
-  // each warp walks rows of 32 keys, 4 rows per trip for memory-level parallelism
-  const uint64_t warpsTotal = static_cast<uint64_t>(gridDim.x) * HIST_WARPS;
-  const uint64_t warpId     = static_cast<uint64_t>(blockIdx.x) * HIST_WARPS + warp;
-  for(uint64_t base = warpId * 128; base < count; base += warpsTotal * 128)
+  uint32_t (*mine)[256] = s[tid % HIST_COPIES];
+  const uint64_t vecs   = count / 4;
+  const uint4*   k4     = reinterpret_cast<const uint4*>(keys);
+  for(uint64_t i = static_cast<uint64_t>(blockIdx.x) * HIST_THREADS + tid; i < vecs; i += static_cast<uint64_t>(gridDim.x) * HIST_THREADS)
   {
-    uint32_t k[4];
-    bool     ok[4];
+    const uint4    v    = k4[i];
+    const uint32_t k[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for(int r = 0; r < 4; r++)
-    {
-      const uint64_t i = base + r * 32 + lane;
-      ok[r]            = i < count;
-      k[r]             = ok[r] ? keys[i] : 0u;
-    }
-#pragma unroll
-    for(int r = 0; r < 4; r++)
-    {
-      // all 32 lanes take part in the ballots (full-mask votes are the fast path); lanes past the
-      // end of the input are masked out of the peer sets afterwards
-      const unsigned active = __ballot_sync(FULL_MASK, ok[r]);
-      if(active == 0u)
-        break;
+    for(int j = 0; j < 4; j++)
 #pragma unroll
       for(int p = 0; p < PASSES; p++)
-      {
-        const uint32_t d     = (k[r] >> (firstShift + 8 * p)) & 0xffu;
-        const unsigned peers = match_digit<8>(FULL_MASK, d) & active;
-        if(ok[r] && lane == static_cast<unsigned>(__ffs(peers) - 1))
-          s[warp][p][d] += __popc(peers);
-      }
-    }
+        atomicAdd(&mine[p][(k[j] >> (firstShift + 8 * p)) & 0xffu], 1u);
+  }
+  if(blockIdx.x == 0 && tid < (count & 3u))
+  {
+    const uint32_t kk = keys[vecs * 4 + tid];
+    for(int p = 0; p < PASSES; p++)
+      atomicAdd(&mine[p][(kk >> (firstShift + 8 * p)) & 0xffu], 1u);
   }
   __syncthreads();
   for(int i = tid; i < PASSES * 256; i += HIST_THREADS)
   {
     uint32_t v = 0;
 #pragma unroll
-    for(int w = 0; w < HIST_WARPS; w++)
-      v += (&s[w][0][0])[i];
+    for(int c = 0; c < HIST_COPIES; c++)
+      v += (&s[c][0][0])[i];
     if(v)
       atomicAdd(hist + i, v);
   }
@@ -300,7 +296,7 @@ void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t ma
                      cudaStream_t stream)
 {
   uint32_t blocks = (maxCount + HIST_THREADS * 16 - 1) / (HIST_THREADS * 16);
-  blocks          = blocks < 1 ? 1 : (blocks > 148 * 2 ? 148 * 2 : blocks);
+  blocks          = blocks < 1 ? 1 : (blocks > 148 * 4 ? 148 * 4 : blocks);
   if(passes == 4)
     k_histogram<4><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, hist, firstShift);
   else if(passes == 2)

@@ -80,6 +80,10 @@ struct SortPassArgs
   uint32_t*       ticket;
   uint32_t        epoch;
   int             shift;
+  // Final pass of the tile sort only: every run of equal (full) keys in the output is a tile's list;
+  // the scatter records its [begin,end) with atomicMin/atomicMax (arrays pre-set to 0xffffffff / 0).
+  uint32_t*       rangeBegin;
+  uint32_t*       rangeEnd;
 };
 
 void launchSortPass(const SortPassArgs& args, cudaStream_t stream);
@@ -108,13 +112,12 @@ struct BinArgs
 
 void launchBinEmit(const BinArgs& args, cudaStream_t stream);
 
-void launchTileRanges(const uint32_t* tileKeys, const FrameCounters* counters, uint32_t capacity, uint2* ranges,
-                      cudaStream_t stream);
 
 struct BlendArgs
 {
   const uint32_t* tileVals;  // tile-sorted splat ids
-  const uint2*    ranges;    // [tiles] (begin,end) into tileVals
+  const uint32_t* rangeBegin;  // [tiles] first entry of the tile's list in tileVals (0xffffffff = empty)
+  const uint32_t* rangeEnd;    // [tiles] one past the last entry (0 = empty)
   const uint32_t* records;
   void*           image;     // [H][W] RGBA in targetFormat (float4 / half4 / uchar4)
   uint32_t        targetFormat;
