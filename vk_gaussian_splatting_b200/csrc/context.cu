@@ -243,6 +243,11 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     sa.shift     = 8 * p;
     if(p == 1)
     {
+      // high digit of a tile id: only ceil(log2(tiles)) - 8 significant bits
+      uint32_t bits = 0;
+      while((1u << (8 + bits)) < tx * ty)
+        bits++;
+      sa.digitBits  = static_cast<int>(bits ? bits : 1);
       sa.rangeBegin = s.dRanges;
       sa.rangeEnd   = s.dRanges + tx * ty;
     }

@@ -39,6 +39,7 @@ struct SortSmem
 };
 static_assert(sizeof(uint32_t) * NWARPS * 256 <= sizeof(uint32_t) * SORT_PART, "warpHist must fit in the key staging area");
 
+template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constant__ SortPassArgs a)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -100,7 +101,17 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
     unsigned peers[SORT_ITEMS];
 #pragma unroll
     for(int i = 0; i < SORT_ITEMS; i++)
-      peers[i] = match_digit<8>(FULL_MASK, (keys[i] >> a.shift) & 0xffu);
+    {
+      const uint32_t digit = (keys[i] >> a.shift) & 0xffu;
+      peers[i]             = match_digit<BITS>(FULL_MASK, digit);
+      if(BITS < 8)
+      {
+        // real digits are < 2^BITS; the padding digit 0xff is told apart by its top bit
+        const bool     top = (digit >> 7) & 1u;
+        const unsigned v   = __ballot_sync(FULL_MASK, top);
+        peers[i] &= top ? v : ~v;
+      }
+    }
 #pragma unroll
     for(int i = 0; i < SORT_ITEMS; i++)
     {
@@ -289,7 +300,10 @@ void launchSortPass(const SortPassArgs& args, cudaStream_t stream)
   const uint32_t parts = (args.maxCount + SORT_PART - 1) / SORT_PART;
   if(parts == 0)
     return;
-  k_sort_pass<<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
+  if(args.digitBits > 0 && args.digitBits <= 5)
+    k_sort_pass<5><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
+  else
+    k_sort_pass<8><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
 }
 
 void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t maxCount, uint32_t* hist, int firstShift, int passes,
@@ -307,7 +321,8 @@ void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t ma
 
 void initSortKernels()
 {
-  cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
+  cudaFuncSetAttribute(k_sort_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
+  cudaFuncSetAttribute(k_sort_pass<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
 }
 
 }  // namespace vkgs

@@ -80,6 +80,7 @@ struct SortPassArgs
   uint32_t*       ticket;
   uint32_t        epoch;
   int             shift;
+  int             digitBits;  // number of significant bits of this pass's digit (0 or 8 = all eight)
   // Final pass of the tile sort only: every run of equal (full) keys in the output is a tile's list;
   // the scatter records its [begin,end) with atomicMin/atomicMax (arrays pre-set to 0xffffffff / 0).
   uint32_t*       rangeBegin;
