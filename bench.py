@@ -50,18 +50,19 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (started before the warm-up;
+    only samples whose timestamps fall inside the timed window are used)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []   # (host time of arrival, fields)
         self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,18 +71,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = [r for (t, r) in self.rows if t_begin is None or (t_begin - 0.02 <= t <= t_end + 0.04)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for (_, r) in self.rows], "whole run (timed region shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -91,7 +102,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -163,7 +174,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -199,13 +210,15 @@ def main():
     r.upload(scene, opt)
 
     # ---- device-resident throughput ---------------------------------------------------------------
-    for _ in range(args.warmup):
-        r.render_async(fp)
-    r.sync()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    for _ in range(args.warmup):
+        r.render_async(fp)
+    r.sync()
     barrier()
+    t_begin = time.time()
     l0 = r.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -213,11 +226,12 @@ def main():
         r.render_async(fp)
     e1.record(stream)
     torch.cuda.synchronize()
+    t_end = time.time()
     launches = r.launch_count() - l0
     r.sync()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     st = r.last_frame_stats()
     fps = world * args.steps / (ms_total / 1000.0)
 

@@ -228,6 +228,18 @@ VKGS_API int vkgs_read_records(vkgs_ctx* ctx, uint32_t* records12, uint64_t firs
 /* Packed device arrays as uploaded (fp32 formats): centers[3N], cov6[6N], rgba[4N], sh[45N]. */
 VKGS_API int vkgs_read_packed(vkgs_ctx* ctx, float* centers, float* cov6, float* rgba, float* sh);
 
+/* ---- scene files -> SplatSet layout (replaces PlyLoaderAsync::innerLoad,
+ *      src/ply_loader_async.cpp:291-453). Format by extension, like the reference: ".splat"
+ *      (antimatter15 32-byte records), ".spz" (Niantic, gzip), anything else is parsed as INRIA
+ *      .ply (ascii / binary_little_endian / binary_big_endian). Arrays come out exactly as the
+ *      reference hands them to SplatSetVk: RUB coordinates, rotation (w,x,y,z), f_rest channel-major.
+ *      Host only, no GPU needed. */
+typedef struct vkgs_scene vkgs_scene;
+VKGS_API int vkgs_scene_load(const char* path, vkgs_scene** out);
+VKGS_API int vkgs_scene_view(const vkgs_scene* scene, vkgs_splat_set_view* view); /* borrowed pointers into the scene */
+VKGS_API int vkgs_scene_free(vkgs_scene* scene);
+VKGS_API const char* vkgs_scene_load_error(void); /* text of the last VKGS_ERR_IO on this thread */
+
 /* ---- deterministic synthetic scene generator; host only, no GPU needed.
  *      Arrays are caller-allocated with the vkgs_splat_set_view sizes; sh_degree is 0 or 3. */
 VKGS_API int vkgs_synth_scene(uint64_t n, uint32_t sh_degree, uint64_t seed, float* positions, float* f_dc, float* f_rest,

@@ -1,0 +1,98 @@
+"""scene loaders. The product's loader (csrc/host_loader.cpp, through the C ABI)
+must reproduce, bit for bit, the SplatSet arrays the REFERENCE's loader stack produces — miniply + spz +
+SplatSet::convertCoordinates, compiled from /root/reference by `make -C oracle ref_loader` and run by
+tests/golden/make_loader_fixtures.py, whose outputs are committed as *.expected.npz."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import vk_gaussian_splatting_b200 as g
+from vk_gaussian_splatting_b200 import _abi as A
+from util import f32_bits
+
+GOLD = Path(__file__).resolve().parent / "golden"
+FILES = sorted(p.name for p in GOLD.glob("loader_*") if not p.name.endswith(".npz"))
+FIELDS = ("positions", "f_dc", "f_rest", "opacity", "scale", "rotation")
+
+
+def test_fixture_set_is_complete():
+    assert len(FILES) == 9
+    assert {Path(f).suffix for f in FILES} == {".ply", ".spz", ".splat"}
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_loader_matches_reference_loader_bitwise(name):
+    want = np.load(GOLD / (name + ".expected.npz"))
+    s = g.load_scene(GOLD / name)
+    assert s.size() == want["positions"].shape[0] > 0
+    for f in FIELDS:
+        got = getattr(s, f)
+        assert got.shape == want[f].shape, (name, f, got.shape, want[f].shape)
+        assert np.array_equal(f32_bits(got), f32_bits(want[f])), (name, f)
+
+
+def test_ply_semantics():
+    le = g.load_scene(GOLD / "loader_le_shuffled.ply")
+    be = g.load_scene(GOLD / "loader_be.ply")
+    # same cloud, different encodings / property order / an extra element in front
+    for f in FIELDS:
+        assert np.array_equal(getattr(le, f), getattr(be, f))
+    assert le.max_sh_degree() == 3 and le.f_rest.shape == (300, 45)
+    # 44 of 45 f_rest properties -> no SH at all (src/ply_loader_async.cpp:383-395)
+    assert g.load_scene(GOLD / "loader_partial_sh.ply").f_rest.shape[1] == 0
+    assert g.load_scene(GOLD / "loader_deg0_double.ply").max_sh_degree() == 0
+
+
+def test_rdf_to_rub_flip_signs_on_ply():
+    """positions (x,-y,-z); quaternion (w,x,-y,-z); SH coefficient signs per spz coordinateConverter."""
+    import struct
+    raw = (GOLD / "loader_partial_sh.ply").read_bytes()
+    hdr_end = raw.index(b"end_header\n") + len(b"end_header\n")
+    names = [l.split()[-1] for l in raw[:hdr_end].decode().splitlines() if l.startswith("property")]
+    rows = np.frombuffer(raw[hdr_end:], "<f4").reshape(-1, len(names))
+    col = {n: rows[:, i] for i, n in enumerate(names)}
+    s = g.load_scene(GOLD / "loader_partial_sh.ply")
+    assert np.array_equal(s.positions, np.stack([col["x"], -col["y"], -col["z"]], 1))
+    assert np.array_equal(s.rotation, np.stack([col["rot_0"], col["rot_1"], -col["rot_2"], -col["rot_3"]], 1))
+    assert np.array_equal(s.scale, np.stack([col["scale_0"], col["scale_1"], col["scale_2"]], 1))
+    le = g.load_scene(GOLD / "loader_le_shuffled.ply")
+    want = np.load(GOLD / "loader_le_shuffled.ply.expected.npz")
+    assert np.array_equal(le.f_rest, want["f_rest"])
+
+
+def test_loader_errors():
+    with pytest.raises(g.VkgsError) as e:
+        g.load_scene(GOLD / "does_not_exist.ply")
+    assert e.value.code == A.VKGS_ERR_IO
+    bad = Path("/tmp/vkgs_bad.splat")
+    bad.write_bytes(b"x" * 33)  # not a multiple of 32 bytes
+    with pytest.raises(g.VkgsError):
+        g.load_scene(bad)
+    bad = Path("/tmp/vkgs_bad.ply")
+    bad.write_bytes(b"ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nend_header\n1.0\n")
+    with pytest.raises(g.VkgsError):
+        g.load_scene(bad)  # not a 3DGS ply
+    bad = Path("/tmp/vkgs_bad.spz")
+    bad.write_bytes(b"not gzip")
+    with pytest.raises(g.VkgsError):
+        g.load_scene(bad)
+
+
+def test_live_reference_loader_when_available():
+    """In the build container the reference's loader stack is compiled from /root/reference: re-run it."""
+    ref = Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "ref_loader"
+    if not ref.exists() or not Path("/root/reference").exists():
+        pytest.skip("oracle/_ref/ref_loader not built (no /root/reference on this machine)")
+    import struct
+    for name in [f for f in FILES if not f.endswith(".splat")]:
+        out = Path("/tmp") / (name + ".live.bin")
+        subprocess.run([str(ref), "dump", str(GOLD / name), str(out)], check=True, stderr=subprocess.DEVNULL)
+        raw = out.read_bytes()
+        n, rest = struct.unpack("<II", raw[:8])
+        a = np.frombuffer(raw[8:], np.float32)
+        s = g.load_scene(GOLD / name)
+        flat = np.concatenate([s.positions.ravel(), s.f_dc.ravel(), s.f_rest.ravel(), s.opacity.ravel(), s.scale.ravel(), s.rotation.ravel()])
+        assert n == s.size() and rest == s.f_rest.shape[1]
+        assert np.array_equal(f32_bits(flat), f32_bits(a)), name

@@ -8,8 +8,8 @@ from ._abi import (FORMAT_FLOAT16, FORMAT_FLOAT32, FORMAT_UINT8, FRUSTUM_CULLING
                    FRUSTUM_CULLING_NONE, SIZE_CULLING_DISABLED, SIZE_CULLING_ENABLED, Camera, FrameParams, Options, Outputs,
                    SplatSetView, lib)
 from .api import (FrameStats, GaussianSplatting, SplatSet, VkgsError, default_camera, default_options, frame_params,
-                  make_camera, orbit_camera, pack_host, synth_scene)
+                  load_scene, make_camera, orbit_camera, pack_host, synth_scene)
 
 __all__ = ["GaussianSplatting", "SplatSet", "FrameStats", "VkgsError", "Camera", "FrameParams", "Options", "Outputs",
            "SplatSetView", "default_camera", "default_options", "frame_params", "make_camera", "orbit_camera",
-           "synth_scene", "pack_host", "lib"]
+           "synth_scene", "pack_host", "load_scene", "lib"]

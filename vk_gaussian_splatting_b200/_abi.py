@@ -92,6 +92,10 @@ SYMBOLS = {
     "vkgs_sort_pairs": (C.c_int, [C.c_void_p, u32p, u32p, C.c_uint64, u32p, u32p, C.c_int, f32p]),
     "vkgs_read_records": (C.c_int, [C.c_void_p, u32p, C.c_uint64, C.c_uint64]),
     "vkgs_read_packed": (C.c_int, [C.c_void_p, f32p, f32p, f32p, f32p]),
+    "vkgs_scene_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "vkgs_scene_view": (C.c_int, [C.c_void_p, C.POINTER(SplatSetView)]),
+    "vkgs_scene_free": (C.c_int, [C.c_void_p]),
+    "vkgs_scene_load_error": (C.c_char_p, []),
     "vkgs_synth_scene": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, f32p, f32p, f32p, f32p, f32p, f32p]),
 }
 

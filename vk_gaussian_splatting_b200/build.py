@@ -24,7 +24,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 # per-file extra flags: the per-splat front end must not contract mul+add (bit-exact vs the oracle)
 EXTRA = {"k_preprocess.cu": ["-fmad=false"]}
 SOURCES = ["context.cu", "sort_api.cu", "k_preprocess.cu", "k_radix_sort.cu", "k_binning.cu", "k_blend.cu",
-           "host_camera.cpp", "host_pack.cpp", "host_synth.cpp"]
+           "host_camera.cpp", "host_pack.cpp", "host_synth.cpp", "host_loader.cpp"]
 
 
 def _nvcc() -> str:
@@ -63,7 +63,8 @@ def build_lib(verbose: bool = False, force: bool = False) -> Path:
                 print(" ".join(cmd), flush=True)
             subprocess.run(cmd, check=True)
     if force or _newer(LIB, objs):
-        cmd = [nvcc, "-ccbin", _host_cxx(), *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
+        # zlib: gzip container of .spz (the image's libz.a is not PIC, so the system libz.so.1 is used)
+        cmd = [nvcc, "-ccbin", _host_cxx(), *ARCH, "-shared", "-o", str(LIB), *map(str, objs), "-lz"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)
