@@ -82,14 +82,6 @@ __device__ __forceinline__ uint32_t ldsU32(uint32_t addr)
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void stsV4(uint32_t addr, float4 v)
-{
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void stsV2(uint32_t addr, float2 v)
-{
-  asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
-}
 __device__ __forceinline__ void stsU32(uint32_t addr, uint32_t v)
 {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -136,7 +128,21 @@ __device__ __forceinline__ void add2acc(f32x2& c, f32x2 a)
   c = __fadd2_rn(c, a);
 }
 
-constexpr uint32_t REC_BYTES   = RECORD_WORDS * 4;  // staged record, 48 B: cx -cy w1x w1y | w2x w2y -r -g | -b -a . .
+// 16-byte asynchronous global -> shared copy (LDGSTS), per-thread addresses
+__device__ __forceinline__ void cpAsync16(uint32_t smemDst, const void* gmemSrc)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemDst), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll()
+{
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr uint32_t REC_BYTES   = RECORD_WORDS * 4;  // record, 48 B: cx cy w1x w1y | w2x w2y r g | b a bbox bbox
 constexpr int      BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int      BATCH       = BLEND_THREADS;     // list entries staged per round (one per thread)
 constexpr uint32_t SMEM_REC    = BATCH * REC_BYTES; // bytes of one record buffer
@@ -146,12 +152,20 @@ static_assert(BLEND_WARPS == 4 && BATCH == 128, "the tile is split into 2x2 warp
 // One CTA (4 warps) per 16x16 tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
 // it (same column, rows ly and ly+4), evaluated together with packed fp32 instructions: the loads,
 // the loop control and the x-dependent products are shared by the pair and every FFMA2 retires two
-// IEEE-rounded results in one issue slot (the kernel is issue-bound, not FMA-pipe bound).
-// The list is consumed in batches of 128 entries through a double-buffered shared staging area
-// (one barrier per batch). The staging thread of an entry also decides which of the four warp
-// blocks the splat can touch (pixel bbox, then a separating-axis test along the splat's own axes
-// against the opacity-limited radius) and the warp ballots of those bits become per-warp hit masks:
-// the blending warps iterate set bits only.
+// IEEE-rounded results in one issue slot (the kernel is issue/latency bound, not FMA-pipe bound).
+//
+// The tile's list is consumed in batches of 128 entries through a double-buffered shared ring:
+// every thread gathers ONE 48-byte record of the next batch straight into shared memory with
+// cp.async (no staging registers) while the current batch is blended, then classifies its entry —
+// which of the four warp blocks can the splat touch (pixel bbox, then a separating-axis test along
+// the splat's own axes against the opacity-limited radius) — and the warp ballots of those bits
+// become per-warp hit masks, so the blending warps iterate set bits only. One barrier per batch.
+//
+// Inner loop: two list entries are evaluated per trip, branch-free up to the blend (discards are
+// zeros), so their shared loads, SFU ex2 and dependent FMA chains interleave; only the final
+// transmittance update is ordered. Signs are arranged so that no negation is needed per hit:
+// the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
+// colour.
 template <bool FTB, bool NOGAUSS>
 __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constant__ BlendArgs a)
 {
@@ -164,13 +178,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
   const uint32_t tileX0 = tx * TILE_W, tileY0 = ty * TILE_H;
   const uint32_t px = tileX0 + (warp & 1u) * 8u + (lane & 7u), pyA = tileY0 + (warp >> 1) * 8u + (lane >> 3), pyB = pyA + 4u;
   const bool     insideA = px < a.width && pyA < a.height, insideB = px < a.width && pyB < a.height;
-  const float    fx = static_cast<float>(px) + 0.5f;
-  const f32x2    fy2 = pk(static_cast<float>(pyA) + 0.5f, static_cast<float>(pyB) + 0.5f);
+  const float    nfx = -(static_cast<float>(px) + 0.5f);
+  const f32x2    nfy2 = pk(-(static_cast<float>(pyA) + 0.5f), -(static_cast<float>(pyB) + 0.5f));
   const float    tileCx = static_cast<float>(tileX0) + 4.0f, tileCy = static_cast<float>(tileY0) + 4.0f;  // centre of warp block 0
 
   const uint2 range = make_uint2(a.rangeBegin[tile], a.rangeEnd[tile]);  // empty tile: begin > end
-  f32x2       c0 = pk(0.f, 0.f), c1 = c0, c2 = c0;          // colour accumulators of the two pixels
-  f32x2       acc = FTB ? pk(1.0f, 1.0f) : pk(0.f, 0.f);        // FTB: transmittance T = 1 - A_dst;  BTF: MINUS the sum of alphas
+  f32x2       c0 = pk(0.f, 0.f), c1 = c0, c2 = c0;            // MINUS the colour accumulators of the two pixels
+  f32x2       acc = FTB ? pk(1.0f, 1.0f) : pk(0.f, 0.f);      // FTB: transmittance T = 1 - A_dst;  BTF: MINUS the sum of alphas
   const f32x2 one2 = pk(1.0f, 1.0f);
   const f32x2 kExp = pk(-0.72134752044448170368f, -0.72134752044448170368f);  // exp(-A/2) = 2^(-A/2 * log2 e)
   const float THRESHOLD = 1.0f / 255.0f;
@@ -178,23 +192,21 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
   const float eps       = a.transmittanceEpsilon;
   bool        warpDone  = __all_sync(FULL_MASK, !insideA && !insideB);
 
-  // gather of this thread's entry of a batch (record, prefetched one batch ahead)
-  float4 r0, r1, r2;
-  auto   fetch = [&](uint32_t base) {
-    if(base + tid < range.y)
-    {
-      const uint32_t id  = a.tileVals[base + tid];
-      const float4*  rec = reinterpret_cast<const float4*>(a.records + static_cast<uint64_t>(id) * RECORD_WORDS);
-      r0                 = __ldg(rec + 0);
-      r1                 = __ldg(rec + 1);
-      r2                 = __ldg(rec + 2);
-    }
+  // asynchronous gather of this thread's entry of a batch into record buffer `buf`
+  auto gather = [&](uint32_t id, uint32_t buf) {
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.records + static_cast<uint64_t>(id) * RECORD_WORDS);
+    const uint32_t       dst = sbase + buf * SMEM_REC + tid * REC_BYTES;
+    cpAsync16(dst, src);
+    cpAsync16(dst + 16, src + 16);
+    cpAsync16(dst + 32, src + 32);
   };
-  // park the entry in shared memory (sign conventions of the inner loop) + per-warp-block hit bits
-  auto stage = [&](uint32_t base, uint32_t buf) {
+  // classify this thread's (landed) entry: per-warp-block hit bits -> per-warp hit masks
+  auto classify = [&](bool have, uint32_t buf) {
     uint32_t bits = 0;
-    if(base + tid < range.y)
+    if(have)
     {
+      const uint32_t src = sbase + buf * SMEM_REC + tid * REC_BYTES;
+      const float4   r0 = ldsV4(src), r1 = ldsV4(src + 16), r2 = ldsV4(src + 32);
       const uint32_t bb0 = __float_as_uint(r2.z), bb1 = __float_as_uint(r2.w);
       const uint32_t x0 = bb0 & 0xffffu, y0 = bb0 >> 16, x1 = bb1 & 0xffffu, y1 = bb1 >> 16;
       const uint32_t colL = (x0 <= tileX0 + 7u && x1 >= tileX0) ? 0x5u : 0u;        // warps 0,2
@@ -222,13 +234,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
         if(!(fmaxf(f1, f2) <= lim))
           bits &= ~(1u << b);
       }
-      if(bits)
-      {
-        const uint32_t dst = sbase + buf * SMEM_REC + tid * REC_BYTES;
-        stsV4(dst, make_float4(r0.x, -r0.y, r0.z, r0.w));
-        stsV4(dst + 16, make_float4(r1.x, r1.y, -r1.z, -r1.w));
-        stsV2(dst + 32, make_float2(-r2.x, -r2.y));
-      }
     }
     const unsigned m0 = __ballot_sync(FULL_MASK, bits & 1u), m1 = __ballot_sync(FULL_MASK, bits & 2u),
                    m2 = __ballot_sync(FULL_MASK, bits & 4u), m3 = __ballot_sync(FULL_MASK, bits & 8u);
@@ -236,82 +241,143 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
       stsU32(sbase + SMEM_HIT + ((buf * BLEND_WARPS + lane) * (BATCH / 32) + warp) * 4u, lane == 0 ? m0 : (lane == 1 ? m1 : (lane == 2 ? m2 : m3)));
   };
 
+  // One list entry against this thread's two pixels, up to (not including) the ordered blend.
+  // Returns MINUS the fragment opacities (0 = discarded); `gmin` = distance of the nearer of the two
+  // SFU opacities to the discard threshold (the caller sends near misses to the exact path).
+  struct Frag
+  {
+    f32x2  A2, n2;  // A of the two pixels; minus opacity (masked)
+    float  gmin;
+    float  r, g, b, alpha;
+  };
+  auto evalFrag = [&](uint32_t addr) {
+    Frag         f;
+    const float4 ra  = ldsV4(addr);       // cx cy w1x w1y
+    const float4 rb  = ldsV4(addr + 16);  // w2x w2y r g
+    const float2 rc  = ldsV2(addr + 32);  // b a
+    const float  ndx = __fadd_rn(ra.x, nfx);            // -(px - cx): A is even in (dx,dy)
+    const f32x2  ndy2 = add2(pk(ra.y, ra.y), nfy2);
+    const float  t = __fmul_rn(ndx, ra.z), u = __fmul_rn(ndx, rb.x);
+    const f32x2  fpx2 = fma2(ndy2, pk(ra.w, ra.w), pk(t, t));
+    const f32x2  fpy2 = fma2(ndy2, pk(rb.y, rb.y), pk(u, u));
+    f.A2              = fma2(fpy2, fpy2, mul2(fpx2, fpx2));
+    f.r = rb.z, f.g = rb.w, f.b = rc.x, f.alpha = rc.y;
+    float Alo, Ahi;
+    upk(f.A2, Alo, Ahi);
+    const bool vA = !(Alo > 8.0f), vB = !(Ahi > 8.0f);
+    if(NOGAUSS)
+    {
+      f.n2   = pk(vA ? -1.0f : 0.0f, vB ? -1.0f : 0.0f);
+      f.gmin = 1.0f;
+    }
+    else
+    {
+      float xlo, xhi, nlo, nhi, glo, ghi;
+      upk(mul2(f.A2, kExp), xlo, xhi);
+      const float na = -rc.y;
+      const f32x2 n2 = mul2(pk(ex2Approx(xlo), ex2Approx(xhi)), pk(na, na));
+      upk(n2, nlo, nhi);
+      upk(add2(n2, pk(THRESHOLD, THRESHOLD)), glo, ghi);
+      f.n2   = pk((vA && nlo < -THRESHOLD) ? nlo : 0.0f, (vB && nhi < -THRESHOLD) ? nhi : 0.0f);
+      f.gmin = fminf(fabsf(glo), fabsf(ghi));
+    }
+    return f;
+  };
+  // within the guard band of the 1/255 discard threshold (rare): decide exactly, like the oracle
+  auto fixFrag = [&](Frag& f) {
+    float Alo, Ahi, mlo, mhi;
+    upk(f.A2, Alo, Ahi);
+    upk(f.n2, mlo, mhi);
+    const float opLo = ex2Approx(Alo * -0.72134752044448170368f) * f.alpha, opHi = ex2Approx(Ahi * -0.72134752044448170368f) * f.alpha;
+    if(!(Alo > 8.0f) && fabsf(opLo - THRESHOLD) <= BAND)
+      mlo = exactNegOpacity(Alo, -f.alpha);
+    if(!(Ahi > 8.0f) && fabsf(opHi - THRESHOLD) <= BAND)
+      mhi = exactNegOpacity(Ahi, -f.alpha);
+    f.n2 = pk(mlo, mhi);
+  };
+  auto blendFrag = [&](const Frag& f) {
+    if(FTB)
+    {
+      const f32x2 nw2 = mul2(f.n2, acc);  // -(opacity * T)
+      fma2acc(c0, nw2, pk(f.r, f.r));
+      fma2acc(c1, nw2, pk(f.g, f.g));
+      fma2acc(c2, nw2, pk(f.b, f.b));
+      add2acc(acc, nw2);
+    }
+    else
+    {
+      const f32x2 t2 = add2(one2, f.n2);  // 1 - opacity
+      c0             = mul2(c0, t2);
+      c1             = mul2(c1, t2);
+      c2             = mul2(c2, t2);
+      fma2acc(c0, f.n2, pk(f.r, f.r));
+      fma2acc(c1, f.n2, pk(f.g, f.g));
+      fma2acc(c2, f.n2, pk(f.b, f.b));
+      add2acc(acc, f.n2);
+    }
+  };
+
   if(range.x < range.y)
   {
-    fetch(range.x);
-    stage(range.x, 0);
+    // prologue: batch 0 lands and is classified; the list index of batch 1 is already on its way
+    uint32_t idNext = 0;
+    {
+      const bool have = range.x + tid < range.y;
+      if(have)
+        gather(a.tileVals[range.x + tid], 0);
+      cpAsyncCommit();
+      if(range.x + BATCH + tid < range.y)
+        idNext = a.tileVals[range.x + BATCH + tid];
+      cpAsyncWaitAll();
+      classify(have, 0);
+    }
     __syncthreads();
     for(uint32_t base = range.x, buf = 0;; base += BATCH, buf ^= 1u)
     {
-      const bool more = base + BATCH < range.y;
+      const bool more     = base + BATCH < range.y;
+      const bool haveNext = base + BATCH + tid < range.y;
       if(more)
-        fetch(base + BATCH);  // global gathers of the next batch fly while this one is blended
+      {
+        // records of the next batch fly into the other buffer while this one is blended
+        if(haveNext)
+          gather(idNext, buf ^ 1u);
+        cpAsyncCommit();
+        if(base + 2 * BATCH + tid < range.y)
+          idNext = a.tileVals[base + 2 * BATCH + tid];
+      }
 
       if(!warpDone)
       {
         const uint32_t recBase = sbase + buf * SMEM_REC;
         const uint32_t hitBase = sbase + SMEM_HIT + (buf * BLEND_WARPS + warp) * (BATCH / 32) * 4u;
+#pragma unroll 1
         for(uint32_t chunk = 0; chunk < BATCH / 32; chunk++)
         {
           unsigned       m         = ldsU32(hitBase + chunk * 4u);
           const uint32_t chunkAddr = recBase + chunk * 32u * REC_BYTES;
           while(m)
           {
-            const uint32_t addr = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
+            const uint32_t addr0 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
             m &= m - 1;
-            const float4 ra  = ldsV4(addr);       // cx -cy w1x w1y
-            const float4 rb  = ldsV4(addr + 16);  // w2x w2y -r -g
-            const float  dx  = __fsub_rn(fx, ra.x);
-            const f32x2  dy2 = add2(fy2, pk(ra.y, ra.y));
-            const float  t = __fmul_rn(dx, ra.z), u = __fmul_rn(dx, rb.x);
-            const f32x2  fpx2 = fma2(dy2, pk(ra.w, ra.w), pk(t, t));
-            const f32x2  fpy2 = fma2(dy2, pk(rb.y, rb.y), pk(u, u));
-            const f32x2  A2   = fma2(fpy2, fpy2, mul2(fpx2, fpx2));
-            float        Alo, Ahi;
-            upk(A2, Alo, Ahi);
-            const bool vA = !(Alo > 8.0f), vB = !(Ahi > 8.0f);
-            if(!(vA || vB))
-              continue;
-            const float2 rc = ldsV2(addr + 32);  // -b -a
-            // MINUS the fragment opacity of the two pixels, 0 for a discarded fragment
-            float mlo = vA ? -1.0f : 0.0f, mhi = vB ? -1.0f : 0.0f;
-            if(!NOGAUSS)
+            if(m)
             {
-              float xlo, xhi, nlo, nhi, glo, ghi;
-              upk(mul2(A2, kExp), xlo, xhi);
-              const f32x2 n2 = mul2(pk(ex2Approx(xlo), ex2Approx(xhi)), pk(rc.y, rc.y));
-              upk(n2, nlo, nhi);
-              upk(add2(n2, pk(THRESHOLD, THRESHOLD)), glo, ghi);
-              mlo = (vA && nlo < -THRESHOLD) ? nlo : 0.0f;
-              mhi = (vB && nhi < -THRESHOLD) ? nhi : 0.0f;
-              if(fminf(fabsf(glo), fabsf(ghi)) <= BAND)
+              const uint32_t addr1 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
+              m &= m - 1;
+              Frag f0 = evalFrag(addr0), f1 = evalFrag(addr1);
+              if(fminf(f0.gmin, f1.gmin) <= BAND)
               {
-                // within the guard band of the 1/255 discard threshold (rare): decide exactly
-                if(vA && fabsf(glo) <= BAND)
-                  mlo = exactNegOpacity(Alo, rc.y);
-                if(vB && fabsf(ghi) <= BAND)
-                  mhi = exactNegOpacity(Ahi, rc.y);
+                fixFrag(f0);
+                fixFrag(f1);
               }
-            }
-            const f32x2 nop2 = pk(mlo, mhi);
-            if(FTB)
-            {
-              const f32x2 nw2 = mul2(nop2, acc);  // -(opacity * T)
-              fma2acc(c0, nw2, pk(rb.z, rb.z));
-              fma2acc(c1, nw2, pk(rb.w, rb.w));
-              fma2acc(c2, nw2, pk(rc.x, rc.x));
-              add2acc(acc, nw2);
+              blendFrag(f0);
+              blendFrag(f1);
             }
             else
             {
-              const f32x2 t2 = add2(one2, nop2);  // 1 - opacity
-              c0             = mul2(c0, t2);
-              c1             = mul2(c1, t2);
-              c2             = mul2(c2, t2);
-              fma2acc(c0, nop2, pk(rb.z, rb.z));
-              fma2acc(c1, nop2, pk(rb.w, rb.w));
-              fma2acc(c2, nop2, pk(rc.x, rc.x));
-              add2acc(acc, nop2);
+              Frag f0 = evalFrag(addr0);
+              if(f0.gmin <= BAND)
+                fixFrag(f0);
+              blendFrag(f0);
             }
           }
           if(FTB)
@@ -328,9 +394,12 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
         }
       }
       if(more)
-        stage(base + BATCH, buf ^ 1u);
-      // one barrier per batch: publishes the next staged batch, retires this one, and votes on
-      // whether any warp block of the tile still needs the rest of the list
+      {
+        cpAsyncWaitAll();
+        classify(haveNext, buf ^ 1u);
+      }
+      // one barrier per batch: publishes the next batch, retires this one, and votes on whether any
+      // warp block of the tile still needs the rest of the list
       const int active = __syncthreads_or(!warpDone);
       if(!more || !active)
         break;
@@ -350,8 +419,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
     if(!(p ? insideB : insideA))
       continue;
     const uint64_t o  = static_cast<uint64_t>(p ? pyB : pyA) * a.width + px;
-    const float    c0f = ca[p][0], c1f = ca[p][1], c2f = ca[p][2];
-    const float    al = FTB ? 1.0f - ca[p][3] : -ca[p][3];
+    // (0 - x, not -x: an untouched pixel must come out as +0)
+    const float    c0f = __fsub_rn(0.0f, ca[p][0]), c1f = __fsub_rn(0.0f, ca[p][1]), c2f = __fsub_rn(0.0f, ca[p][2]);
+    const float    al = FTB ? 1.0f - ca[p][3] : __fsub_rn(0.0f, ca[p][3]);
     if(a.targetFormat == VKGS_FORMAT_FLOAT32)
       static_cast<float4*>(a.image)[o] = make_float4(c0f, c1f, c2f, al);
     else if(a.targetFormat == VKGS_FORMAT_FLOAT16)
