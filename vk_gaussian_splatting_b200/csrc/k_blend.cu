@@ -144,10 +144,11 @@ __device__ __forceinline__ void cpAsyncWaitAll()
 
 constexpr uint32_t REC_BYTES   = RECORD_WORDS * 4;  // record, 48 B: cx cy w1x w1y | w2x w2y r g | b a bbox bbox
 constexpr int      BLEND_WARPS = BLEND_THREADS / 32;
-constexpr int      BATCH       = BLEND_THREADS;     // list entries staged per round (one per thread)
+constexpr int      EPT         = 1;                  // list entries gathered + classified per thread per round
+constexpr int      BATCH       = EPT * BLEND_THREADS;  // list entries staged per round
 constexpr uint32_t SMEM_REC    = BATCH * REC_BYTES; // bytes of one record buffer
 constexpr uint32_t SMEM_HIT    = 2 * SMEM_REC;      // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
-static_assert(BLEND_WARPS == 4 && BATCH == 128, "the tile is split into 2x2 warp blocks of 8x8 pixels");
+static_assert(BLEND_WARPS == 4, "the tile is split into 2x2 warp blocks of 8x8 pixels");
 
 // One CTA (4 warps) per 16x16 tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
 // it (same column, rows ly and ly+4), evaluated together with packed fp32 instructions: the loads,
@@ -167,7 +168,7 @@ static_assert(BLEND_WARPS == 4 && BATCH == 128, "the tile is split into 2x2 warp
 // the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
 // colour.
 template <bool FTB, bool NOGAUSS>
-__global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constant__ BlendArgs a)
+__global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_constant__ BlendArgs a)
 {
   __shared__ __align__(16) unsigned char s_raw[2 * SMEM_REC + 2 * BLEND_WARPS * (BATCH / 32) * 4];
   const uint32_t sbase = smemBaseOpaque(s_raw);
@@ -193,19 +194,19 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
   bool        warpDone  = __all_sync(FULL_MASK, !insideA && !insideB);
 
   // asynchronous gather of this thread's entry of a batch into record buffer `buf`
-  auto gather = [&](uint32_t id, uint32_t buf) {
+  auto gather = [&](uint32_t id, uint32_t buf, uint32_t slot) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.records + static_cast<uint64_t>(id) * RECORD_WORDS);
-    const uint32_t       dst = sbase + buf * SMEM_REC + tid * REC_BYTES;
+    const uint32_t       dst = sbase + buf * SMEM_REC + slot * REC_BYTES;
     cpAsync16(dst, src);
     cpAsync16(dst + 16, src + 16);
     cpAsync16(dst + 32, src + 32);
   };
   // classify this thread's (landed) entry: per-warp-block hit bits -> per-warp hit masks
-  auto classify = [&](bool have, uint32_t buf) {
+  auto classify = [&](bool have, uint32_t buf, uint32_t slot) {
     uint32_t bits = 0;
     if(have)
     {
-      const uint32_t src = sbase + buf * SMEM_REC + tid * REC_BYTES;
+      const uint32_t src = sbase + buf * SMEM_REC + slot * REC_BYTES;
       const float4   r0 = ldsV4(src), r1 = ldsV4(src + 16), r2 = ldsV4(src + 32);
       const uint32_t bb0 = __float_as_uint(r2.z), bb1 = __float_as_uint(r2.w);
       const uint32_t x0 = bb0 & 0xffffu, y0 = bb0 >> 16, x1 = bb1 & 0xffffu, y1 = bb1 >> 16;
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
     }
     const unsigned m0 = __ballot_sync(FULL_MASK, bits & 1u), m1 = __ballot_sync(FULL_MASK, bits & 2u),
                    m2 = __ballot_sync(FULL_MASK, bits & 4u), m3 = __ballot_sync(FULL_MASK, bits & 8u);
-    if(lane < 4)  // hit[buf][blend warp = lane][word = this staging warp]
-      stsU32(sbase + SMEM_HIT + ((buf * BLEND_WARPS + lane) * (BATCH / 32) + warp) * 4u, lane == 0 ? m0 : (lane == 1 ? m1 : (lane == 2 ? m2 : m3)));
+    if(lane < 4)  // hit[buf][blend warp = lane][word = slot / 32]
+      stsU32(sbase + SMEM_HIT + ((buf * BLEND_WARPS + lane) * (BATCH / 32) + (slot >> 5)) * 4u, lane == 0 ? m0 : (lane == 1 ? m1 : (lane == 2 ? m2 : m3)));
   };
 
   // One list entry against this thread's two pixels, up to (not including) the ordered blend.
@@ -320,30 +321,37 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
   if(range.x < range.y)
   {
     // prologue: batch 0 lands and is classified; the list index of batch 1 is already on its way
-    uint32_t idNext = 0;
+    uint32_t idNext[EPT];
     {
-      const bool have = range.x + tid < range.y;
-      if(have)
-        gather(a.tileVals[range.x + tid], 0);
+#pragma unroll
+      for(int e = 0; e < EPT; e++)
+        if(range.x + e * BLEND_THREADS + tid < range.y)
+          gather(a.tileVals[range.x + e * BLEND_THREADS + tid], 0, e * BLEND_THREADS + tid);
       cpAsyncCommit();
-      if(range.x + BATCH + tid < range.y)
-        idNext = a.tileVals[range.x + BATCH + tid];
+#pragma unroll
+      for(int e = 0; e < EPT; e++)
+        idNext[e] = (range.x + BATCH + e * BLEND_THREADS + tid < range.y) ? a.tileVals[range.x + BATCH + e * BLEND_THREADS + tid] : 0u;
       cpAsyncWaitAll();
-      classify(have, 0);
+#pragma unroll
+      for(int e = 0; e < EPT; e++)
+        classify(range.x + e * BLEND_THREADS + tid < range.y, 0, e * BLEND_THREADS + tid);
     }
     __syncthreads();
     for(uint32_t base = range.x, buf = 0;; base += BATCH, buf ^= 1u)
     {
-      const bool more     = base + BATCH < range.y;
-      const bool haveNext = base + BATCH + tid < range.y;
+      const bool more = base + BATCH < range.y;
       if(more)
       {
         // records of the next batch fly into the other buffer while this one is blended
-        if(haveNext)
-          gather(idNext, buf ^ 1u);
+#pragma unroll
+        for(int e = 0; e < EPT; e++)
+          if(base + BATCH + e * BLEND_THREADS + tid < range.y)
+            gather(idNext[e], buf ^ 1u, e * BLEND_THREADS + tid);
         cpAsyncCommit();
-        if(base + 2 * BATCH + tid < range.y)
-          idNext = a.tileVals[base + 2 * BATCH + tid];
+#pragma unroll
+        for(int e = 0; e < EPT; e++)
+          if(base + 2 * BATCH + e * BLEND_THREADS + tid < range.y)
+            idNext[e] = a.tileVals[base + 2 * BATCH + e * BLEND_THREADS + tid];
       }
 
       if(!warpDone)
@@ -396,7 +404,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) k_blend(const __grid_constan
       if(more)
       {
         cpAsyncWaitAll();
-        classify(haveNext, buf ^ 1u);
+#pragma unroll
+        for(int e = 0; e < EPT; e++)
+          classify(base + BATCH + e * BLEND_THREADS + tid < range.y, buf ^ 1u, e * BLEND_THREADS + tid);
       }
       // one barrier per batch: publishes the next batch, retires this one, and votes on whether any
       // warp block of the tile still needs the rest of the list
