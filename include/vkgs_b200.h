@@ -171,7 +171,7 @@ VKGS_API int vkgs_set_stream(vkgs_ctx* ctx, void* cuda_stream);
 VKGS_API const char* vkgs_last_error(const vkgs_ctx* ctx);
 VKGS_API const char* vkgs_version(void);
 /* sizeof() of the ABI structs as compiled, for binding validation:
- * 0 vkgs_splat_set_view, 1 vkgs_options, 2 vkgs_frame_params, 3 vkgs_camera, 4 vkgs_outputs */
+ * 0 vkgs_splat_set_view, 1 vkgs_options, 2 vkgs_frame_params, 3 vkgs_camera, 4 vkgs_outputs, 5 vkgs_instance */
 VKGS_API uint32_t vkgs_abi_struct_size(int which);
 
 /* ---- scene upload (replaces SplatSetVk::initDataStorage/initDataBuffers,
@@ -185,6 +185,32 @@ VKGS_API int vkgs_upload(vkgs_ctx* ctx, const vkgs_splat_set_view* set, const vk
 VKGS_API int vkgs_pack_host(const vkgs_splat_set_view* set, const vkgs_options* opt, float* centers, float* cov6, void* rgba,
                             void* sh);
 VKGS_API void vkgs_default_options(vkgs_options* opt);
+
+/* ---- multi-instance scenes (replaces SplatSetManagerVk's splat sets + instances and its global
+ *      index table: createInstance / rebuildGlobalIndexTables, src/splat_set_manager_vk.cpp:2304-2360,
+ *      GlobalSplatIndexEntry shaders/shaderio.h:523-527, resolveGlobalSplatID
+ *      shaders/threedgs_particle_storage.h.slang:34-42). An instance places one splat set in the world
+ *      with its own transform (SplatSetDesc.transform / transformInverse, glm column-major, both
+ *      supplied by the caller like the reference keeps both); several instances may share a set.
+ *      Global splat id = (splat count of all earlier instances) + local id: the ids the sort
+ *      returns and vkgs_read_records is indexed by. All instances are culled, sorted and blended
+ *      together. With a scene uploaded this way vkgs_frame_params.model / model_inverse are ignored. */
+typedef struct vkgs_instance
+{
+  uint32_t splat_set_index; /* index into the `sets` array of vkgs_upload_scene */
+  uint32_t _pad;
+  float    transform[16];
+  float    transform_inverse[16];
+} vkgs_instance;
+VKGS_API int vkgs_upload_scene(vkgs_ctx* ctx, const vkgs_splat_set_view* sets, uint32_t set_count, const vkgs_instance* instances,
+                               uint32_t instance_count, const vkgs_options* opt);
+/* Move an instance (takes effect for frames enqueued afterwards; nothing is re-uploaded). */
+VKGS_API int vkgs_set_instance_transform(vkgs_ctx* ctx, uint32_t instance, const float* transform, const float* transform_inverse);
+/* The global index table as the reference builds it: for every global splat id the instance
+ * index and the splat index inside that instance's set (either array may be NULL; `total`
+ * receives the global splat count). */
+VKGS_API int vkgs_global_index_table(const vkgs_ctx* ctx, uint32_t* instance_index, uint32_t* splat_index, uint64_t capacity,
+                                     uint64_t* total);
 
 /* ---- frame (replaces updateAndUploadFrameInfoUBO + processSortingOnGPU + drawSplatPrimitives,
  *      src/gaussian_splatting.cpp:1150,1298,1369). */

@@ -28,6 +28,16 @@ class Quad(C.Structure):
 QUAD_DTYPE = np.dtype([("center", "<f4", 2), ("basis1", "<f4", 2), ("basis2", "<f4", 2), ("w1", "<f4", 2), ("w2", "<f4", 2),
                        ("rgba", "<f4", 4), ("ndc_z", "<f4"), ("valid", "<u4")])
 
+class OrcSet(C.Structure):
+    _fields_ = [("centers", f32p), ("cov6", f32p), ("rgba", f32p), ("sh45", f32p), ("scale_log", f32p), ("n", C.c_uint64),
+                ("sh_degree", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class OrcInstance(C.Structure):
+    _fields_ = [("set_index", C.c_uint32), ("_pad", C.c_uint32), ("transform", C.c_float * 16),
+                ("transform_inverse", C.c_float * 16)]
+
+
 _lib = None
 
 
@@ -66,6 +76,9 @@ def lib() -> C.CDLL:
         l.orc_render.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams),
                                  C.POINTER(A.Options), f32p, u32p, u32p, C.c_void_p]
         l.orc_render.restype = C.c_uint32
+        l.orc_render_scene.argtypes = [C.POINTER(OrcSet), C.c_uint32, C.POINTER(OrcInstance), C.c_uint32,
+                                       C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p, u32p, u32p]
+        l.orc_render_scene.restype = C.c_uint32
         l.orc_quad_size.restype = C.c_uint32
         l.orc_cpu_sort.argtypes = [f32p, C.c_uint64, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, u32p, f32p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -140,6 +153,27 @@ def render(packed: Packed, fp, opt, want_quads=False):
                          packed.sh_degree, C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids),
                          quads.ctypes.data_as(C.c_void_p) if want_quads else None)
     return img, keys[:v].copy(), ids[:v].copy(), quads
+
+
+def render_scene(packed_sets, instances, fp, opt):
+    """Multi-instance oracle frame. `instances`: list of (set_index, transform[4,4], transform_inverse[4,4]) in glm
+    column-major memory order. Returns (image, sorted_keys, sorted_global_ids)."""
+    sets = (OrcSet * len(packed_sets))()
+    for i, p in enumerate(packed_sets):
+        sets[i].centers, sets[i].cov6, sets[i].rgba, sets[i].sh45, sets[i].scale_log = _p(p.centers), _p(p.cov6), _p(p.rgba), _p(p.sh), _p(p.scale)
+        sets[i].n, sets[i].sh_degree = p.n, p.sh_degree
+    inst = (OrcInstance * len(instances))()
+    total = 0
+    for k, (si, t, ti) in enumerate(instances):
+        inst[k].set_index = int(si)
+        inst[k].transform[:] = np.asarray(t, np.float32).reshape(16).tolist()
+        inst[k].transform_inverse[:] = np.asarray(ti, np.float32).reshape(16).tolist()
+        total += packed_sets[int(si)].n
+    img = np.zeros((fp.height, fp.width, 4), np.float32)
+    keys = np.empty(total, np.uint32)
+    ids = np.empty(total, np.uint32)
+    v = lib().orc_render_scene(sets, len(packed_sets), inst, len(instances), C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids))
+    return img, keys[:v].copy(), ids[:v].copy()
 
 
 def project_splat(packed: Packed, idx: int, fp, opt) -> Quad:

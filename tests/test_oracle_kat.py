@@ -213,3 +213,31 @@ def test_cpu_sorter_orders_by_plane_distance():
             assert np.all(np.diff(ds) >= 0) if ftb else np.all(np.diff(ds) <= 0)
     want = np.abs((s.positions.astype(np.float64) - eye) @ (d / np.linalg.norm(d)))
     assert np.allclose(dist, want, atol=1e-5)
+
+
+def test_multi_instance_oracle_reduces_to_single_instance_and_composes():
+    """orc_render_scene (global index table + per-instance transform): one identity instance == orc_render;
+    an instance with model M == orc_render with fp.model = M; ids of later instances are offset by the
+    splat counts before them (src/splat_set_manager_vk.cpp:2304-2360)."""
+    s = g.synth_scene(3000, 3, 77)
+    pk = O.Packed(s)
+    cam = g.default_camera()
+    fp = O.frame_params(cam, 160, 90)
+    opt = O.default_options(front_to_back=1)
+    ident = np.eye(4, dtype=np.float32)
+    img0, k0, i0, _ = O.render(pk, fp, opt)
+    img1, k1, i1 = O.render_scene([pk], [(0, ident, ident)], fp, opt)
+    assert np.array_equal(img0, img1) and np.array_equal(k0, k1) and np.array_equal(i0, i1)
+    m = np.eye(4)
+    m[:3, 3] = (0.3, -0.1, 0.2)
+    t, ti = np.ascontiguousarray(m.T, np.float32), np.ascontiguousarray(np.linalg.inv(m).T, np.float32)
+    fpm = O.frame_params(cam, 160, 90)
+    fpm.model[:] = t.reshape(16).tolist()
+    fpm.model_inverse[:] = ti.reshape(16).tolist()
+    img2, k2, i2, _ = O.render(pk, fpm, opt)
+    img3, k3, i3 = O.render_scene([pk], [(0, t, ti)], fp, opt)
+    assert np.array_equal(img2, img3) and np.array_equal(i2, i3)
+    # two instances: every id of the second is offset by the first's splat count, both present
+    img4, k4, i4 = O.render_scene([pk], [(0, ident, ident), (0, t, ti)], fp, opt)
+    assert np.array_equal(np.sort(i4[i4 < 3000]), np.sort(i0)) and np.array_equal(np.sort(i4[i4 >= 3000]) - 3000, np.sort(i2))
+    assert np.all(k4[1:] >= k4[:-1])

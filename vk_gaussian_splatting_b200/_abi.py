@@ -66,6 +66,11 @@ class Outputs(C.Structure):
                 ("bytes_algorithmic", C.c_uint64)]
 
 
+class Instance(C.Structure):
+    _fields_ = [("splat_set_index", C.c_uint32), ("_pad", C.c_uint32), ("transform", C.c_float * 16),
+                ("transform_inverse", C.c_float * 16)]
+
+
 # every symbol include/vkgs_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vkgs_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -77,6 +82,10 @@ SYMBOLS = {
     "vkgs_pack_host": (C.c_int, [C.POINTER(SplatSetView), C.POINTER(Options), f32p, f32p, C.c_void_p, C.c_void_p]),
     "vkgs_upload": (C.c_int, [C.c_void_p, C.POINTER(SplatSetView), C.POINTER(Options)]),
     "vkgs_default_options": (None, [C.POINTER(Options)]),
+    "vkgs_upload_scene": (C.c_int, [C.c_void_p, C.POINTER(SplatSetView), C.c_uint32, C.POINTER(Instance), C.c_uint32,
+                                    C.POINTER(Options)]),
+    "vkgs_set_instance_transform": (C.c_int, [C.c_void_p, C.c_uint32, f32p, f32p]),
+    "vkgs_global_index_table": (C.c_int, [C.c_void_p, u32p, u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "vkgs_frame_params_from_camera": (C.c_int, [C.POINTER(Camera), C.c_uint32, C.c_uint32, C.POINTER(FrameParams)]),
     "vkgs_default_camera": (None, [C.POINTER(Camera)]),
     "vkgs_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.POINTER(Outputs)]),

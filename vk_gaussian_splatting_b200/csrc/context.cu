@@ -45,7 +45,11 @@ void freeSlotScene(FrameSlot& s)
 
 void freeScene(vkgs_ctx* c)
 {
-  freeDev(c->dCenters), freeDev(c->dCov), freeDev(c->dScales), freeDev(c->dRgba), freeDev(c->dSh);
+  for(auto& st : c->sets)
+    freeDev(st.dCenters), freeDev(st.dCov), freeDev(st.dScales), freeDev(st.dRgba), freeDev(st.dSh);
+  c->sets.clear();
+  c->instances.clear();
+  c->totalSplats = c->totalTiles = 0;
   for(auto& s : c->slots)
     freeSlotScene(s);
   c->uploaded = false;
@@ -70,7 +74,7 @@ int allocTileLists(vkgs_ctx* c, FrameSlot& s, uint64_t capacity)
   return VKGS_OK;
 }
 
-int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n)
+int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n, uint64_t preTiles)
 {
   for(int i = 0; i < 2; i++)
   {
@@ -78,7 +82,7 @@ int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n)
     CU_TRY(c, cudaMalloc(&s.dIds[i], n * sizeof(uint32_t)));
   }
   CU_TRY(c, cudaMalloc(&s.dRecords, n * RECORD_WORDS * sizeof(uint32_t)));
-  const uint64_t preTiles = (n + PRE_TILE - 1) / PRE_TILE, binParts = (n + 255) / 256, sortParts = (n + SORT_PART - 1) / SORT_PART;
+  const uint64_t binParts = (n + 255) / 256, sortParts = (n + SORT_PART - 1) / SORT_PART;
   CU_TRY(c, cudaMalloc(&s.dPreStatus, preTiles * sizeof(uint64_t)));
   CU_TRY(c, cudaMalloc(&s.dBinStatus, binParts * sizeof(uint64_t)));
   CU_TRY(c, cudaMalloc(&s.dSortStatus, sortParts * 256 * sizeof(uint64_t)));
@@ -113,13 +117,13 @@ uint32_t nextEpoch(vkgs_ctx* c)
   if(c->epoch >= (1u << 30))
   {
     // epoch space exhausted (2^30 launches): clear the status arrays once and restart
-    const uint64_t n = c->set.count;
+    const uint64_t n = c->totalSplats;
     for(auto& s : c->slots)
     {
       cudaStreamSynchronize(s.stream);
       if(!s.dPreStatus)
         continue;
-      cudaMemset(s.dPreStatus, 0, ((n + PRE_TILE - 1) / PRE_TILE) * sizeof(uint64_t));
+      cudaMemset(s.dPreStatus, 0, c->totalTiles * sizeof(uint64_t));
       cudaMemset(s.dBinStatus, 0, ((n + 255) / 256) * sizeof(uint64_t));
       cudaMemset(s.dSortStatus, 0, ((n + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
       cudaMemset(s.dTileSortStatus, 0, ((s.tileCapacity + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
@@ -132,6 +136,7 @@ uint32_t nextEpoch(vkgs_ctx* c)
 // host-side per-frame constants, evaluated in the oracle's operation order
 void frameConstants(const vkgs_frame_params& fp, float mv[16], float camModel[3])
 {
+  // (fp.model / fp.model_inverse hold the transform of the instance being launched)
   for(int i = 0; i < 4; i++)
     for(int j = 0; j < 4; j++)
       mv[4 * i + j] = ((fp.model[4 * i + 0] * fp.view[0 + j] + fp.model[4 * i + 1] * fp.view[4 + j]) + fp.model[4 * i + 2] * fp.view[8 + j])
@@ -154,7 +159,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   FrameSlot& s  = c->slots[si];
   if(int rc = ensureTargets(c, s, fp.width, fp.height))
     return rc;
-  const uint32_t n  = c->set.count;
+  const uint32_t n  = c->totalSplats;
   const uint32_t tx = (fp.width + TILE_W - 1) / TILE_W, ty = (fp.height + TILE_H - 1) / TILE_H;
   cudaStream_t   st = s.stream;
   auto           mark = [&](int slot) {
@@ -169,20 +174,35 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   mark(0);
 
   // ---- "GPU Dist" (+ the per-splat half of "Rasterization", fused) -----------------------------
-  PreprocessArgs pa{};
-  pa.set = c->set;
-  pa.fp  = fp;
-  pa.opt = c->opt;
-  frameConstants(fp, pa.mv, pa.camModel);
-  pa.keys       = s.dKeys[0];
-  pa.ids        = s.dIds[0];
-  pa.records    = s.dRecords;
-  pa.counters   = s.dCounters;
-  pa.status     = s.dPreStatus;
-  pa.epoch      = nextEpoch(c);
-  pa.ticketSlot = 0;
-  launchPreprocess(pa, st);
-  c->launches++;
+  // One launch per splat-set instance, in global-id order (dist.comp.slang:53 resolves the global id
+  // through the global index table; here the table is implicit in the launch sequence). The launches
+  // chain their deterministic append through counters->visible.
+  for(size_t k = 0; k < c->instances.size(); k++)
+  {
+    const vkgs_ctx::Instance& inst = c->instances[k];
+    PreprocessArgs            pa{};
+    pa.set = c->sets[inst.setIndex].view;
+    pa.fp  = fp;
+    if(!inst.frameModel)
+    {
+      std::memcpy(pa.fp.model, inst.transform, sizeof(pa.fp.model));
+      std::memcpy(pa.fp.model_inverse, inst.transformInverse, sizeof(pa.fp.model_inverse));
+    }
+    pa.opt = c->opt;
+    frameConstants(pa.fp, pa.mv, pa.camModel);
+    pa.keys       = s.dKeys[0];
+    pa.ids        = s.dIds[0];
+    pa.records    = s.dRecords;
+    pa.counters   = s.dCounters;
+    pa.status     = s.dPreStatus + inst.tileOffset;
+    pa.epoch      = nextEpoch(c);
+    pa.ticketSlot = 0;
+    pa.idBase     = inst.globalOffset;
+    pa.ticketBase = inst.tileOffset;
+    pa.chained    = k > 0;
+    launchPreprocess(pa, st);
+    c->launches++;
+  }
   mark(VKGS_K_PREPROCESS + 1);
   mark(VKGS_K_SORT_SCAN + 1);  // (depth-key digit histograms are fused into the preprocess kernel)
 
@@ -333,10 +353,17 @@ void fillStats(vkgs_ctx* c, FrameSlot& s, vkgs_outputs* out)
 {
   out->visible_count = s.hCounters->visible;
   out->tile_pairs    = s.hCounters->tilePairs;
-  const uint64_t n = c->set.count, v = out->visible_count, p = static_cast<uint64_t>(s.lastFp.width) * s.lastFp.height;
-  const uint32_t deg     = std::min(c->set.shDegree, s.lastFp.sh_degree);
-  const uint64_t shB     = 12ull * ((deg + 1) * (deg + 1) - 1);
-  out->bytes_algorithmic = 12 * n + (132 + shB) * v + 16 * p;
+  const uint64_t n = c->totalSplats, v = out->visible_count, p = static_cast<uint64_t>(s.lastFp.width) * s.lastFp.height;
+  // SH bytes per visible splat: exact for one set, splat-count weighted over the instances otherwise
+  double shB = 0.0;
+  for(const auto& inst : c->instances)
+  {
+    const DeviceSplatSet& set = c->sets[inst.setIndex].view;
+    const uint32_t        deg = std::min(set.shDegree, s.lastFp.sh_degree);
+    shB += 12.0 * ((deg + 1) * (deg + 1) - 1) * set.count;
+  }
+  shB                    = n ? shB / static_cast<double>(n) : 0.0;
+  out->bytes_algorithmic = 12 * n + static_cast<uint64_t>((132.0 + shB) * static_cast<double>(v)) + 16 * p;
   std::memset(out->ms_kernel, 0, sizeof(out->ms_kernel));
   out->ms_dist = out->ms_sort = out->ms_raster = out->ms_total = 0.0f;
   if(s.evRecorded)
@@ -376,6 +403,8 @@ uint32_t vkgs_abi_struct_size(int which)
       return sizeof(vkgs_camera);
     case 4:
       return sizeof(vkgs_outputs);
+    case 5:
+      return sizeof(vkgs_instance);
     default:
       return 0;
   }
@@ -518,61 +547,155 @@ int vkgs_set_profiling(vkgs_ctx* c, int enabled)
   return VKGS_OK;
 }
 
-int vkgs_upload(vkgs_ctx* c, const vkgs_splat_set_view* set, const vkgs_options* optIn)
+}  // extern "C"
+
+namespace {
+
+int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount, const vkgs_instance* instances,
+                uint32_t instanceCount, const vkgs_options* optIn)
 {
-  if(!c || !set)
-    return VKGS_ERR_INVALID_ARGUMENT;
   vkgs_options opt;
   if(optIn)
     opt = *optIn;
   else
     vkgs_default_options(&opt);
-  if(set->count == 0 || set->count > 0x7fffffffull)
-    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "splat count must be in 1..2^31-1");
+  if(setCount == 0 || (instances && instanceCount == 0))
+    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "a scene needs at least one splat set and one instance");
   if(opt.frustum_culling_mode > VKGS_FRUSTUM_CULLING_AT_RASTER)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad frustum_culling_mode");
   if(opt.target_format > VKGS_FORMAT_UINT8)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad target_format");
+  uint64_t total = 0;
+  for(uint32_t k = 0; k < (instances ? instanceCount : 1u); k++)
+  {
+    const uint32_t si = instances ? instances[k].splat_set_index : 0u;
+    if(si >= setCount)
+      return fail(c, VKGS_ERR_INVALID_ARGUMENT, "instance refers to a splat set that does not exist");
+    if(sets[si].count == 0)
+      return fail(c, VKGS_ERR_INVALID_ARGUMENT, "splat count must be in 1..2^31-1");
+    total += sets[si].count;
+  }
+  if(total > 0x7fffffffull)
+    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "splat count must be in 1..2^31-1");
   CU_TRY(c, cudaSetDevice(c->device));
   if(int rc = syncAll(c))
     return rc;
 
-  PackedSplatSet packed;
-  if(int rc = packSplatSet(*set, opt, PRE_TILE, packed))
-    return fail(c, rc, "packSplatSet failed (null array, or f_rest_per_splat not 0/45)");
-
   freeScene(c);
-  const uint64_t n  = packed.count;
-  auto           up = [&](void*& dst, const void* src, size_t bytes) -> cudaError_t {
+  auto up = [&](void*& dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(&dst, bytes);
     if(e != cudaSuccess)
       return e;
     return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
   };
-  CU_TRY(c, up(c->dCenters, packed.centers.data(), packed.centers.size() * 4));
-  CU_TRY(c, up(c->dCov, packed.cov6.data(), packed.cov6.size() * 4));
-  CU_TRY(c, up(c->dScales, packed.scales.data(), packed.scales.size() * 4));
-  CU_TRY(c, up(c->dRgba, packed.rgba.data(), packed.rgba.size()));
-  if(packed.shDegree)
-    CU_TRY(c, up(c->dSh, packed.sh.data(), packed.sh.size()));
-  c->set.centers    = static_cast<const float*>(c->dCenters);
-  c->set.cov6       = static_cast<const float*>(c->dCov);
-  c->set.scales     = static_cast<const float*>(c->dScales);
-  c->set.rgba       = c->dRgba;
-  c->set.sh         = c->dSh;
-  c->set.count      = static_cast<uint32_t>(n);
-  c->set.shDegree   = packed.shDegree;
-  c->set.shFormat   = packed.shFormat;
-  c->set.rgbaFormat = packed.rgbaFormat;
-  c->opt            = opt;
+  c->sets.resize(setCount);
+  for(uint32_t i = 0; i < setCount; i++)
+  {
+    PackedSplatSet packed;
+    if(int rc = packSplatSet(sets[i], opt, PRE_TILE, packed))
+    {
+      freeScene(c);
+      return fail(c, rc, "packSplatSet failed (null array, or f_rest_per_splat not 0/45)");
+    }
+    vkgs_ctx::SetStorage& st = c->sets[i];
+    CU_TRY(c, up(st.dCenters, packed.centers.data(), packed.centers.size() * 4));
+    CU_TRY(c, up(st.dCov, packed.cov6.data(), packed.cov6.size() * 4));
+    CU_TRY(c, up(st.dScales, packed.scales.data(), packed.scales.size() * 4));
+    CU_TRY(c, up(st.dRgba, packed.rgba.data(), packed.rgba.size()));
+    if(packed.shDegree)
+      CU_TRY(c, up(st.dSh, packed.sh.data(), packed.sh.size()));
+    st.view.centers    = static_cast<const float*>(st.dCenters);
+    st.view.cov6       = static_cast<const float*>(st.dCov);
+    st.view.scales     = static_cast<const float*>(st.dScales);
+    st.view.rgba       = st.dRgba;
+    st.view.sh         = st.dSh;
+    st.view.count      = static_cast<uint32_t>(packed.count);
+    st.view.shDegree   = packed.shDegree;
+    st.view.shFormat   = packed.shFormat;
+    st.view.rgbaFormat = packed.rgbaFormat;
+  }
+  // instances in creation order: global id = globalOffset + local id (rebuildGlobalIndexTables)
+  uint32_t offset = 0, tiles = 0;
+  for(uint32_t k = 0; k < (instances ? instanceCount : 1u); k++)
+  {
+    vkgs_ctx::Instance inst;
+    inst.setIndex     = instances ? instances[k].splat_set_index : 0u;
+    inst.globalOffset = offset;
+    inst.tileOffset   = tiles;
+    inst.frameModel   = instances == nullptr;
+    if(instances)
+    {
+      std::memcpy(inst.transform, instances[k].transform, sizeof(inst.transform));
+      std::memcpy(inst.transformInverse, instances[k].transform_inverse, sizeof(inst.transformInverse));
+    }
+    const uint32_t cnt = c->sets[inst.setIndex].view.count;
+    offset += cnt;
+    tiles += (cnt + PRE_TILE - 1) / PRE_TILE;
+    c->instances.push_back(inst);
+  }
+  c->totalSplats = offset;
+  c->totalTiles  = tiles;
+  c->opt         = opt;
 
   // sorting / raster buffers (the reference allocates its sorting buffers with the splat set too,
   // src/splat_set_manager_vk.cpp:2426-2517), one set per frame in flight
   for(auto& s : c->slots)
-    if(int rc = allocSlotScene(c, s, n))
+    if(int rc = allocSlotScene(c, s, offset, tiles))
       return rc;
   c->uploaded = true;
   c->nextSlot = 0;
+  return VKGS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vkgs_upload(vkgs_ctx* c, const vkgs_splat_set_view* set, const vkgs_options* optIn)
+{
+  if(!c || !set)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  return uploadScene(c, set, 1, nullptr, 0, optIn);
+}
+
+int vkgs_upload_scene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t set_count, const vkgs_instance* instances,
+                      uint32_t instance_count, const vkgs_options* optIn)
+{
+  if(!c || !sets || !instances)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  return uploadScene(c, sets, set_count, instances, instance_count, optIn);
+}
+
+int vkgs_set_instance_transform(vkgs_ctx* c, uint32_t instance, const float* transform, const float* transform_inverse)
+{
+  if(!c || !transform || !transform_inverse)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(!c->uploaded || instance >= c->instances.size() || c->instances[instance].frameModel)
+    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "no such instance (scenes uploaded with vkgs_upload take their transform from the frame parameters)");
+  // frames already enqueued captured the old transform by value (kernel arguments): no sync needed
+  std::memcpy(c->instances[instance].transform, transform, 16 * sizeof(float));
+  std::memcpy(c->instances[instance].transformInverse, transform_inverse, 16 * sizeof(float));
+  return VKGS_OK;
+}
+
+int vkgs_global_index_table(const vkgs_ctx* c, uint32_t* instance_index, uint32_t* splat_index, uint64_t capacity, uint64_t* total)
+{
+  if(!c || !c->uploaded)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(total)
+    *total = c->totalSplats;
+  for(size_t k = 0; k < c->instances.size(); k++)
+  {
+    const vkgs_ctx::Instance& inst = c->instances[k];
+    const uint32_t            cnt  = c->sets[inst.setIndex].view.count;
+    for(uint32_t i = 0; i < cnt && inst.globalOffset + i < capacity; i++)
+    {
+      if(instance_index)
+        instance_index[inst.globalOffset + i] = static_cast<uint32_t>(k);
+      if(splat_index)
+        splat_index[inst.globalOffset + i] = i;
+    }
+  }
   return VKGS_OK;
 }
 
@@ -646,7 +769,7 @@ int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
 
 int vkgs_read_records(vkgs_ctx* c, uint32_t* records12, uint64_t first, uint64_t count)
 {
-  if(!c || !records12 || !c->uploaded || c->lastSlot < 0 || first + count > c->set.count)
+  if(!c || !records12 || !c->uploaded || c->lastSlot < 0 || first + count > c->totalSplats)
     return VKGS_ERR_INVALID_ARGUMENT;
   FrameSlot& s = c->slots[c->lastSlot];
   CU_TRY(c, cudaStreamSynchronize(s.stream));
@@ -658,17 +781,18 @@ int vkgs_read_packed(vkgs_ctx* c, float* centers, float* cov6, float* rgba, floa
 {
   if(!c || !c->uploaded)
     return VKGS_ERR_INVALID_ARGUMENT;
-  if(c->set.shFormat != VKGS_FORMAT_FLOAT32 || c->set.rgbaFormat != VKGS_FORMAT_FLOAT32)
+  const vkgs_ctx::SetStorage& st = c->sets[0];  // (splat set 0)
+  if(st.view.shFormat != VKGS_FORMAT_FLOAT32 || st.view.rgbaFormat != VKGS_FORMAT_FLOAT32)
     return fail(c, VKGS_ERR_UNSUPPORTED, "vkgs_read_packed needs fp32 formats");
-  const uint64_t n = c->set.count;
+  const uint64_t n = st.view.count;
   if(centers)
-    CU_TRY(c, cudaMemcpy(centers, c->dCenters, n * 12, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(centers, st.dCenters, n * 12, cudaMemcpyDeviceToHost));
   if(cov6)
-    CU_TRY(c, cudaMemcpy(cov6, c->dCov, n * 24, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(cov6, st.dCov, n * 24, cudaMemcpyDeviceToHost));
   if(rgba)
-    CU_TRY(c, cudaMemcpy(rgba, c->dRgba, n * 16, cudaMemcpyDeviceToHost));
-  if(sh && c->dSh)
-    CU_TRY(c, cudaMemcpy(sh, c->dSh, n * 180, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(rgba, st.dRgba, n * 16, cudaMemcpyDeviceToHost));
+  if(sh && st.dSh)
+    CU_TRY(c, cudaMemcpy(sh, st.dSh, n * 180, cudaMemcpyDeviceToHost));
   return VKGS_OK;
 }
 

@@ -1,6 +1,7 @@
 // context.hpp — the context object behind the C ABI (shared by context.cu and sort_api.cu)
 #pragma once
 #include <string>
+#include <vector>
 
 #include "kernels.hpp"
 #include "vkgs_b200.h"
@@ -46,11 +47,29 @@ struct vkgs_ctx
   int          nextSlot  = 0;
   int          lastSlot  = -1;
 
-  // scene (shared by all slots)
-  bool                 uploaded = false;
-  vkgs_options         opt{};
-  vkgs::DeviceSplatSet set{};
-  void *               dCenters = nullptr, *dCov = nullptr, *dScales = nullptr, *dRgba = nullptr, *dSh = nullptr;
+  // scene (shared by all slots): splat sets in HBM + the instances that place them in the world.
+  // Global splat id = instance.globalOffset + local id, instances in creation order — the layout of
+  // the reference's global index table (SplatSetManagerVk::rebuildGlobalIndexTables,
+  // src/splat_set_manager_vk.cpp:2304-2360), here implicit: one preprocess launch per instance.
+  struct SetStorage
+  {
+    vkgs::DeviceSplatSet view{};
+    void *               dCenters = nullptr, *dCov = nullptr, *dScales = nullptr, *dRgba = nullptr, *dSh = nullptr;
+  };
+  struct Instance
+  {
+    uint32_t setIndex     = 0;
+    uint32_t globalOffset = 0;
+    uint32_t tileOffset   = 0;     // first preprocess tile (ticket / look-back status index) of the instance
+    bool     frameModel   = false; // transform comes from vkgs_frame_params.model (single-set vkgs_upload)
+    float    transform[16]{}, transformInverse[16]{};
+  };
+  bool                  uploaded = false;
+  vkgs_options          opt{};
+  std::vector<SetStorage> sets;
+  std::vector<Instance>   instances;
+  uint32_t              totalSplats = 0;  // sum over instances
+  uint32_t              totalTiles  = 0;  // preprocess tiles over all instances
 
   vkgs::FrameSlot slots[vkgs::MAX_FRAMES_IN_FLIGHT];
 };

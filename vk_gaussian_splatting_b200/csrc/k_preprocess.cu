@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   // ---- claim a tile (ticket order == look-back order) and start the bulk copies ---------------
   if(tid == 0)
   {
-    sm.tile = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u);
+    sm.tile = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u) - a.ticketBase;
     mbar_init(&sm.mbarA, 1);
     mbar_init(&sm.mbarB, 1);
     mbar_fence_init();
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     atomicAdd(&sm.hist[3][key >> 24], 1u);
   }
   __syncthreads();
-  uint32_t tileTotal = 0;
+  uint32_t tileTotal = 0, chainBase = 0;
   if(warp == 0)
   {
     const uint32_t cnt = lane < NWARPS ? sm.warpScan[lane] : 0u;
@@ -226,8 +226,12 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     if(lane < NWARPS)
       sm.warpScan[lane] = inc - cnt;
     tileTotal = __shfl_sync(FULL_MASK, inc, NWARPS - 1);
+    // (tile 0 of a chained launch continues after the pairs appended by the earlier instances: those
+    //  launches completed, stream order, so counters->visible is final)
+    if(tile == 0 && a.chained)
+      chainBase = a.counters->visible;
     if(lane == 0 && !(ablate & 1u))
-      lb_store(a.status + tile, lb_pack(a.epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, tileTotal));
+      lb_store(a.status + tile, lb_pack(a.epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, chainBase + tileTotal));
   }
 
   // ---- K5: per-splat projection + colour (threedgs_raster.mesh.slang:161-289) -------------------
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     }
     if(!valid)
       bb0 = 1u, bb1 = 0u;
-    float4* rec = reinterpret_cast<float4*>(a.records + id * RECORD_WORDS);
+    float4* rec = reinterpret_cast<float4*>(a.records + (a.idBase + id) * RECORD_WORDS);
     if(!(ablate & 4u))
     {
     rec[0]      = make_float4(cx, cy, w1x, w1y);
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   // ---- deterministic append, part 2: resolve the exclusive prefix (predecessors published long ago)
   if(warp == 0)
   {
-    uint32_t excl = 0;
+    uint32_t excl = chainBase;  // (non-zero for tile 0 of a chained launch only)
     if(ablate & 1u)
     {
       if(lane == 0)
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   {
     const uint32_t slot = sm.basePrefix + sm.warpScan[warp] + warpRank;
     a.keys[slot]        = key;
-    a.ids[slot]         = static_cast<uint32_t>(id);
+    a.ids[slot]         = a.idBase + static_cast<uint32_t>(id);
   }
   // flush the digit histograms of the four sort passes (only bins this tile touched)
   for(int i = tid; i < 4 * 256; i += PRE_TILE)

@@ -56,9 +56,16 @@ struct PreprocessArgs
   uint32_t*         ids;         // [V]
   uint32_t*         records;     // [N][RECORD_WORDS], indexed by splat id
   FrameCounters*    counters;
-  uint64_t*         status;      // look-back chain, one word per tile
+  uint64_t*         status;      // look-back chain, one word per tile (of THIS launch)
   uint32_t          epoch;
   uint32_t          ticketSlot;
+  // Multi-instance scenes (one launch per splat-set instance, in global-id order; replaces the
+  // reference's global index table, src/splat_set_manager_vk.cpp:2304-2360): global id = idBase +
+  // local id; tickets already handed out by earlier launches of the frame; and whether the append
+  // continues after the pairs of earlier instances (base = counters->visible).
+  uint32_t          idBase;
+  uint32_t          ticketBase;
+  uint32_t          chained;
 };
 
 void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream);
