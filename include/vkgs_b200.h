@@ -171,7 +171,7 @@ VKGS_API int vkgs_set_stream(vkgs_ctx* ctx, void* cuda_stream);
 VKGS_API const char* vkgs_last_error(const vkgs_ctx* ctx);
 VKGS_API const char* vkgs_version(void);
 /* sizeof() of the ABI structs as compiled, for binding validation:
- * 0 vkgs_splat_set_view, 1 vkgs_options, 2 vkgs_frame_params, 3 vkgs_camera, 4 vkgs_outputs, 5 vkgs_instance */
+ * 0 vkgs_splat_set_view, 1 vkgs_options, 2 vkgs_frame_params, 3 vkgs_camera, 4 vkgs_outputs, 5 vkgs_instance, 6 vkgs_image_metrics */
 VKGS_API uint32_t vkgs_abi_struct_size(int which);
 
 /* ---- scene upload (replaces SplatSetVk::initDataStorage/initDataBuffers,
@@ -245,6 +245,27 @@ VKGS_API uint64_t vkgs_launch_count(const vkgs_ctx* ctx);
  *      averaged over `repeats` runs (>=1) on the same input. */
 VKGS_API int vkgs_sort_pairs(vkgs_ctx* ctx, const uint32_t* keys, const uint32_t* values, uint64_t n,
                     uint32_t* keys_out, uint32_t* values_out, int repeats, float* ms_device);
+
+/* ---- image comparison metrics (replaces ImageCompare's metrics pass: shaders/image_compare_metric.comp.slang:84-190,
+ *      371-477, dispatch src/image_compare.cpp:770-830, read-back src/image_compare.cpp:874-905).
+ *      MSE over RGB with the reference's fixed-point accumulation (uint32, x1e9, normalised by W*H*3),
+ *      PSNR = min(10 log10(1/MSE), 99.99) dB, and the reference's fast FLIP approximation (YCxCz colour
+ *      error + Sobel feature error, Minkowski pooling q = 3). FLIP "reference" mode is not built. */
+#define VKGS_FLIP_DISABLED 0
+#define VKGS_FLIP_APPROX 1
+typedef struct vkgs_image_metrics
+{
+  float    mse, psnr, flip;
+  uint32_t mse_fixed, flip_fixed; /* the raw accumulators of the reference's result buffer ([0] and [8]) */
+  float    ms_device;             /* device time of the metrics kernel */
+} vkgs_image_metrics;
+/* Keep a copy of the last rendered frame as the "capture image" (fp32 colour target). */
+VKGS_API int vkgs_capture_frame(vkgs_ctx* ctx);
+/* Metrics between the capture and the last rendered frame (same size). */
+VKGS_API int vkgs_compare_with_capture(vkgs_ctx* ctx, uint32_t flip_mode, vkgs_image_metrics* out);
+/* The same kernel on two HOST images (W*H*4 fp32 each): reference = capture, current. */
+VKGS_API int vkgs_image_metrics_host(vkgs_ctx* ctx, const float* reference, const float* current, uint32_t width, uint32_t height,
+                                     uint32_t flip_mode, vkgs_image_metrics* out);
 
 /* ---- parity/debug read-backs of per-splat intermediates of the last frame ----------------
  * Per-splat record, indexed by splat id (only ids that passed the dist-stage cull are valid):

@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         l.orc_render_scene.argtypes = [C.POINTER(OrcSet), C.c_uint32, C.POINTER(OrcInstance), C.c_uint32,
                                        C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p, u32p, u32p]
         l.orc_render_scene.restype = C.c_uint32
+        l.orc_image_metrics.argtypes = [f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
         l.orc_quad_size.restype = C.c_uint32
         l.orc_cpu_sort.argtypes = [f32p, C.c_uint64, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, u32p, f32p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -174,6 +175,20 @@ def render_scene(packed_sets, instances, fp, opt):
     ids = np.empty(total, np.uint32)
     v = lib().orc_render_scene(sets, len(packed_sets), inst, len(instances), C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids))
     return img, keys[:v].copy(), ids[:v].copy()
+
+
+def image_metrics(reference, current, flip_mode=0):
+    """(mse_fixed, flip_fixed, mse, psnr, flip): the shader's accumulators + the read-back arithmetic of
+    src/image_compare.cpp:874-905."""
+    ref = np.ascontiguousarray(reference, np.float32)
+    cur = np.ascontiguousarray(current, np.float32)
+    h, w = ref.shape[:2]
+    res = np.zeros(4, np.uint32)
+    lib().orc_image_metrics(_p(ref), _p(cur), w, h, flip_mode, _u(res))
+    mse = np.float32(res[0]) / np.float32(1000000000.0)
+    psnr = np.float32(99.99) if mse < 1e-10 else min(np.float32(10.0) * np.log10(np.float32(1.0) / mse), np.float32(99.99))
+    flip = np.float32((float(res[2]) / 1000000000.0) ** (1.0 / 3.0))
+    return int(res[0]), int(res[2]), float(mse), float(psnr), float(flip)
 
 
 def project_splat(packed: Packed, idx: int, fp, opt) -> Quad:

@@ -30,7 +30,7 @@ def test_header_declares_and_library_exports_every_symbol():
 
 def test_struct_sizes_match_compiled_abi():
     l = A.lib()
-    for which, st in enumerate([A.SplatSetView, A.Options, A.FrameParams, A.Camera, A.Outputs, A.Instance]):
+    for which, st in enumerate([A.SplatSetView, A.Options, A.FrameParams, A.Camera, A.Outputs, A.Instance, A.ImageMetrics]):
         assert l.vkgs_abi_struct_size(which) == C.sizeof(st), st.__name__
     assert l.vkgs_abi_struct_size(99) == 0
 

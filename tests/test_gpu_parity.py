@@ -392,3 +392,31 @@ def _with_model(fp, t, ti):
     fp.model[:] = np.asarray(t, np.float32).reshape(16).tolist()
     fp.model_inverse[:] = np.asarray(ti, np.float32).reshape(16).tolist()
     return fp
+
+
+def test_image_metrics_match_oracle(gpu_renderer):
+    """MSE accumulator bit-exact (integer adds of identically rounded per-pixel terms), PSNR identical,
+    FLIP-approx within 1e-4 relative (libm vs device powf/expf differ in the last ulp); capture/compare
+    on rendered frames (ImageCompare, src/image_compare.cpp:770-905)."""
+    r = gpu_renderer
+    rng = np.random.default_rng(11)
+    for (h, w) in ((37, 53), (360, 640)):
+        a = rng.random((h, w, 4), dtype=np.float32)
+        b = np.clip(a + rng.normal(0, 0.05, a.shape).astype(np.float32), 0, 1)
+        for mode in (A.FLIP_DISABLED, A.FLIP_APPROX):
+            m = r.image_metrics(a, b, mode)
+            mf, ff, mse, psnr, flip = O.image_metrics(a, b, mode)
+            assert m.mse_fixed == mf and m.mse == mse and m.psnr == pytest.approx(psnr, abs=1e-5)
+            assert abs(int(m.flip_fixed) - ff) <= max(4, 1e-4 * ff) and m.flip == pytest.approx(flip, rel=1e-4, abs=1e-6)
+    # rendered frames: capture one camera, compare with a slightly different one
+    s = g.synth_scene(40_000, 3, 0x3D6500D1)
+    r.upload(s, g.default_options(front_to_back=1))
+    cam0, cam1 = g.default_camera(), g.make_camera((1.72, 1.5, 1.68))
+    img0, _, _, _ = r.render(g.frame_params(cam0, 480, 270))
+    r.capture_frame()
+    same = r.compare_with_capture(A.FLIP_APPROX)
+    assert same.mse_fixed == 0 and same.flip_fixed == 0 and same.psnr == pytest.approx(99.99)
+    img1, _, _, _ = r.render(g.frame_params(cam1, 480, 270))
+    m = r.compare_with_capture(A.FLIP_APPROX)
+    mf, ff, mse, psnr, flip = O.image_metrics(img0, img1, 1)
+    assert m.mse_fixed == mf > 0 and m.psnr == pytest.approx(psnr, abs=1e-5) and m.flip == pytest.approx(flip, rel=1e-4)

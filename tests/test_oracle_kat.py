@@ -241,3 +241,41 @@ def test_multi_instance_oracle_reduces_to_single_instance_and_composes():
     img4, k4, i4 = O.render_scene([pk], [(0, ident, ident), (0, t, ti)], fp, opt)
     assert np.array_equal(np.sort(i4[i4 < 3000]), np.sort(i0)) and np.array_equal(np.sort(i4[i4 >= 3000]) - 3000, np.sort(i2))
     assert np.all(k4[1:] >= k4[:-1])
+
+
+def test_image_metrics_known_answers():
+    """MSE / PSNR / FLIP-approx restatement (image_compare_metric.comp.slang, image_compare.cpp:874-905)."""
+    rng = np.random.default_rng(3)
+    a = rng.random((48, 64, 4), dtype=np.float32)
+    # identical images: zero error, PSNR clamps to 99.99 dB, FLIP 0
+    mf, ff, mse, psnr, flip = O.image_metrics(a, a, 1)
+    assert (mf, ff, mse, flip) == (0, 0, 0.0, 0.0) and psnr == pytest.approx(99.99)
+    # constant offset d on RGB: MSE = d^2 (alpha ignored), PSNR = -20 log10 d; truncation loses < 1 unit per pixel
+    b = a.copy()
+    b[..., :3] += np.float32(0.1)
+    b[..., 3] = 0.0
+    mf, ff, mse, psnr, flip = O.image_metrics(a, b, 0)
+    n = 48 * 64
+    assert 0.01 * 1e9 - n <= mf <= 0.01 * 1e9 + 40 and ff == 0
+    assert mse == pytest.approx(0.01, rel=1e-3) and psnr == pytest.approx(20.0, abs=0.01)
+    # float64 restatement of the per-pixel MSE sum
+    c = rng.random((48, 64, 4), dtype=np.float32)
+    mf, _, mse, _, _ = O.image_metrics(a, c, 0)
+    want = np.sum((a[..., :3].astype(np.float64) - c[..., :3]) ** 2) / (n * 3)
+    assert mse == pytest.approx(want, rel=1e-4)
+    # FLIP approx, flat black vs flat white (no Sobel response), worked by hand in float64:
+    # F_L = 0.2 k^(1/3) (1 - exp(-0.42 k^(1/3))), k = 5; YCxCz(white) = F_L (M, L-M, M-S) with the HPE row sums;
+    # error = csf(1cpd) (|dY| + 0.4 |dCx| + 0.4 |dCz|); uniform image -> pooled value = per-pixel error
+    z, o = np.zeros((32, 32, 4), np.float32), np.ones((32, 32, 4), np.float32)
+    _, ff, _, _, flip = O.image_metrics(z, o, 1)
+    kc = 5.0 ** (1 / 3)
+    fl = 0.2 * kc * (1 - math.exp(-0.42 * kc))
+    L, M, S = 0.31670331 + 0.70299344 - 0.01969366, 0.10938715 + 0.87060437 + 0.01990658, 0.01840087 + 0.10476914 + 0.87470614
+    csf = math.exp(-0.5) / math.sqrt(1 + (1 / 4) ** 2)
+    want = fl * csf * (M + 0.4 * abs(L - M) + 0.4 * abs(M - S))
+    # (each of the 1024 pixels contributes uint(want^3 / 1024 * 1e9) = 1072 of 1072.8: truncation, as in the shader)
+    assert ff == 1024 * int(np.float32(want) ** 3 / 1024 * 1e9) and flip == pytest.approx(want, rel=5e-4)
+    # monotone in the size of the error
+    f1 = O.image_metrics(a, np.clip(a + 0.02, 0, 1), 1)[4]
+    f2 = O.image_metrics(a, np.clip(a + 0.10, 0, 1), 1)[4]
+    assert 0 < f1 < f2 < 1

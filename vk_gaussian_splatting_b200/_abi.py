@@ -71,6 +71,13 @@ class Instance(C.Structure):
                 ("transform_inverse", C.c_float * 16)]
 
 
+class ImageMetrics(C.Structure):
+    _fields_ = [("mse", C.c_float), ("psnr", C.c_float), ("flip", C.c_float), ("mse_fixed", C.c_uint32),
+                ("flip_fixed", C.c_uint32), ("ms_device", C.c_float)]
+
+
+FLIP_DISABLED, FLIP_APPROX = 0, 1
+
 # every symbol include/vkgs_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vkgs_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -99,6 +106,9 @@ SYMBOLS = {
     "vkgs_device_framebuffer": (C.c_void_p, [C.c_void_p]),
     "vkgs_launch_count": (C.c_uint64, [C.c_void_p]),
     "vkgs_sort_pairs": (C.c_int, [C.c_void_p, u32p, u32p, C.c_uint64, u32p, u32p, C.c_int, f32p]),
+    "vkgs_capture_frame": (C.c_int, [C.c_void_p]),
+    "vkgs_compare_with_capture": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ImageMetrics)]),
+    "vkgs_image_metrics_host": (C.c_int, [C.c_void_p, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ImageMetrics)]),
     "vkgs_read_records": (C.c_int, [C.c_void_p, u32p, C.c_uint64, C.c_uint64]),
     "vkgs_read_packed": (C.c_int, [C.c_void_p, f32p, f32p, f32p, f32p]),
     "vkgs_scene_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -22,8 +22,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
           f"-I{ROOT / 'include'}", f"-I{CSRC}"]
 # per-file extra flags: the per-splat front end must not contract mul+add (bit-exact vs the oracle)
-EXTRA = {"k_preprocess.cu": ["-fmad=false"]}
-SOURCES = ["context.cu", "sort_api.cu", "k_preprocess.cu", "k_radix_sort.cu", "k_binning.cu", "k_blend.cu",
+EXTRA = {"k_preprocess.cu": ["-fmad=false"], "k_metrics.cu": ["-fmad=false"]}
+SOURCES = ["context.cu", "sort_api.cu", "k_preprocess.cu", "k_radix_sort.cu", "k_binning.cu", "k_blend.cu", "k_metrics.cu",
            "host_camera.cpp", "host_pack.cpp", "host_synth.cpp", "host_loader.cpp"]
 
 

@@ -405,6 +405,8 @@ uint32_t vkgs_abi_struct_size(int which)
       return sizeof(vkgs_outputs);
     case 5:
       return sizeof(vkgs_instance);
+    case 6:
+      return sizeof(vkgs_image_metrics);
     default:
       return 0;
   }
@@ -481,6 +483,7 @@ int vkgs_destroy(vkgs_ctx* c)
     if(s.stream)
       cudaStreamSynchronize(s.stream);
   freeScene(c);
+  freeDev(c->dCapture);
   for(auto& s : c->slots)
   {
     freeDev(s.dImage), freeDev(s.dRanges), freeDev(s.dCounters);

@@ -72,6 +72,10 @@ struct vkgs_ctx
   uint32_t              totalTiles  = 0;  // preprocess tiles over all instances
 
   vkgs::FrameSlot slots[vkgs::MAX_FRAMES_IN_FLIGHT];
+
+  // image comparison: the captured frame (ImageCompare's capture image, src/image_compare.cpp)
+  void*    dCapture = nullptr;
+  uint32_t captureW = 0, captureH = 0;
 };
 
 #define CU_TRY(ctx, expr)                                                                                                      \
