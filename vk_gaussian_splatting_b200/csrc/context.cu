@@ -177,6 +177,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   // One launch per splat-set instance, in global-id order (dist.comp.slang:53 resolves the global id
   // through the global index table; here the table is implicit in the launch sequence). The launches
   // chain their deterministic append through counters->visible.
+  uint32_t ticketsDrawn = 0;
   for(size_t k = 0; k < c->instances.size(); k++)
   {
     const vkgs_ctx::Instance& inst = c->instances[k];
@@ -198,8 +199,9 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     pa.epoch      = nextEpoch(c);
     pa.ticketSlot = 0;
     pa.idBase     = inst.globalOffset;
-    pa.ticketBase = inst.tileOffset;
+    pa.ticketBase = ticketsDrawn;
     pa.chained    = k > 0;
+    ticketsDrawn += (pa.set.count + PRE_TILE - 1) / PRE_TILE + preprocessGrid(pa);
     launchPreprocess(pa, st);
     c->launches++;
   }

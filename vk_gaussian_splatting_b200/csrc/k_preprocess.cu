@@ -125,39 +125,52 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   const unsigned tid  = threadIdx.x;
   const unsigned lane = tid & 31u, warp = tid >> 5;
 
-  // ---- claim a tile (ticket order == look-back order) and start the bulk copies ---------------
-  if(tid == 0)
-  {
-    sm.tile = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u) - a.ticketBase;
-    mbar_init(&sm.mbarA, 1);
-    mbar_init(&sm.mbarB, 1);
-    mbar_fence_init();
-  }
-  for(int i = tid; i < 4 * 256; i += PRE_TILE)
-    (&sm.hist[0][0])[i] = 0u;
-  __syncthreads();
-  const uint32_t tile    = sm.tile;
-  const uint64_t first   = static_cast<uint64_t>(tile) * PRE_TILE;
   const uint32_t shElem  = SHFMT == VKGS_FORMAT_FLOAT32 ? 4u : (SHFMT == VKGS_FORMAT_FLOAT16 ? 2u : 1u);
   const uint32_t rgbaEl  = a.set.rgbaFormat == VKGS_FORMAT_FLOAT32 ? 4u : (a.set.rgbaFormat == VKGS_FORMAT_FLOAT16 ? 2u : 1u);
   const bool     hasSh   = a.set.sh != nullptr && a.set.shDegree > 0 && a.fp.sh_degree > 0;
   const bool     sizeCul = a.opt.size_culling_mode == VKGS_SIZE_CULLING_ENABLED;
+  const uint32_t ablate  = a.opt._reserved[4];
+  const uint32_t tiles   = (a.set.count + PRE_TILE - 1) / PRE_TILE;
+
+  // claim a tile (ticket order == look-back order) and start its bulk copies. Stage A: what the
+  // cull needs; stage B: everything else — two barriers so the cull (and the early publication of
+  // the tile's visible count) does not wait for the 46 KB of SH.
+  auto claimAndLoad = [&]() -> uint32_t {
+    const uint32_t t = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u) - a.ticketBase;
+    if(t < tiles)
+    {
+      const uint64_t f = static_cast<uint64_t>(t) * PRE_TILE;
+      mbar_arrive_expect_tx(&sm.mbarA, PRE_TILE * 3 * 4 * (sizeCul ? 2u : 1u));
+      bulk_copy_g2s(sm.center, a.set.centers + f * 3, PRE_TILE * 3 * 4, &sm.mbarA);
+      if(sizeCul)
+        bulk_copy_g2s(sm.scale, a.set.scales + f * 3, PRE_TILE * 3 * 4, &sm.mbarA);
+      mbar_arrive_expect_tx(&sm.mbarB, PRE_TILE * 6 * 4 + PRE_TILE * 4 * rgbaEl + (hasSh ? PRE_TILE * 45 * shElem : 0u));
+      bulk_copy_g2s(sm.cov, a.set.cov6 + f * 6, PRE_TILE * 6 * 4, &sm.mbarB);
+      bulk_copy_g2s(sm.rgba, static_cast<const unsigned char*>(a.set.rgba) + f * 4 * rgbaEl, PRE_TILE * 4 * rgbaEl, &sm.mbarB);
+      if(hasSh)
+        bulk_copy_g2s(sm.sh, static_cast<const unsigned char*>(a.set.sh) + f * 45 * shElem, PRE_TILE * 45 * shElem, &sm.mbarB);
+    }
+    return t;
+  };
+
+  // ---- persistent CTA: per-CTA fixed costs (barrier init, histogram zero / flush, launch) are paid
+  // once, and the bulk copies of tile i+1 are issued as soon as tile i's shared data is dead, so
+  // they fly during tile i's look-back / append ------------------------------------------------
   if(tid == 0)
   {
-    // stage A: what the cull needs; stage B: everything else. Two barriers so the cull (and the
-    // early publication of this tile's visible count) does not wait for the 46 KB of SH.
-    mbar_arrive_expect_tx(&sm.mbarA, PRE_TILE * 3 * 4 * (sizeCul ? 2u : 1u));
-    bulk_copy_g2s(sm.center, a.set.centers + first * 3, PRE_TILE * 3 * 4, &sm.mbarA);
-    if(sizeCul)
-      bulk_copy_g2s(sm.scale, a.set.scales + first * 3, PRE_TILE * 3 * 4, &sm.mbarA);
-    mbar_arrive_expect_tx(&sm.mbarB, PRE_TILE * 6 * 4 + PRE_TILE * 4 * rgbaEl + (hasSh ? PRE_TILE * 45 * shElem : 0u));
-    bulk_copy_g2s(sm.cov, a.set.cov6 + first * 6, PRE_TILE * 6 * 4, &sm.mbarB);
-    bulk_copy_g2s(sm.rgba, static_cast<const unsigned char*>(a.set.rgba) + first * 4 * rgbaEl, PRE_TILE * 4 * rgbaEl, &sm.mbarB);
-    if(hasSh)
-      bulk_copy_g2s(sm.sh, static_cast<const unsigned char*>(a.set.sh) + first * 45 * shElem, PRE_TILE * 45 * shElem, &sm.mbarB);
+    mbar_init(&sm.mbarA, 1);
+    mbar_init(&sm.mbarB, 1);
+    mbar_fence_init();
+    sm.tile = claimAndLoad();
   }
-  mbar_wait(&sm.mbarA, 0);
-  const uint32_t ablate = a.opt._reserved[4];
+  for(int i = tid; i < 4 * 256; i += PRE_TILE)
+    (&sm.hist[0][0])[i] = 0u;
+  __syncthreads();
+  uint32_t tile = sm.tile;
+  for(uint32_t phase = 0; tile < tiles; phase ^= 1u)
+  {
+  const uint64_t first = static_cast<uint64_t>(tile) * PRE_TILE;
+  mbar_wait(&sm.mbarA, phase);
 
   const uint64_t id    = first + tid;
   const bool     inSet = id < a.set.count;
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   }
 
   // ---- K5: per-splat projection + colour (threedgs_raster.mesh.slang:161-289) -------------------
-  mbar_wait(&sm.mbarB, 0);
+  mbar_wait(&sm.mbarB, phase);
   if(keep)
   {
     float4   col   = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
@@ -380,6 +393,11 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   }
 
 
+  // every thread is done with this tile's shared data: claim the next tile and start its copies now
+  __syncthreads();
+  if(tid == 0)
+    sm.tile = claimAndLoad();
+
   // ---- deterministic append, part 2: resolve the exclusive prefix (predecessors published long ago)
   if(warp == 0)
   {
@@ -410,7 +428,11 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     a.keys[slot]        = key;
     a.ids[slot]         = a.idBase + static_cast<uint32_t>(id);
   }
-  // flush the digit histograms of the four sort passes (only bins this tile touched)
+  tile = sm.tile;
+  }  // persistent tile loop
+
+  // flush the digit histograms of the four sort passes (only bins this CTA touched)
+  __syncthreads();
   for(int i = tid; i < 4 * 256; i += PRE_TILE)
   {
     const uint32_t v = (&sm.hist[0][0])[i];
@@ -421,28 +443,50 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
 
 }  // namespace
 
+namespace {
+int g_preGrid[3] = {0, 0, 0};  // resident CTAs of k_preprocess<fmt> on this device (SMs x CTAs per SM)
+}
+
 void initPreprocessKernels()
 {
   const int smem = static_cast<int>(sizeof(PreSmem));
   cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_UINT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int dev = 0, sms = 0, per[3] = {0, 0, 0};
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per[0], k_preprocess<VKGS_FORMAT_FLOAT32>, PRE_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per[1], k_preprocess<VKGS_FORMAT_FLOAT16>, PRE_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per[2], k_preprocess<VKGS_FORMAT_UINT8>, PRE_TILE, smem);
+  for(int i = 0; i < 3; i++)
+    g_preGrid[i] = sms * (per[i] > 0 ? per[i] : 1);
+}
+
+uint32_t preprocessGrid(const PreprocessArgs& args)
+{
+  const uint32_t tiles = (args.set.count + PRE_TILE - 1) / PRE_TILE;
+  const uint32_t fmt   = args.set.shFormat <= VKGS_FORMAT_UINT8 ? args.set.shFormat : 0u;
+  const uint32_t cap   = g_preGrid[fmt] > 0 ? static_cast<uint32_t>(g_preGrid[fmt]) : 148u * 3u;
+  return tiles < cap ? tiles : cap;
 }
 
 void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream)
 {
-  const uint32_t tiles = (args.set.count + PRE_TILE - 1) / PRE_TILE;
-  const size_t   smem  = sizeof(PreSmem);
+  const uint32_t grid = preprocessGrid(args);
+  if(grid == 0)
+    return;
+  const size_t smem = sizeof(PreSmem);
   switch(args.set.shFormat)
   {
     case VKGS_FORMAT_FLOAT16:
-      k_preprocess<VKGS_FORMAT_FLOAT16><<<tiles, PRE_TILE, smem, stream>>>(args);
+      k_preprocess<VKGS_FORMAT_FLOAT16><<<grid, PRE_TILE, smem, stream>>>(args);
       break;
     case VKGS_FORMAT_UINT8:
-      k_preprocess<VKGS_FORMAT_UINT8><<<tiles, PRE_TILE, smem, stream>>>(args);
+      k_preprocess<VKGS_FORMAT_UINT8><<<grid, PRE_TILE, smem, stream>>>(args);
       break;
     default:
-      k_preprocess<VKGS_FORMAT_FLOAT32><<<tiles, PRE_TILE, smem, stream>>>(args);
+      k_preprocess<VKGS_FORMAT_FLOAT32><<<grid, PRE_TILE, smem, stream>>>(args);
       break;
   }
 }

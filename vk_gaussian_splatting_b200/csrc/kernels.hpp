@@ -61,7 +61,7 @@ struct PreprocessArgs
   uint32_t          ticketSlot;
   // Multi-instance scenes (one launch per splat-set instance, in global-id order; replaces the
   // reference's global index table, src/splat_set_manager_vk.cpp:2304-2360): global id = idBase +
-  // local id; tickets already handed out by earlier launches of the frame; and whether the append
+  // local id; tickets already drawn by earlier launches of the frame (tiles + CTAs of each); and whether the append
   // continues after the pairs of earlier instances (base = counters->visible).
   uint32_t          idBase;
   uint32_t          ticketBase;
@@ -69,6 +69,9 @@ struct PreprocessArgs
 };
 
 void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream);
+// CTAs of the (persistent) preprocess launch for these arguments; each CTA draws one ticket per tile
+// it processes plus one final ticket, so a launch consumes tiles + grid tickets.
+uint32_t preprocessGrid(const PreprocessArgs& args);
 
 struct SortPassArgs
 {
