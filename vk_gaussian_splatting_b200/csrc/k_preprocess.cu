@@ -41,7 +41,7 @@ struct PreSmem
   uint32_t hist[4][256];  // digit histograms of this tile's keys (all four sort passes)
   uint32_t warpScan[NWARPS + 1];
   uint32_t tile;
-  uint32_t basePrefix;
+  uint32_t basePrefix[2];  // exclusive prefix of the tile processed in iteration parity 0 / 1
 };
 
 __device__ __forceinline__ uint32_t encodeMinMaxFp32(float v)
@@ -135,9 +135,14 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   // claim a tile (ticket order == look-back order) and start its bulk copies. Stage A: what the
   // cull needs; stage B: everything else — two barriers so the cull (and the early publication of
   // the tile's visible count) does not wait for the 46 KB of SH.
-  auto claimAndLoad = [&]() -> uint32_t {
+  // (thread 0 only. The tile index travels with barrier A: it is stored before the arrive (release) and
+  //  read by everybody after the wait (acquire); with no tile left the barrier completes at once.)
+  auto claimAndLoad = [&]() {
     const uint32_t t = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u) - a.ticketBase;
-    if(t < tiles)
+    sm.tile          = t;
+    if(t >= tiles)
+      mbar_arrive_expect_tx(&sm.mbarA, 0u);
+    else
     {
       const uint64_t f = static_cast<uint64_t>(t) * PRE_TILE;
       mbar_arrive_expect_tx(&sm.mbarA, PRE_TILE * 3 * 4 * (sizeCul ? 2u : 1u));
@@ -150,7 +155,6 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
       if(hasSh)
         bulk_copy_g2s(sm.sh, static_cast<const unsigned char*>(a.set.sh) + f * 45 * shElem, PRE_TILE * 45 * shElem, &sm.mbarB);
     }
-    return t;
   };
 
   // ---- persistent CTA: per-CTA fixed costs (barrier init, histogram zero / flush, launch) are paid
@@ -161,16 +165,23 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     mbar_init(&sm.mbarA, 1);
     mbar_init(&sm.mbarB, 1);
     mbar_fence_init();
-    sm.tile = claimAndLoad();
   }
   for(int i = tid; i < 4 * 256; i += PRE_TILE)
     (&sm.hist[0][0])[i] = 0u;
   __syncthreads();
-  uint32_t tile = sm.tile;
-  for(uint32_t phase = 0; tile < tiles; phase ^= 1u)
+  if(tid == 0)
+    claimAndLoad();
+  // the append of a tile is finished one iteration later (see below): what this thread still owes
+  bool     pendKeep = false;
+  uint32_t pendKey = 0, pendId = 0, pendSlot = 0;
+  uint32_t phase = 0;
+  for(;; phase ^= 1u)
   {
-  const uint64_t first = static_cast<uint64_t>(tile) * PRE_TILE;
   mbar_wait(&sm.mbarA, phase);
+  const uint32_t tile = sm.tile;
+  if(tile >= tiles)
+    break;
+  const uint64_t first = static_cast<uint64_t>(tile) * PRE_TILE;
 
   const uint64_t id    = first + tid;
   const bool     inSet = id < a.set.count;
@@ -248,6 +259,14 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   }
 
   // ---- K5: per-splat projection + colour (threedgs_raster.mesh.slang:161-289) -------------------
+  // finish the previous tile's append: its exclusive prefix was resolved by warp 0 while this
+  // tile's centers were in flight (nobody waits on a look-back)
+  if(pendKeep)
+  {
+    const uint32_t slot = sm.basePrefix[phase ^ 1u] + pendSlot;
+    a.keys[slot]        = pendKey;
+    a.ids[slot]         = pendId;
+  }
   mbar_wait(&sm.mbarB, phase);
   if(keep)
   {
@@ -396,9 +415,13 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   // every thread is done with this tile's shared data: claim the next tile and start its copies now
   __syncthreads();
   if(tid == 0)
-    sm.tile = claimAndLoad();
+    claimAndLoad();
+  pendKeep = keep, pendKey = key, pendId = a.idBase + static_cast<uint32_t>(id), pendSlot = sm.warpScan[warp] + warpRank;
 
-  // ---- deterministic append, part 2: resolve the exclusive prefix (predecessors published long ago)
+  // ---- deterministic append, part 2: resolve the exclusive prefix (predecessors published long ago).
+  // Warp 0 only, and nobody waits for it: the (key,id) writes of this tile happen in the next
+  // iteration, after that iteration's first barrier, so the look-back's L2 round trips overlap the
+  // bulk copies of the next tile.
   if(warp == 0)
   {
     uint32_t excl = chainBase;  // (non-zero for tile 0 of a chained launch only)
@@ -415,24 +438,23 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     }
     if(lane == 0)
     {
-      sm.basePrefix = excl;
+      sm.basePrefix[phase] = excl;
       // the tile holding the last splat knows V once its prefix is resolved
       if(first + PRE_TILE >= a.set.count && !(ablate & 1u))
         a.counters->visible = excl + tileTotal;
     }
   }
-  __syncthreads();
-  if(keep)
-  {
-    const uint32_t slot = sm.basePrefix + sm.warpScan[warp] + warpRank;
-    a.keys[slot]        = key;
-    a.ids[slot]         = a.idBase + static_cast<uint32_t>(id);
-  }
-  tile = sm.tile;
   }  // persistent tile loop
 
-  // flush the digit histograms of the four sort passes (only bins this CTA touched)
+  // the last tile's append
   __syncthreads();
+  if(pendKeep)
+  {
+    const uint32_t slot = sm.basePrefix[phase ^ 1u] + pendSlot;
+    a.keys[slot]        = pendKey;
+    a.ids[slot]         = pendId;
+  }
+  // flush the digit histograms of the four sort passes (only bins this CTA touched)
   for(int i = tid; i < 4 * 256; i += PRE_TILE)
   {
     const uint32_t v = (&sm.hist[0][0])[i];
