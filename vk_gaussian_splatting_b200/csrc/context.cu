@@ -294,14 +294,22 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   bl.frontToBack            = c->opt.front_to_back;
   bl.disableOpacityGaussian = c->opt.disable_opacity_gaussian;
   bl.transmittanceEpsilon   = c->opt.front_to_back ? c->opt.transmittance_epsilon : 0.0f;
-  launchBlend(bl, st);
+  // the blend (and the copies to host) run on the slot's low-priority stream; the slot's main stream
+  // waits for them, so frame completion / buffer reuse are still ordered on `st`
+  CU_TRY(c, cudaEventRecord(s.evFront, st));
+  CU_TRY(c, cudaStreamWaitEvent(s.streamBlend, s.evFront, 0));
+  launchBlend(bl, s.streamBlend);
   c->launches++;
-  mark(VKGS_K_BLEND + 1);
+  if(c->profiling)
+    cudaEventRecord(s.ev[VKGS_K_BLEND + 1], s.streamBlend);
   s.evRecorded = c->profiling;
 
-  CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, 32, cudaMemcpyDeviceToHost, st));
+  CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, 32, cudaMemcpyDeviceToHost, s.streamBlend));
   if(hostRgba)
-    CU_TRY(c, cudaMemcpyAsync(hostRgba, s.dImage, 4ull * formatSize(c->opt.target_format) * fp.width * fp.height, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaMemcpyAsync(hostRgba, s.dImage, 4ull * formatSize(c->opt.target_format) * fp.width * fp.height, cudaMemcpyDeviceToHost,
+                              s.streamBlend));
+  CU_TRY(c, cudaEventRecord(s.evBlend, s.streamBlend));
+  CU_TRY(c, cudaStreamWaitEvent(st, s.evBlend, 0));
   if(c->userStream)
   {
     // completion of this frame becomes visible on the caller's stream, in submission order
@@ -454,9 +462,14 @@ int vkgs_create(int device, vkgs_ctx** out)
   vkgs_ctx* c = new vkgs_ctx();
   c->device   = device;
   bool ok     = true;
+  int  prioLeast = 0, prioGreatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
   for(auto& s : c->slots)
   {
-    ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prioGreatest) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&s.streamBlend, cudaStreamNonBlocking, prioLeast) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.evFront, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.evBlend, cudaEventDisableTiming) == cudaSuccess;
     for(auto& e : s.ev)
       ok = ok && cudaEventCreate(&e) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming) == cudaSuccess;
@@ -496,6 +509,12 @@ int vkgs_destroy(vkgs_ctx* c)
         cudaEventDestroy(e);
     if(s.evDone)
       cudaEventDestroy(s.evDone);
+    if(s.evFront)
+      cudaEventDestroy(s.evFront);
+    if(s.evBlend)
+      cudaEventDestroy(s.evBlend);
+    if(s.streamBlend)
+      cudaStreamDestroy(s.streamBlend);
     if(s.stream)
       cudaStreamDestroy(s.stream);
   }

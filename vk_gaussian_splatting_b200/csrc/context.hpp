@@ -15,7 +15,10 @@ constexpr int MAX_FRAMES_IN_FLIGHT = 4;
 // same GPU, like the frames-in-flight of the reference's swapchain loop.
 struct FrameSlot
 {
-  cudaStream_t   stream = nullptr;
+  cudaStream_t   stream = nullptr;       // front end (preprocess, sorts, binning): HIGH priority; frame completion is visible here
+  cudaStream_t   streamBlend = nullptr;  // blend + copies to host: LOW priority, so another frame's latency-bound front end is
+                                         // scheduled ahead of the remaining blend CTAs and fills the issue slots they leave idle
+  cudaEvent_t    evFront = nullptr, evBlend = nullptr;
   uint32_t *     dKeys[2] = {nullptr, nullptr}, *dIds[2] = {nullptr, nullptr};
   uint32_t*      dRecords    = nullptr;
   FrameCounters* dCounters   = nullptr;
