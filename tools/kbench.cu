@@ -91,7 +91,7 @@ int main(int argc, char** argv)
     Ctl h{}; h.count = n; CK(cudaMemcpy(dctl, &h, sizeof(h), cudaMemcpyHostToDevice));
     CK(cudaDeviceSynchronize());
     cudaEventRecord(ev[0]);
-    launchHistogram(dk[0], &dctl->count, n, &dctl->hist[0][0], 0, passes == 4 ? 4 : 2, 0);
+    launchHistogram(dk[0], &dctl->count, n, &dctl->hist[0][0], 0, 4, 0);
     cudaEventRecord(ev[1]);
     for(int p = 0; p < passes; p++)
     {

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
     sm.part = atomicAdd(a.ticket, 1u);
   for(int i = tid; i < NWARPS * 256; i += SORT_THREADS)
     (&sm.warpHist[0][0])[i] = 0u;
+  if(tid < 256)
+    sm.digitStart[tid] = 0u;  // (first used as the partition's digit counters, see below)
   __syncthreads();
   const uint32_t part = sm.part;
   if(part >= parts)
@@ -93,6 +95,44 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
     keys[i]            = idx < count ? keysIn[idx] : 0xffffffffu;  // padding sorts last, is never written back
   }
   VKGS_TL(part, 2);
+
+  // ---- count the partition's digits FIRST (shared atomics, a few hundred cycles) and publish them:
+  // successors' look-backs only need these counts, so they must not wait for the ranking below
+  // (several thousand cycles, twice that on an SM shared by two partitions) ------------------------
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+    atomicAdd(&sm.digitStart[(keys[i] >> a.shift) & 0xffu], 1u);
+  __syncthreads();
+  uint32_t  realCount = 0;
+  uint64_t* mine      = a.status + static_cast<uint64_t>(part) * 256 + (tid & 255u);
+  if(tid < 256)
+  {
+    // padding keys (digit 0xff of the last partition) are not counted
+    realCount = sm.digitStart[tid];
+    if(tid == 255 && partBase + SORT_PART > count)
+      realCount -= (partBase + SORT_PART - count);
+    if(part == 0)
+    {
+      // exclusive scan of the global digit histogram = first global position of each digit.
+      // (only partition 0 needs it; everyone else inherits it through the look-back chain)
+      const uint32_t h   = a.histogram[tid];
+      uint32_t       inc = warp_inclusive_scan(h, lane);
+      __shared__ uint32_t warpTot[8];
+      if(lane == 31)
+        warpTot[warp] = inc;
+      asm volatile("bar.sync 1, 256;");
+      uint32_t add = 0;
+      for(unsigned w = 0; w < warp; w++)
+        add += warpTot[w];
+      const uint32_t excl = inc - h + add;
+      lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
+      sm.globalBase[tid] = excl;
+      if(tid == 0 && a.srcSelOut)
+        *a.srcSelOut = cur ^ 1u;
+    }
+    else
+      lb_store(mine, lb_pack(a.epoch, LB_AGGREGATE, realCount));
+  }
 
   // ---- rank within the warp (ballot multi-split) ------------------------------------------------
   // peer masks first (see match_digit), then the dependent counter updates
@@ -139,9 +179,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
   __syncthreads();
   VKGS_TL(part, 3);
 
-  // ---- per-digit: exclusive scan over warps, block totals; publish the aggregate at once -------
-  uint32_t  digitCount = 0, realCount = 0;
-  uint64_t* mine       = a.status + static_cast<uint64_t>(part) * 256 + (tid & 255u);
+  // ---- per-digit: exclusive scan over warps, block totals ------------------------------------------
+  uint32_t digitCount = 0;
   if(tid < 256)
   {
     uint32_t run = 0;
@@ -153,31 +192,6 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constan
       run += c;
     }
     digitCount = run;
-    // padding keys (digit 0xff of the last partition) are not counted
-    realCount = digitCount;
-    if(tid == 255 && partBase + SORT_PART > count)
-      realCount -= (partBase + SORT_PART - count);
-    if(part == 0)
-    {
-      // exclusive scan of the global digit histogram = first global position of each digit.
-      // (only partition 0 needs it; everyone else inherits it through the look-back chain)
-      const uint32_t h   = a.histogram[tid];
-      uint32_t       inc = warp_inclusive_scan(h, lane);
-      __shared__ uint32_t warpTot[8];
-      if(lane == 31)
-        warpTot[warp] = inc;
-      asm volatile("bar.sync 1, 256;");
-      uint32_t add = 0;
-      for(unsigned w = 0; w < warp; w++)
-        add += warpTot[w];
-      const uint32_t excl = inc - h + add;
-      lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
-      sm.globalBase[tid] = excl;
-      if(tid == 0 && a.srcSelOut)
-        *a.srcSelOut = cur ^ 1u;
-    }
-    else
-      lb_store(mine, lb_pack(a.epoch, LB_AGGREGATE, realCount));  // successors never wait on our staging
   }
   // exclusive scan of the 256 digit totals -> block-local start of each digit
   {
