@@ -44,6 +44,20 @@ def main():
         md.append("")
     open(out, "w").write("\n".join(md) + "\n")
     print("wrote", out)
+    if len(sys.argv) > 3:
+        # per-launch DRAM traffic by kernel (bench.py's roofline.traffic reads this file)
+        import json
+        import re
+        traffic = {}
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            name = re.sub(r"<.*", "", r[idx["Kernel Name"]].split("::")[-1].split("(")[0]).strip()
+            b = sum(float(r[idx[m]]) * unit.get(units[idx[m]], 1.0) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            traffic.setdefault(name, []).append({"grid": r[idx["Grid Size"]], "dram_bytes": b,
+                                                 "time_us": float(r[idx["gpu__time_duration.sum"]])})
+        json.dump({"source": rep, "how": "ncu --set full --clock-control none, one frame of configs[1]", "kernels": traffic},
+                  open(sys.argv[3], "w"), indent=1)
+        print("wrote", sys.argv[3])
 
 
 if __name__ == "__main__":
