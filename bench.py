@@ -215,6 +215,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     rank, local, world = dist_env()
     torch.cuda.set_device(local)
+    # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     farm = F.Farm(backend="nccl", device="cuda")  # no-op control plane when world == 1
     barrier, max_over_ranks = farm.barrier, farm.max_over_ranks
 
