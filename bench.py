@@ -296,7 +296,14 @@ def main():
         for k, v in s.ms_kernel.items():
             acc[k] = acc.get(k, 0.0) + v / nprof
     r.set_profiling(False)
-    r.set_frames_in_flight(2)
+    # blend workload of this frame (separate, untimed frame with the counting variant of the blend kernel)
+    copt = g.default_options(front_to_back=1, transmittance_epsilon=EPS)
+    copt._reserved[4] = 128
+    r.upload(scene, copt)
+    r.render_async(fp)
+    cst = r.last_frame_stats()
+    r.upload(scene, opt)
+    r.set_frames_in_flight(4)
     stage_ms = {"GPU Dist": acc["preprocess"], "GPU Sort": acc["sort_hist"] + sum(acc[f"sort_pass{i}"] for i in range(4)),
                 "Rasterization": acc["bin_emit"] + acc["tile_hist"] + acc["tile_sort0"] + acc["tile_sort1"] + acc["tile_ranges"] + acc["blend"]}
     dominant = max(acc, key=acc.get)
@@ -334,6 +341,10 @@ def main():
             "msplats_per_sec": fps * N_SPLATS / 1e6, "visible_splats": v, "tile_pairs": d,
             "stage_ms": stage_ms, "kernel_ms": acc,
             "frame_algorithmic_bytes": st.bytes_algorithmic, "frame_hbm_gbs": whole, "frame_hbm_frac": whole / peak,
+            "blend_workload": {"list_entries_evaluated_x64px": cst.list_entries_evaluated, "fragments_blended": cst.fragments_blended,
+                               "fragments_per_s": cst.fragments_blended / (acc["blend"] * 1e-3),
+                               "pixel_evaluations_per_s": 64 * cst.list_entries_evaluated / (acc["blend"] * 1e-3),
+                               "note": "the blend stage is bounded by fp32 issue: its natural unit is fragments/s (BASELINE.md 3)"},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": C.sizeof(A.FrameParams),
                     "d2h_bytes_per_step": d2h_bytes + 32, "steps": e2e_steps, "ms_per_step": ms_e2e_step,

@@ -93,7 +93,7 @@ typedef struct vkgs_options
                                         VKGS_FORMAT_FLOAT16 (the reference's default COLOR_MAIN format,
                                         R16G16B16A16_SFLOAT, src/gaussian_splatting.h:338) or VKGS_FORMAT_UINT8
                                         (R8G8B8A8_UNORM). Blending is always fp32; the target is rounded once. */
-  uint32_t _reserved[5];             /* [4]: profiling ablation flags (0 in production) */
+  uint32_t _reserved[5];             /* [4]: profiling flags (0 in production); bit 7 (128) = count blended fragments */
 } vkgs_options;
 
 /* Per-frame parameters: the fields of shaderio::FrameInfo the path reads
@@ -148,6 +148,10 @@ typedef struct vkgs_outputs
   float     ms_total;        /* first kernel to framebuffer complete (device time) */
   float     ms_kernel[16];   /* per-kernel device time, see VKGS_K_* */
   uint64_t  bytes_algorithmic; /* 12N + (132+SH(d))V + 16P, SURVEY.md §8(d) */
+  /* profiling only, 0 unless options._reserved[4] & 128: (list entry, 8x8 pixel block) pairs the blend evaluated, and
+   * fragments that passed both discards and were blended (the reference's ROP invocations) */
+  uint64_t  list_entries_evaluated;
+  uint64_t  fragments_blended;
 } vkgs_outputs;
 
 /* indices into vkgs_outputs.ms_kernel */

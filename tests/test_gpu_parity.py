@@ -247,6 +247,37 @@ def test_config3_6m_deg3_4k_properties(gpu_renderer):
     assert st.visible_count > 5_000_000
 
 
+def test_config5_30m_deg3_1080p_sort_properties(gpu_renderer):
+    """BASELINE configs[4]: the 30 M-splat stress scene. Dist/cull + radix sort at full size through
+    size-independent properties (sortedness, key multiset, permutation, tie order, idempotence); the oracle's
+    dist stage runs on the raw positions (the packed centers ARE the positions, src/splat_set_vk.cpp:253-262)."""
+    import types
+    n = 30_000_000
+    r = gpu_renderer
+    s = g.synth_scene(n, 3, 0x3D650004)
+    r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0 ** -15))
+    fp = g.frame_params(g.default_camera(), 1920, 1080)
+    img, st, ids, keys = r.render(fp, want_sorted=True)
+    light = types.SimpleNamespace(centers=s.positions, scale=s.scale, n=n)
+    okeys, oids = O.dist_cull(light, O.frame_params(g.default_camera(), 1920, 1080), O.default_options(front_to_back=1))
+    del s
+    assert st.visible_count == len(oids) > 29_000_000
+    assert np.all(keys[1:] >= keys[:-1])
+    same = keys[1:] == keys[:-1]
+    assert np.all(ids[1:][same] > ids[:-1][same])
+    assert np.array_equal(np.sort(okeys), keys)
+    # permutation: order-independent checksums of the id set (sum and xor) + exact equality against the oracle's stable sort
+    assert int(ids.astype(np.uint64).sum()) == int(oids.astype(np.uint64).sum())
+    assert int(np.bitwise_xor.reduce(ids)) == int(np.bitwise_xor.reduce(oids))
+    sk, si = O.radix_sort_pairs(okeys, oids)
+    assert np.array_equal(si, ids)
+    assert np.isfinite(img).all() and 0.0 <= img[..., 3].min() and img[..., 3].max() <= 1.0 + 1e-5
+    img2, _, ids2, _ = r.render(fp, want_sorted=True)
+    assert np.array_equal(ids, ids2) and np.array_equal(img, img2)
+    # release the 19 GB of device buffers for the tests that follow
+    r.upload(g.synth_scene(1000, 0, 1), g.default_options())
+
+
 # ---- frames in flight / asynchronous API -----------------------------------------------------------------
 
 def test_frames_in_flight_match_sequential_frames(gpu_renderer):
@@ -420,3 +451,40 @@ def test_image_metrics_match_oracle(gpu_renderer):
     m = r.compare_with_capture(A.FLIP_APPROX)
     mf, ff, mse, psnr, flip = O.image_metrics(img0, img1, 1)
     assert m.mse_fixed == mf > 0 and m.psnr == pytest.approx(psnr, abs=1e-5) and m.flip == pytest.approx(flip, rel=1e-4)
+
+
+def test_fragment_counters_are_consistent_and_do_not_change_the_frame(gpu_renderer):
+    """Profiling variant of the blend kernel (options._reserved[4] & 128): same image bit for bit; every blended
+    fragment belongs to an evaluated (list entry, 8x8 block) pair; without early termination the number of blended
+    fragments equals the number of non-discarded fragments of the oracle's rasterizer (alpha channel of a BTF frame
+    rendered with rgb = 0, a = fragment count is not available, so the oracle count comes from its quads)."""
+    r = gpu_renderer
+    s = g.synth_scene(20_000, 0, 0x3D6500E1)
+    cam, w, h = g.default_camera(), 320, 180
+    fp = g.frame_params(cam, w, h)
+    r.upload(s, g.default_options(front_to_back=1))
+    img0, st0, _, _ = r.render(fp)
+    assert st0.fragments_blended == 0 and st0.list_entries_evaluated == 0
+    opt = g.default_options(front_to_back=1)
+    opt._reserved[4] = 128
+    r.upload(s, opt)
+    img1, st1, _, _ = r.render(fp)
+    assert np.array_equal(img0, img1)
+    assert 0 < st1.fragments_blended <= 64 * st1.list_entries_evaluated
+    # oracle: count fragments passing both discards (threedgs_raster.frag.slang:242,258) splat by splat
+    pk = O.Packed(s)
+    ofp, oopt = O.frame_params(cam, w, h), O.default_options(front_to_back=1)
+    _, _, oids, quads = O.render(pk, ofp, oopt, want_quads=True)
+    ys, xs = np.mgrid[0:h, 0:w]
+    px, py = xs + 0.5, ys + 0.5
+    total = 0
+    for i in oids:
+        q = quads[i]
+        if not q["valid"]:
+            continue
+        dx, dy = (px - q["center"][0]).astype(np.float32), (py - q["center"][1]).astype(np.float32)
+        f1 = dx * q["w1"][0] + dy * q["w1"][1]
+        f2 = dx * q["w2"][0] + dy * q["w2"][1]
+        A_ = f1 * f1 + f2 * f2
+        total += int(np.count_nonzero((A_ <= 8.0) & (np.exp(-0.5 * A_) * q["rgba"][3] > 1.0 / 255.0)))
+    assert abs(st1.fragments_blended - total) <= max(8, 2e-4 * total)  # (numpy's rounding of A near the two thresholds)

@@ -63,7 +63,7 @@ class Outputs(C.Structure):
     _fields_ = [("rgba", f32p), ("sorted_ids", u32p), ("sorted_keys", u32p), ("sorted_ids_capacity", C.c_uint64),
                 ("visible_count", C.c_uint32), ("_pad", C.c_uint32), ("tile_pairs", C.c_uint64), ("ms_dist", C.c_float),
                 ("ms_sort", C.c_float), ("ms_raster", C.c_float), ("ms_total", C.c_float), ("ms_kernel", C.c_float * 16),
-                ("bytes_algorithmic", C.c_uint64)]
+                ("bytes_algorithmic", C.c_uint64), ("list_entries_evaluated", C.c_uint64), ("fragments_blended", C.c_uint64)]
 
 
 class Instance(C.Structure):

@@ -294,6 +294,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   bl.frontToBack            = c->opt.front_to_back;
   bl.disableOpacityGaussian = c->opt.disable_opacity_gaussian;
   bl.transmittanceEpsilon   = c->opt.front_to_back ? c->opt.transmittance_epsilon : 0.0f;
+  bl.fragmentCounters       = (c->opt._reserved[4] & 128u) ? &s.dCounters->fragments[0] : nullptr;
   // the blend (and the copies to host) run on the slot's low-priority stream; the slot's main stream
   // waits for them, so frame completion / buffer reuse are still ordered on `st`
   CU_TRY(c, cudaEventRecord(s.evFront, st));
@@ -304,7 +305,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     cudaEventRecord(s.ev[VKGS_K_BLEND + 1], s.streamBlend);
   s.evRecorded = c->profiling;
 
-  CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, 32, cudaMemcpyDeviceToHost, s.streamBlend));
+  CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, 48, cudaMemcpyDeviceToHost, s.streamBlend));
   if(hostRgba)
     CU_TRY(c, cudaMemcpyAsync(hostRgba, s.dImage, 4ull * formatSize(c->opt.target_format) * fp.width * fp.height, cudaMemcpyDeviceToHost,
                               s.streamBlend));
@@ -363,6 +364,8 @@ void fillStats(vkgs_ctx* c, FrameSlot& s, vkgs_outputs* out)
 {
   out->visible_count = s.hCounters->visible;
   out->tile_pairs    = s.hCounters->tilePairs;
+  out->list_entries_evaluated = s.hCounters->fragments[0];
+  out->fragments_blended      = s.hCounters->fragments[1];
   const uint64_t n = c->totalSplats, v = out->visible_count, p = static_cast<uint64_t>(s.lastFp.width) * s.lastFp.height;
   // SH bytes per visible splat: exact for one set, splat-count weighted over the instances otherwise
   double shB = 0.0;

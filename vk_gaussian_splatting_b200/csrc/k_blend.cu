@@ -167,7 +167,7 @@ static_assert(BLEND_WARPS == 4, "the tile is split into 2x2 warp blocks of 8x8 p
 // transmittance update is ordered. Signs are arranged so that no negation is needed per hit:
 // the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
 // colour.
-template <bool FTB, bool NOGAUSS>
+template <bool FTB, bool NOGAUSS, bool COUNT>
 __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_constant__ BlendArgs a)
 {
   __shared__ __align__(16) unsigned char s_raw[2 * SMEM_REC + 2 * BLEND_WARPS * (BATCH / 32) * 4];
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
   const float BAND      = THRESHOLD * 4e-6f;  // ex2.approx + the two roundings are within 1e-6 relative
   const float eps       = a.transmittanceEpsilon;
   bool        warpDone  = __all_sync(FULL_MASK, !insideA && !insideB);
+  uint32_t    nEvaluated = 0, nBlended = 0;  // COUNT only
 
   // asynchronous gather of this thread's entry of a batch into record buffer `buf`
   auto gather = [&](uint32_t id, uint32_t buf, uint32_t slot) {
@@ -297,6 +298,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
     f.n2 = pk(mlo, mhi);
   };
   auto blendFrag = [&](const Frag& f) {
+    if(COUNT)
+    {
+      float mlo, mhi;
+      upk(f.n2, mlo, mhi);
+      nEvaluated += 1u;
+      nBlended += (mlo != 0.0f && insideA ? 1u : 0u) + (mhi != 0.0f && insideB ? 1u : 0u);
+    }
     if(FTB)
     {
       const f32x2 nw2 = mul2(f.n2, acc);  // -(opacity * T)
@@ -416,6 +424,17 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
     }
   }
 
+  if(COUNT)
+  {
+    // list entries this warp block evaluated (one count per warp) and fragments blended (all lanes)
+    const uint32_t blended = __reduce_add_sync(FULL_MASK, nBlended);
+    if(lane == 0)
+    {
+      atomicAdd(a.fragmentCounters + 0, static_cast<unsigned long long>(nEvaluated));
+      atomicAdd(a.fragmentCounters + 1, static_cast<unsigned long long>(blended));
+    }
+  }
+
   // the colour target is rounded ONCE from the fp32 accumulators (the reference's ROP rounds after
   // every blend in the target format)
   float ca[2][4];
@@ -454,20 +473,30 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
 void launchBlend(const BlendArgs& args, cudaStream_t stream)
 {
   const uint32_t tiles = args.tilesX * args.tilesY;
+  const bool count = args.fragmentCounters != nullptr;
+#define VKGS_BLEND_LAUNCH(F, G)                                                                                                  \
+  do                                                                                                                             \
+  {                                                                                                                              \
+    if(count)                                                                                                                    \
+      k_blend<F, G, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                            \
+    else                                                                                                                         \
+      k_blend<F, G, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                           \
+  } while(0)
   if(args.frontToBack)
   {
     if(args.disableOpacityGaussian)
-      k_blend<true, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      VKGS_BLEND_LAUNCH(true, true);
     else
-      k_blend<true, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      VKGS_BLEND_LAUNCH(true, false);
   }
   else
   {
     if(args.disableOpacityGaussian)
-      k_blend<false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      VKGS_BLEND_LAUNCH(false, true);
     else
-      k_blend<false, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      VKGS_BLEND_LAUNCH(false, false);
   }
+#undef VKGS_BLEND_LAUNCH
 }
 
 }  // namespace vkgs

@@ -27,6 +27,8 @@ struct FrameCounters
   uint32_t overflow;           // set when D exceeded the tile-list capacity
   uint32_t sortSrc[4];         // [p]: which (key,id) buffer holds the output of depth-sort pass p (a pass
                                // whose digit is constant over all keys is skipped and does not flip it)
+  unsigned long long fragments[2];  // profiling only (vkgs_options._reserved[4] & 128): list entries evaluated by a
+                                    // warp block (x64 pixels), and fragments that passed both discards and were blended
   uint32_t ticket[12];         // dynamic tile / partition tickets, one per kernel launch
   uint32_t depthHist[4][256];  // digit histograms of the depth keys (filled by the preprocess kernel)
   uint32_t tileHist[2][256];   // digit histograms of the tile ids (filled by the binning kernel)
@@ -136,6 +138,7 @@ struct BlendArgs
   uint32_t        frontToBack;
   uint32_t        disableOpacityGaussian;
   float           transmittanceEpsilon;
+  unsigned long long* fragmentCounters;  // null in production: see FrameCounters::fragments
 };
 
 void launchBlend(const BlendArgs& args, cudaStream_t stream);
