@@ -36,14 +36,16 @@ static void benchBin(uint32_t n)
   CK(cudaMalloc(&drec, rec.size() * 4)); CK(cudaMalloc(&dids, n * 4)); CK(cudaMalloc(&dk, (size_t)cap * 4)); CK(cudaMalloc(&dv, (size_t)cap * 4));
   CK(cudaMalloc(&dc, sizeof(FrameCounters))); CK(cudaMalloc(&dst, parts * 8)); CK(cudaMemset(dst, 0, parts * 8));
   CK(cudaMalloc(&dtl, (size_t)parts * 16 * 8)); CK(cudaMemset(dtl, 0, (size_t)parts * 16 * 8));
-  CK(cudaMemcpy(drec, rec.data(), rec.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dids, ids.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(drec, rec.data(), rec.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<uint2> hbb(n); for(uint32_t i = 0; i < n; i++) hbb[i] = make_uint2(rec[(size_t)i * RECORD_WORDS + 10], rec[(size_t)i * RECORD_WORDS + 11]);
+  uint2* dbb; CK(cudaMalloc(&dbb, (size_t)n * 8)); CK(cudaMemcpy(dbb, hbb.data(), (size_t)n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dids, ids.data(), n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpyToSymbol(g_vkgsTimeline, &dtl, sizeof(dtl)));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   float best = 1e9f; FrameCounters hc{};
   for(int rep = 0; rep < 10; rep++)
   {
     FrameCounters h{}; h.visible = n; CK(cudaMemcpy(dc, &h, sizeof(h), cudaMemcpyHostToDevice));
-    BinArgs ba{}; ba.sortedIds[0] = dids; ba.sortedIds[1] = dids; ba.sortedSel = nullptr; ba.records = drec; ba.counters = dc; ba.tileKeys = dk; ba.tileVals = dv; ba.capacity = cap; ba.maxCount = n;
+    BinArgs ba{}; ba.sortedIds[0] = dids; ba.sortedIds[1] = dids; ba.sortedSel = nullptr; ba.bboxes = dbb; ba.counters = dc; ba.tileKeys = dk; ba.tileVals = dv; ba.capacity = cap; ba.maxCount = n;
     ba.tilesX = 120; ba.tilesY = 68; ba.status = dst; ba.epoch = rep + 1; ba.ticketSlot = 5; ba.debugFlags = 0;
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0); launchBinEmit(ba, 0); cudaEventRecord(e1); CK(cudaDeviceSynchronize());

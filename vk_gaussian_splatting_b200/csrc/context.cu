@@ -38,7 +38,7 @@ void freeSlotScene(FrameSlot& s)
 {
   for(int i = 0; i < 2; i++)
     freeDev(s.dKeys[i]), freeDev(s.dIds[i]), freeDev(s.dTileKeys[i]), freeDev(s.dTileVals[i]);
-  freeDev(s.dRecords), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
+  freeDev(s.dRecords), freeDev(s.dBboxes), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
   s.tileCapacity = 0;
   s.haveFrame    = false;
 }
@@ -82,6 +82,7 @@ int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n, uint64_t preTiles)
     CU_TRY(c, cudaMalloc(&s.dIds[i], n * sizeof(uint32_t)));
   }
   CU_TRY(c, cudaMalloc(&s.dRecords, n * RECORD_WORDS * sizeof(uint32_t)));
+  CU_TRY(c, cudaMalloc(&s.dBboxes, n * sizeof(uint2)));
   const uint64_t binParts = (n + 255) / 256, sortParts = (n + SORT_PART - 1) / SORT_PART;
   CU_TRY(c, cudaMalloc(&s.dPreStatus, preTiles * sizeof(uint64_t)));
   CU_TRY(c, cudaMalloc(&s.dBinStatus, binParts * sizeof(uint64_t)));
@@ -194,6 +195,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     pa.keys       = s.dKeys[0];
     pa.ids        = s.dIds[0];
     pa.records    = s.dRecords;
+    pa.bboxes     = s.dBboxes;
     pa.counters   = s.dCounters;
     pa.status     = s.dPreStatus + inst.tileOffset;
     pa.epoch      = nextEpoch(c);
@@ -233,7 +235,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   BinArgs ba{};
   ba.sortedIds[0] = s.dIds[0], ba.sortedIds[1] = s.dIds[1];
   ba.sortedSel  = &s.dCounters->sortSrc[3];
-  ba.records    = s.dRecords;
+  ba.bboxes     = s.dBboxes;
   ba.counters   = s.dCounters;
   ba.tileKeys   = s.dTileKeys[0];
   ba.tileVals   = s.dTileVals[0];

@@ -21,6 +21,7 @@ struct FrameSlot
   cudaEvent_t    evFront = nullptr, evBlend = nullptr;
   uint32_t *     dKeys[2] = {nullptr, nullptr}, *dIds[2] = {nullptr, nullptr};
   uint32_t*      dRecords    = nullptr;
+  uint2*         dBboxes     = nullptr;
   FrameCounters* dCounters   = nullptr;
   FrameCounters* hCounters   = nullptr;  // pinned; first 32 bytes are copied back every frame
   uint64_t *     dPreStatus = nullptr, *dSortStatus = nullptr, *dBinStatus = nullptr, *dTileSortStatus = nullptr;

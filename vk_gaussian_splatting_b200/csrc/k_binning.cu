@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
   uint2 bb[BIN_ITEMS];
 #pragma unroll
   for(int i = 0; i < BIN_ITEMS; i++)
-    bb[i] = (id[i] != 0xffffffffu) ? __ldg(reinterpret_cast<const uint2*>(a.records + static_cast<uint64_t>(id[i]) * RECORD_WORDS + 10))
-                                   : make_uint2(1u, 0u);
+    bb[i] = (id[i] != 0xffffffffu) ? __ldg(a.bboxes + id[i]) : make_uint2(1u, 0u);
   uint32_t x0[BIN_ITEMS], nx[BIN_ITEMS], y0[BIN_ITEMS], n[BIN_ITEMS], mine = 0;
 #pragma unroll
   for(int i = 0; i < BIN_ITEMS; i++)

@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     rec[0]      = make_float4(cx, cy, w1x, w1y);
     rec[1]      = make_float4(w2x, w2y, col.x, col.y);
     rec[2]      = make_float4(col.z, col.w, __uint_as_float(bb0), __uint_as_float(bb1));
+    a.bboxes[a.idBase + id] = make_uint2(bb0, bb1);
     }
   }
 

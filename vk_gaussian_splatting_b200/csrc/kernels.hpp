@@ -57,6 +57,8 @@ struct PreprocessArgs
   uint32_t*         keys;        // [V] compacted, ascending splat id
   uint32_t*         ids;         // [V]
   uint32_t*         records;     // [N][RECORD_WORDS], indexed by splat id
+  uint2*            bboxes;      // [N] copy of the two pixel-bbox words of the record: the binning gathers 8 B per splat
+                                 // by sorted id, and a compact array stays L2-resident where the 48-byte records do not
   FrameCounters*    counters;
   uint64_t*         status;      // look-back chain, one word per tile (of THIS launch)
   uint32_t          epoch;
@@ -110,7 +112,7 @@ struct BinArgs
 {
   const uint32_t* sortedIds[2];  // [V] depth-sorted splat ids: buffer *sortedSel holds them
   const uint32_t* sortedSel;
-  const uint32_t* records;
+  const uint2*    bboxes;      // [N] pixel bounding boxes (x0 | y0<<16, x1 | y1<<16), indexed by splat id
   FrameCounters*  counters;
   uint32_t*       tileKeys;    // [capacity]
   uint32_t*       tileVals;    // [capacity] splat id
