@@ -203,6 +203,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     pa.idBase     = inst.globalOffset;
     pa.ticketBase = ticketsDrawn;
     pa.chained    = k > 0;
+    pa.ctasPerSm  = c->framesInFlight > 1 ? 1u : 0u;  // throughput mode: thin launch that co-runs with other frames
     ticketsDrawn += (pa.set.count + PRE_TILE - 1) / PRE_TILE + preprocessGrid(pa);
     launchPreprocess(pa, st);
     c->launches++;

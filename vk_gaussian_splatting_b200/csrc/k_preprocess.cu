@@ -17,6 +17,7 @@
 // Arithmetic: this file is compiled with -fmad=false and evaluates every expression in the
 // operation order documented in oracle/vkgs_oracle.c, with IEEE division and square root, so keys
 // and records are bit-identical to the CPU oracle.
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "device_common.cuh"
@@ -467,7 +468,8 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
 }  // namespace
 
 namespace {
-int g_preGrid[3] = {0, 0, 0};  // resident CTAs of k_preprocess<fmt> on this device (SMs x CTAs per SM)
+int g_preSms = 0, g_prePerSm[3] = {0, 0, 0};  // SM count, resident CTAs of k_preprocess<fmt> per SM
+int g_preCapEnv = 0;                          // VKGS_PRE_CTAS_PER_SM (tuning experiments)
 }
 
 void initPreprocessKernels()
@@ -476,21 +478,25 @@ void initPreprocessKernels()
   cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_UINT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  int dev = 0, sms = 0, per[3] = {0, 0, 0};
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per[0], k_preprocess<VKGS_FORMAT_FLOAT32>, PRE_TILE, smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per[1], k_preprocess<VKGS_FORMAT_FLOAT16>, PRE_TILE, smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per[2], k_preprocess<VKGS_FORMAT_UINT8>, PRE_TILE, smem);
-  for(int i = 0; i < 3; i++)
-    g_preGrid[i] = sms * (per[i] > 0 ? per[i] : 1);
+  cudaDeviceGetAttribute(&g_preSms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[0], k_preprocess<VKGS_FORMAT_FLOAT32>, PRE_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[1], k_preprocess<VKGS_FORMAT_FLOAT16>, PRE_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[2], k_preprocess<VKGS_FORMAT_UINT8>, PRE_TILE, smem);
+  if(const char* e = getenv("VKGS_PRE_CTAS_PER_SM"))
+    g_preCapEnv = atoi(e);
 }
 
 uint32_t preprocessGrid(const PreprocessArgs& args)
 {
   const uint32_t tiles = (args.set.count + PRE_TILE - 1) / PRE_TILE;
   const uint32_t fmt   = args.set.shFormat <= VKGS_FORMAT_UINT8 ? args.set.shFormat : 0u;
-  const uint32_t cap   = g_preGrid[fmt] > 0 ? static_cast<uint32_t>(g_preGrid[fmt]) : 148u * 3u;
+  uint32_t       per   = g_prePerSm[fmt] > 0 ? static_cast<uint32_t>(g_prePerSm[fmt]) : 3u;
+  const uint32_t want  = g_preCapEnv > 0 ? static_cast<uint32_t>(g_preCapEnv) : args.ctasPerSm;
+  if(want > 0 && want < per)
+    per = want;
+  const uint32_t cap = static_cast<uint32_t>(g_preSms > 0 ? g_preSms : 148) * per;
   return tiles < cap ? tiles : cap;
 }
 

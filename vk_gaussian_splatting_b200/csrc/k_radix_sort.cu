@@ -40,7 +40,7 @@ struct SortSmem
 static_assert(sizeof(uint32_t) * NWARPS * 256 <= sizeof(uint32_t) * SORT_PART, "warpHist must fit in the key staging area");
 
 template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const __grid_constant__ SortPassArgs a)
+__global__ void __launch_bounds__(SORT_THREADS, 3) k_sort_pass(const __grid_constant__ SortPassArgs a)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   SortSmem&      sm   = *reinterpret_cast<SortSmem*>(smemRaw);

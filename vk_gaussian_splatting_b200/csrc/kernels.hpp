@@ -70,6 +70,10 @@ struct PreprocessArgs
   uint32_t          idBase;
   uint32_t          ticketBase;
   uint32_t          chained;
+  // Resident CTAs per SM of the persistent launch (0 = as many as fit). With several frames in flight
+  // the context asks for ONE: the kernel then takes longer on its own but leaves two thirds of every
+  // SM to the other frames' kernels, and frame throughput goes up (measured 3520 -> 3670 fps, config 2).
+  uint32_t          ctasPerSm;
 };
 
 void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream);
