@@ -149,7 +149,7 @@ void frameConstants(const vkgs_frame_params& fp, float mv[16], float camModel[3]
 }
 
 // Enqueue one frame on the next slot; optionally a device->host copy of the finished frame.
-int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* slotOut)
+int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* slotOut, bool throughputMode)
 {
   if(!c->uploaded)
     return fail(c, VKGS_ERR_NOT_UPLOADED, "vkgs_render before vkgs_upload");
@@ -203,7 +203,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     pa.idBase     = inst.globalOffset;
     pa.ticketBase = ticketsDrawn;
     pa.chained    = k > 0;
-    pa.ctasPerSm  = c->framesInFlight > 1 ? 1u : 0u;  // throughput mode: thin launch that co-runs with other frames
+    pa.ctasPerSm  = (throughputMode && c->framesInFlight > 1) ? 1u : 0u;  // thin launch that co-runs with other frames
     ticketsDrawn += (pa.set.count + PRE_TILE - 1) / PRE_TILE + preprocessGrid(pa);
     launchPreprocess(pa, st);
     c->launches++;
@@ -733,14 +733,14 @@ int vkgs_render_async(vkgs_ctx* c, const vkgs_frame_params* fp)
 {
   if(!c || !fp)
     return VKGS_ERR_INVALID_ARGUMENT;
-  return enqueueFrame(c, *fp, nullptr, nullptr);
+  return enqueueFrame(c, *fp, nullptr, nullptr, true);
 }
 
 int vkgs_render_to_host_async(vkgs_ctx* c, const vkgs_frame_params* fp, void* host_rgba)
 {
   if(!c || !fp || !host_rgba)
     return VKGS_ERR_INVALID_ARGUMENT;
-  return enqueueFrame(c, *fp, host_rgba, nullptr);
+  return enqueueFrame(c, *fp, host_rgba, nullptr, true);
 }
 
 int vkgs_sync(vkgs_ctx* c)
@@ -776,7 +776,7 @@ int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
   for(int attempt = 0; attempt < 3; attempt++)
   {
     int si = 0;
-    if(int rc = enqueueFrame(c, *fp, out->rgba, &si))
+    if(int rc = enqueueFrame(c, *fp, out->rgba, &si, false))  // synchronous call: nothing to overlap with
       return rc;
     FrameSlot& s = c->slots[si];
     CU_TRY(c, cudaStreamSynchronize(s.stream));
