@@ -254,9 +254,10 @@ VKGS_API int vkgs_sort_pairs(vkgs_ctx* ctx, const uint32_t* keys, const uint32_t
  *      371-477, dispatch src/image_compare.cpp:770-830, read-back src/image_compare.cpp:874-905).
  *      MSE over RGB with the reference's fixed-point accumulation (uint32, x1e9, normalised by W*H*3),
  *      PSNR = min(10 log10(1/MSE), 99.99) dB, and the reference's fast FLIP approximation (YCxCz colour
- *      error + Sobel feature error, Minkowski pooling q = 3). FLIP "reference" mode is not built. */
+ *      error + Sobel feature error, Minkowski pooling q = 3) or its "reference" mode (multi-scale band-pass features). */
 #define VKGS_FLIP_DISABLED 0
 #define VKGS_FLIP_APPROX 1
+#define VKGS_FLIP_REFERENCE 2 /* five band-pass features per image, brute-force Gaussian windows up to 131x131 taps: slow by design */
 typedef struct vkgs_image_metrics
 {
   float    mse, psnr, flip;

@@ -439,6 +439,13 @@ def test_image_metrics_match_oracle(gpu_renderer):
             mf, ff, mse, psnr, flip = O.image_metrics(a, b, mode)
             assert m.mse_fixed == mf and m.mse == mse and m.psnr == pytest.approx(psnr, abs=1e-5)
             assert abs(int(m.flip_fixed) - ff) <= max(4, 1e-4 * ff) and m.flip == pytest.approx(flip, rel=1e-4, abs=1e-6)
+    # FLIP "reference" mode: multi-scale features; the widest window (131x131) only applies 65 px away from the border
+    a = rng.random((150, 170, 4), dtype=np.float32)
+    b = np.clip(a + rng.normal(0, 0.08, a.shape).astype(np.float32), 0, 1)
+    m = r.image_metrics(a, b, A.FLIP_REFERENCE)
+    mf, ff, mse, psnr, flip = O.image_metrics(a, b, A.FLIP_REFERENCE)
+    assert m.mse_fixed == mf and abs(int(m.flip_fixed) - ff) <= max(8, 2e-4 * ff) and m.flip == pytest.approx(flip, rel=2e-4)
+    assert m.flip != pytest.approx(O.image_metrics(a, b, A.FLIP_APPROX)[4], rel=1e-3)  # a different estimator
     # rendered frames: capture one camera, compare with a slightly different one
     s = g.synth_scene(40_000, 3, 0x3D6500D1)
     r.upload(s, g.default_options(front_to_back=1))

@@ -275,6 +275,13 @@ def test_image_metrics_known_answers():
     want = fl * csf * (M + 0.4 * abs(L - M) + 0.4 * abs(M - S))
     # (each of the 1024 pixels contributes uint(want^3 / 1024 * 1e9) = 1072 of 1072.8: truncation, as in the shader)
     assert ff == 1024 * int(np.float32(want) ** 3 / 1024 * 1e9) and flip == pytest.approx(want, rel=5e-4)
+    # FLIP reference mode: on flat images every band-pass feature vanishes, so it equals the colour term alone
+    assert O.image_metrics(z, o, 2)[4] == pytest.approx(want, rel=5e-4)
+    # and a luminance step in one image only is seen by the multi-scale features (interior pixels)
+    e = np.full((140, 140, 4), 0.25, np.float32)
+    f = e.copy()
+    f[:, 70:, :3] = 0.75
+    assert O.image_metrics(e, f, 2)[4] > O.image_metrics(e, e, 2)[4] == 0.0
     # monotone in the size of the error
     f1 = O.image_metrics(a, np.clip(a + 0.02, 0, 1), 1)[4]
     f2 = O.image_metrics(a, np.clip(a + 0.10, 0, 1), 1)[4]

@@ -76,7 +76,7 @@ class ImageMetrics(C.Structure):
                 ("flip_fixed", C.c_uint32), ("ms_device", C.c_float)]
 
 
-FLIP_DISABLED, FLIP_APPROX = 0, 1
+FLIP_DISABLED, FLIP_APPROX, FLIP_REFERENCE = 0, 1, 2
 
 # every symbol include/vkgs_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {

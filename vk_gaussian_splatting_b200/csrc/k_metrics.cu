@@ -29,6 +29,7 @@ struct MetricArgs
   int           width, height;
   float         sampleDivider;  // W * H * 3
   uint32_t      flipMode;
+  float         pixelsPerDegree;  // 67 in the reference (src/image_compare.cpp:788)
 };
 
 __device__ __forceinline__ float srgbToLinear1(float c)
@@ -75,11 +76,65 @@ __device__ float sobelMagnitude(const float4* img, int x, int y, int w, int h)
   return sqrtf(gx * gx + gy * gy);
 }
 
+// FLIP "reference" mode (image_compare_metric.comp.slang:231-300, 486-543): five band-pass features per
+// image, |centre luminance - Gaussian-blurred luminance| * CSF at 0.5/1/2/4/8 cycles per degree, the blur a
+// brute-force (2r+1)^2 window with r = ceil(3 sigma), sigma = max(ppd / (6.28 f), 0.5) — r = 65 px for the lowest
+// band at the reference's 67 pixels per degree; pixels closer than r to the border keep their own luminance.
+// The 1-D weights exp(-d^2 / (2 sigma^2)) are tabulated once per CTA (the shader evaluates the same two
+// factors per tap); taps are summed in the shader's loop order (dx outer, dy inner).
+constexpr int FLIP_BANDS      = 5;
+constexpr int FLIP_MAX_RADIUS = 96;
+
+struct FlipTables
+{
+  float w[FLIP_BANDS][2 * FLIP_MAX_RADIUS + 1];
+  int   radius[FLIP_BANDS];
+  float csf[FLIP_BANDS];
+};
+
+__device__ float flipBlurredLuminance(const float4* img, int x, int y, int w, int h, const float* wt, int radius)
+{
+  if(x < radius || y < radius || x >= w - radius || y >= h - radius)
+    return lum(img[y * w + x]);
+  float sum = 0.0f, weightSum = 0.0f;
+  for(int dx = -radius; dx <= radius; dx++)
+  {
+    const float wx = wt[dx + radius];
+    for(int dy = -radius; dy <= radius; dy++)
+    {
+      const float weight = wx * wt[dy + radius];
+      sum += lum(img[(y + dy) * w + (x + dx)]) * weight;
+      weightSum += weight;
+    }
+  }
+  return sum / weightSum;
+}
+
 __global__ void __launch_bounds__(256) k_image_metrics(const __grid_constant__ MetricArgs a)
 {
-  __shared__ uint32_t s_sum[2];
+  __shared__ uint32_t   s_sum[2];
+  __shared__ FlipTables s_flip;
   if(threadIdx.x < 2)
     s_sum[threadIdx.x] = 0u;
+  if(a.flipMode == VKGS_FLIP_REFERENCE)
+  {
+    const float freq[FLIP_BANDS] = {0.5f, 1.0f, 2.0f, 4.0f, 8.0f};
+    for(int b = 0; b < FLIP_BANDS; b++)
+    {
+      const float sigma  = fmaxf(a.pixelsPerDegree / (freq[b] * 6.28f), 0.5f);
+      const int   radius = min(static_cast<int>(ceilf(3.0f * sigma)), FLIP_MAX_RADIUS);
+      if(threadIdx.x == 0)
+      {
+        s_flip.radius[b] = radius;
+        s_flip.csf[b]    = csfLuminance(freq[b]);
+      }
+      for(int i = threadIdx.x; i <= 2 * radius; i += blockDim.x)
+      {
+        const float d  = static_cast<float>(i - radius);
+        s_flip.w[b][i] = expf(-(d * d) / (2.0f * sigma * sigma));
+      }
+    }
+  }
   __syncthreads();
   // 16x16 pixels per CTA like the reference's numthreads(16,16,1); a warp covers 16x2 pixels
   const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
@@ -90,7 +145,26 @@ __global__ void __launch_bounds__(256) k_image_metrics(const __grid_constant__ M
     const float  dx = ref.x - cur.x, dy = ref.y - cur.y, dz = ref.z - cur.z;
     const float  squaredError = (dx * dx + dy * dy) + dz * dz;
     mseFixed                  = static_cast<uint32_t>((squaredError / a.sampleDivider) * 1000000000.0f);
-    if(a.flipMode == VKGS_FLIP_APPROX)
+    if(a.flipMode == VKGS_FLIP_REFERENCE)
+    {
+      float rc[3], cc[3];
+      srgbToFlipSpace(ref.x, ref.y, ref.z, rc);
+      srgbToFlipSpace(cur.x, cur.y, cur.z, cc);
+      const float csfY = csfLuminance(1.0f), csfC = csfY * 0.4f;
+      const float colorError = (fabsf(rc[0] - cc[0]) * csfY + fabsf(rc[1] - cc[1]) * csfC) + fabsf(rc[2] - cc[2]) * csfC;
+      const float refLum = lum(ref), curLum = lum(cur);
+      float       featureError = 0.0f;
+      for(int b = 0; b < FLIP_BANDS; b++)
+      {
+        const float fr = fabsf(refLum - flipBlurredLuminance(a.reference, x, y, a.width, a.height, s_flip.w[b], s_flip.radius[b])) * s_flip.csf[b];
+        const float fc = fabsf(curLum - flipBlurredLuminance(a.current, x, y, a.width, a.height, s_flip.w[b], s_flip.radius[b])) * s_flip.csf[b];
+        featureError += fabsf(fr - fc);
+      }
+      const float powered    = powf(__saturatef(colorError + featureError), 3.0f);
+      const float pixelCount = a.sampleDivider / 3.0f;
+      flipFixed              = static_cast<uint32_t>((powered / pixelCount) * 1000000000.0f);
+    }
+    else if(a.flipMode == VKGS_FLIP_APPROX)
     {
       float rc[3], cc[3];
       srgbToFlipSpace(ref.x, ref.y, ref.z, rc);
@@ -138,7 +212,7 @@ int runMetrics(vkgs_ctx* c, const float4* dRef, const float4* dCur, uint32_t w, 
   cudaEvent_t  e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  MetricArgs a{dRef, dCur, dResult, static_cast<int>(w), static_cast<int>(h), static_cast<float>(w * h * 3), flipMode};
+  MetricArgs a{dRef, dCur, dResult, static_cast<int>(w), static_cast<int>(h), static_cast<float>(w * h * 3), flipMode, 67.0f};
   cudaMemsetAsync(dResult, 0, 16, st);
   cudaEventRecord(e0, st);
   k_image_metrics<<<dim3((w + 15) / 16, (h + 15) / 16), 256, 0, st>>>(a);
@@ -170,7 +244,7 @@ extern "C" {
 int vkgs_image_metrics_host(vkgs_ctx* c, const float* reference, const float* current, uint32_t width, uint32_t height,
                             uint32_t flip_mode, vkgs_image_metrics* out)
 {
-  if(!c || !reference || !current || !out || width == 0 || height == 0 || flip_mode > VKGS_FLIP_APPROX
+  if(!c || !reference || !current || !out || width == 0 || height == 0 || flip_mode > VKGS_FLIP_REFERENCE
      || static_cast<uint64_t>(width) * height > (1ull << 28))
     return VKGS_ERR_INVALID_ARGUMENT;
   CU_TRY(c, cudaSetDevice(c->device));
@@ -226,7 +300,7 @@ int vkgs_capture_frame(vkgs_ctx* c)
 
 int vkgs_compare_with_capture(vkgs_ctx* c, uint32_t flip_mode, vkgs_image_metrics* out)
 {
-  if(!c || !out || flip_mode > VKGS_FLIP_APPROX)
+  if(!c || !out || flip_mode > VKGS_FLIP_REFERENCE)
     return VKGS_ERR_INVALID_ARGUMENT;
   if(!c->dCapture || c->lastSlot < 0)
   {
