@@ -93,7 +93,10 @@ typedef struct vkgs_options
                                         VKGS_FORMAT_FLOAT16 (the reference's default COLOR_MAIN format,
                                         R16G16B16A16_SFLOAT, src/gaussian_splatting.h:338) or VKGS_FORMAT_UINT8
                                         (R8G8B8A8_UNORM). Blending is always fp32; the target is rounded once. */
-  uint32_t _reserved[5];             /* [4]: profiling flags (0 in production); bit 7 (128) = count blended fragments */
+  uint32_t surface_info;             /* NEED_SURFACE_INFO (front_to_back only, like the reference: src/gaussian_splatting.cpp:2050):
+                                        the frame also produces integrated normals, picked depth + transmittance and the
+                                        splat id per pixel, see vkgs_read_surface_info */
+  uint32_t _reserved[4];             /* [3]: profiling flags (0 in production); bit 7 (128) = count blended fragments */
 } vkgs_options;
 
 /* Per-frame parameters: the fields of shaderio::FrameInfo the path reads
@@ -118,6 +121,8 @@ typedef struct vkgs_frame_params
   float    size_culling_min_pixels;  /* default 1 */
   uint32_t sh_degree;                /* FrameInfo.shDegree, default 3 */
   uint32_t width, height;
+  float    depth_iso_threshold;      /* FrameInfo.depthIsoThreshold, default 0.7 (surface_info only) */
+  float    thin_particle_threshold;  /* FrameInfo.thinParticleThreshold, default 1e-6 (surface_info only) */
 } vkgs_frame_params;
 
 /* The fields of struct Camera (src/camera_set.h:44-63) the pinhole path uses. */
@@ -271,6 +276,16 @@ VKGS_API int vkgs_compare_with_capture(vkgs_ctx* ctx, uint32_t flip_mode, vkgs_i
 /* The same kernel on two HOST images (W*H*4 fp32 each): reference = capture, current. */
 VKGS_API int vkgs_image_metrics_host(vkgs_ctx* ctx, const float* reference, const float* current, uint32_t width, uint32_t height,
                                      uint32_t flip_mode, vkgs_image_metrics* out);
+
+/* ---- surface-info side outputs of the last frame (options.surface_info; replaces the extra attachments of the
+ *      FTB raster pass: COLOR_RASTER_NORMAL, COLOR_RASTER_DEPTH, COLOR_RASTER_SPLATID, src/gaussian_splatting.cpp:594-617,
+ *      664-668; written by threedgs_raster.frag.slang:316-350 and, per splat, threedgs_raster.mesh.slang:209-233).
+ *      HOST buffers, any may be NULL:
+ *        normals            W*H*4 f32  sum over fragments of normalWorld*opacity under the "under" operator, a = 1 - T
+ *        depth_transmittance W*H*2 f32 (NDC depth of the first fragment after which T < depth_iso_threshold, 0 if none; T)
+ *        splat_id           W*H u32    global id of the last blended fragment, 0xffffffff where nothing was blended
+ *      (with transmittance_epsilon > 0 the list is cut short: ids / T are exact only for epsilon = 0) */
+VKGS_API int vkgs_read_surface_info(vkgs_ctx* ctx, float* normals, float* depth_transmittance, uint32_t* splat_id);
 
 /* ---- parity/debug read-backs of per-splat intermediates of the last frame ----------------
  * Per-splat record, indexed by splat id (only ids that passed the dist-stage cull are valid):

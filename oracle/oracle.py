@@ -79,6 +79,10 @@ def lib() -> C.CDLL:
         l.orc_render_scene.argtypes = [C.POINTER(OrcSet), C.c_uint32, C.POINTER(OrcInstance), C.c_uint32,
                                        C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p, u32p, u32p]
         l.orc_render_scene.restype = C.c_uint32
+        l.orc_splat_normal.argtypes = [C.c_uint32, f32p, f32p, f32p, C.POINTER(A.FrameParams), f32p]
+        l.orc_render_surface.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams),
+                                         C.POINTER(A.Options), f32p, f32p, f32p, u32p, u32p]
+        l.orc_render_surface.restype = C.c_uint32
         l.orc_image_metrics.argtypes = [f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
         l.orc_quad_size.restype = C.c_uint32
         l.orc_cpu_sort.argtypes = [f32p, C.c_uint64, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, u32p, f32p,
@@ -175,6 +179,26 @@ def render_scene(packed_sets, instances, fp, opt):
     ids = np.empty(total, np.uint32)
     v = lib().orc_render_scene(sets, len(packed_sets), inst, len(instances), C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids))
     return img, keys[:v].copy(), ids[:v].copy()
+
+
+def splat_normal(packed: Packed, rotation, idx: int, fp) -> np.ndarray:
+    out = np.zeros(3, np.float32)
+    rot = np.ascontiguousarray(rotation, np.float32)
+    lib().orc_splat_normal(idx, _p(packed.centers), _p(packed.scale), _p(rot), C.byref(fp), _p(out))
+    return out
+
+
+def render_surface(packed: Packed, rotation, fp, opt):
+    """Front-to-back frame with the surface-info side outputs.
+    Returns (image [H,W,4], normals [H,W,4], depth_transmittance [H,W,2], splat_id [H,W], sorted_ids)."""
+    h, w = fp.height, fp.width
+    img, nrm = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    dt, sid = np.zeros((h, w, 2), np.float32), np.zeros((h, w), np.uint32)
+    ids = np.empty(packed.n, np.uint32)
+    rot = np.ascontiguousarray(rotation, np.float32)
+    v = lib().orc_render_surface(_p(packed.centers), _p(packed.cov6), _p(packed.rgba), _p(packed.sh), _p(packed.scale), _p(rot),
+                                 packed.n, packed.sh_degree, C.byref(fp), C.byref(opt), _p(img), _p(nrm), _p(dt), _u(sid), _u(ids))
+    return img, nrm, dt, sid, ids[:v].copy()
 
 
 def image_metrics(reference, current, flip_mode=0):

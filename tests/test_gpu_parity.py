@@ -461,7 +461,7 @@ def test_image_metrics_match_oracle(gpu_renderer):
 
 
 def test_fragment_counters_are_consistent_and_do_not_change_the_frame(gpu_renderer):
-    """Profiling variant of the blend kernel (options._reserved[4] & 128): same image bit for bit; every blended
+    """Profiling variant of the blend kernel (options._reserved[3] & 128): same image bit for bit; every blended
     fragment belongs to an evaluated (list entry, 8x8 block) pair; without early termination the number of blended
     fragments equals the number of non-discarded fragments of the oracle's rasterizer (alpha channel of a BTF frame
     rendered with rgb = 0, a = fragment count is not available, so the oracle count comes from its quads)."""
@@ -473,7 +473,7 @@ def test_fragment_counters_are_consistent_and_do_not_change_the_frame(gpu_render
     img0, st0, _, _ = r.render(fp)
     assert st0.fragments_blended == 0 and st0.list_entries_evaluated == 0
     opt = g.default_options(front_to_back=1)
-    opt._reserved[4] = 128
+    opt._reserved[3] = 128
     r.upload(s, opt)
     img1, st1, _, _ = r.render(fp)
     assert np.array_equal(img0, img1)
@@ -495,3 +495,34 @@ def test_fragment_counters_are_consistent_and_do_not_change_the_frame(gpu_render
         A_ = f1 * f1 + f2 * f2
         total += int(np.count_nonzero((A_ <= 8.0) & (np.exp(-0.5 * A_) * q["rgba"][3] > 1.0 / 255.0)))
     assert abs(st1.fragments_blended - total) <= max(8, 2e-4 * total)  # (numpy's rounding of A near the two thresholds)
+
+
+def test_surface_info_side_outputs_match_oracle(gpu_renderer):
+    """NEED_SURFACE_INFO (front to back): integrated normals, picked depth + transmittance and splat id per pixel
+    against the oracle (threedgs_raster.mesh.slang:209-233, frag.slang:316-350); the colour frame is unchanged.
+    Tolerances: normals / transmittance 1e-4 like the colour; picked depth exact where both pick the same fragment
+    (a pick flips only when T lands within 1e-6 of the iso threshold); ids equal except at such near-threshold pixels."""
+    r = gpu_renderer
+    s = g.synth_scene(30_000, 3, 0x3D6500F1)
+    # make some particles flat / needle-like so every branch of the normal computation runs
+    s.scale[::97, 1] = np.log(1e-7)
+    s.scale[::193, :2] = np.log(1e-7)
+    cam, w, h = g.default_camera(), 400, 240
+    fp = g.frame_params(cam, w, h)
+    r.upload(s, g.default_options(front_to_back=1))
+    img0, _, _, _ = r.render(fp)
+    r.upload(s, g.default_options(front_to_back=1, surface_info=1))
+    img, st, ids, _ = r.render(fp, want_sorted=True)
+    assert np.array_equal(img, img0)
+    nrm, dt, sid = r.read_surface_info(w, h)
+    pk = O.Packed(s)
+    oimg, onrm, odt, osid, oids = O.render_surface(pk, s.rotation, O.frame_params(cam, w, h), O.default_options(front_to_back=1))
+    assert np.array_equal(ids, oids)
+    assert np.abs(img - oimg).max() <= RGBA_TOL and np.abs(nrm - onrm).max() <= RGBA_TOL
+    assert np.abs(dt[..., 1] - odt[..., 1]).max() <= RGBA_TOL
+    near_iso = np.abs(odt[..., 1] - 0.7) < 1e-5
+    same_pick = (dt[..., 0] == odt[..., 0]) | near_iso
+    assert same_pick.mean() > 0.9999 and (odt[..., 0] != 0).mean() > 0.3
+    assert (sid == osid).mean() > 0.9999 and (osid != 0xffffffff).mean() > 0.3
+    with pytest.raises(g.VkgsError):
+        r.upload(s, g.default_options(front_to_back=0, surface_info=1))  # the reference has no BTF surface pass (non-stochastic)

@@ -286,3 +286,57 @@ def test_image_metrics_known_answers():
     f1 = O.image_metrics(a, np.clip(a + 0.02, 0, 1), 1)[4]
     f2 = O.image_metrics(a, np.clip(a + 0.10, 0, 1), 1)[4]
     assert 0 < f1 < f2 < 1
+
+
+def test_surface_normal_known_answers():
+    """computeEllipsoidNormalMaxDensityPlane restatement (threedgrt.h.slang:358-418): for an axis-aligned
+    ellipsoid the normal is Sigma^-1 (camera - centre) normalised; a flat particle takes its thin axis,
+    flipped towards the camera; a needle / point falls back to the view direction; unit length always."""
+    cam = g.default_camera()
+    fp = O.frame_params(cam, 64, 64)
+    eye = np.array(cam.eye, np.float64)
+
+    def one(center, scale, rot):
+        s = g.SplatSet(np.array([center], np.float32), np.zeros((1, 3)), np.zeros((1, 0)), np.zeros(1), np.log(np.array([scale], np.float32)),
+                       np.array([rot], np.float32))
+        return O.splat_normal(O.Packed(s), s.rotation, 0, fp).astype(np.float64)
+
+    c = np.array([0.1, -0.2, 0.3])
+    n = one(c, (0.5, 0.1, 0.2), (1, 0, 0, 0))
+    want = (eye - c) / np.array([0.5, 0.1, 0.2]) ** 2
+    assert np.allclose(n, want / np.linalg.norm(want), atol=2e-6) and abs(np.linalg.norm(n) - 1) < 1e-6
+    # rotation by 90 deg about z (w,x,y,z) = (cos45, 0, 0, sin45): the canonical x axis maps to +y
+    q = (np.cos(np.pi / 4), 0, 0, np.sin(np.pi / 4))
+    n = one(c, (0.5, 0.1, 0.2), q)
+    R = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]], np.float64)
+    want = R @ ((R.T @ (eye - c)) / np.array([0.5, 0.1, 0.2]) ** 2)
+    assert np.allclose(n, want / np.linalg.norm(want), atol=2e-6)
+    # a non-normalised quaternion is normalised first
+    assert np.allclose(one(c, (0.5, 0.1, 0.2), tuple(3 * x for x in q)), n, atol=2e-6)
+    # flat particle (one scale below thinParticleThreshold = 1e-6): its thin axis, towards the camera
+    n = one(c, (0.5, 1e-7, 0.2), (1, 0, 0, 0))
+    assert np.allclose(n, [0, np.sign(eye[1] - c[1]), 0], atol=1e-6)
+    # needle: minus the view direction
+    n = one(c, (1e-7, 1e-7, 0.2), (1, 0, 0, 0))
+    assert np.allclose(n, (eye - c) / np.linalg.norm(eye - c), atol=2e-6)
+
+
+def test_surface_outputs_single_splat():
+    """One opaque splat in front of the camera: inside its footprint the side outputs follow the fragment shader
+    (frag.slang:316-350): normal.a == colour.a, transmittance == 1 - alpha, depth picked where T < 0.7, id set;
+    outside: the clear values (0, (0,1), 0xffffffff)."""
+    cam = g.default_camera()
+    s = g.SplatSet(np.zeros((1, 3)), np.ones((1, 3)), np.zeros((1, 0)), np.array([6.0]), np.log(np.full((1, 3), 0.05, np.float32)),
+                   np.array([[1, 0, 0, 0]], np.float32))
+    fp = O.frame_params(cam, 96, 96)
+    pk = O.Packed(s)
+    img, nrm, dt, sid, ids = O.render_surface(pk, s.rotation, fp, O.default_options(front_to_back=1))
+    hit = sid != 0xffffffff
+    assert hit.any() and not hit.all() and set(np.unique(sid[hit])) == {0}
+    assert np.array_equal(nrm[..., 3], img[..., 3]) and np.allclose(dt[..., 1], 1.0 - img[..., 3], atol=1e-6)
+    assert np.all(dt[~hit] == [0.0, 1.0]) and np.all(nrm[~hit] == 0)
+    q = O.project_splat(pk, 0, fp, O.default_options(front_to_back=1))
+    picked = dt[..., 0] != 0
+    assert picked.any() and np.all(dt[picked, 0] == np.float32(q.ndc_z)) and np.all(dt[picked, 1] < 0.7) and np.all(dt[hit & ~picked, 1] >= 0.7)
+    n = O.splat_normal(pk, s.rotation, 0, fp)
+    assert np.allclose(nrm[hit, :3], n[None, :] * img[hit, 3:4], atol=1e-6)

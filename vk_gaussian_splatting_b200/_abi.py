@@ -42,7 +42,8 @@ class Options(C.Structure):
     _fields_ = [("frustum_culling_mode", C.c_uint32), ("size_culling_mode", C.c_uint32), ("front_to_back", C.c_uint32),
                 ("ms_antialiasing", C.c_uint32), ("sh_format", C.c_uint32), ("rgba_format", C.c_uint32),
                 ("point_cloud_mode", C.c_uint32), ("show_sh_only", C.c_uint32), ("disable_opacity_gaussian", C.c_uint32),
-                ("transmittance_epsilon", C.c_float), ("target_format", C.c_uint32), ("_reserved", C.c_uint32 * 5)]
+                ("transmittance_epsilon", C.c_float), ("target_format", C.c_uint32), ("surface_info", C.c_uint32),
+                ("_reserved", C.c_uint32 * 4)]
 
 
 class FrameParams(C.Structure):
@@ -51,7 +52,7 @@ class FrameParams(C.Structure):
                 ("viewport", C.c_float * 2), ("basis_viewport", C.c_float * 2), ("inverse_focal_adjustment", C.c_float),
                 ("splat_scale", C.c_float), ("frustum_dilation", C.c_float), ("alpha_cull_threshold", C.c_float),
                 ("size_culling_min_pixels", C.c_float), ("sh_degree", C.c_uint32), ("width", C.c_uint32),
-                ("height", C.c_uint32)]
+                ("height", C.c_uint32), ("depth_iso_threshold", C.c_float), ("thin_particle_threshold", C.c_float)]
 
 
 class Camera(C.Structure):
@@ -109,6 +110,7 @@ SYMBOLS = {
     "vkgs_capture_frame": (C.c_int, [C.c_void_p]),
     "vkgs_compare_with_capture": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ImageMetrics)]),
     "vkgs_image_metrics_host": (C.c_int, [C.c_void_p, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ImageMetrics)]),
+    "vkgs_read_surface_info": (C.c_int, [C.c_void_p, f32p, f32p, u32p]),
     "vkgs_read_records": (C.c_int, [C.c_void_p, u32p, C.c_uint64, C.c_uint64]),
     "vkgs_read_packed": (C.c_int, [C.c_void_p, f32p, f32p, f32p, f32p]),
     "vkgs_scene_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

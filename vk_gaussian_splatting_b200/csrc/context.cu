@@ -38,7 +38,7 @@ void freeSlotScene(FrameSlot& s)
 {
   for(int i = 0; i < 2; i++)
     freeDev(s.dKeys[i]), freeDev(s.dIds[i]), freeDev(s.dTileKeys[i]), freeDev(s.dTileVals[i]);
-  freeDev(s.dRecords), freeDev(s.dBboxes), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
+  freeDev(s.dRecords), freeDev(s.dBboxes), freeDev(s.dSurface), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
   s.tileCapacity = 0;
   s.haveFrame    = false;
 }
@@ -46,7 +46,7 @@ void freeSlotScene(FrameSlot& s)
 void freeScene(vkgs_ctx* c)
 {
   for(auto& st : c->sets)
-    freeDev(st.dCenters), freeDev(st.dCov), freeDev(st.dScales), freeDev(st.dRgba), freeDev(st.dSh);
+    freeDev(st.dCenters), freeDev(st.dCov), freeDev(st.dScales), freeDev(st.dRgba), freeDev(st.dSh), freeDev(st.dRotations);
   c->sets.clear();
   c->instances.clear();
   c->totalSplats = c->totalTiles = 0;
@@ -83,6 +83,8 @@ int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n, uint64_t preTiles)
   }
   CU_TRY(c, cudaMalloc(&s.dRecords, n * RECORD_WORDS * sizeof(uint32_t)));
   CU_TRY(c, cudaMalloc(&s.dBboxes, n * sizeof(uint2)));
+  if(c->opt.surface_info)
+    CU_TRY(c, cudaMalloc(&s.dSurface, n * sizeof(float4)));
   const uint64_t binParts = (n + 255) / 256, sortParts = (n + SORT_PART - 1) / SORT_PART;
   CU_TRY(c, cudaMalloc(&s.dPreStatus, preTiles * sizeof(uint64_t)));
   CU_TRY(c, cudaMalloc(&s.dBinStatus, binParts * sizeof(uint64_t)));
@@ -100,11 +102,18 @@ int ensureTargets(vkgs_ctx* c, FrameSlot& s, uint32_t w, uint32_t h)
   const uint32_t tx = (w + TILE_W - 1) / TILE_W, ty = (h + TILE_H - 1) / TILE_H;
   if(tx * ty > 65536)
     return fail(c, VKGS_ERR_UNSUPPORTED, "more than 65536 tiles (tile ids are sorted on 16 bits)");
-  if(s.imgW != w || s.imgH != h)
+  if(s.imgW != w || s.imgH != h || (c->opt.surface_info && !s.dOutNormals))
   {
     CU_TRY(c, cudaStreamSynchronize(s.stream));
     freeDev(s.dImage);
     freeDev(s.dRanges);
+    freeDev(s.dOutNormals), freeDev(s.dOutDepthT), freeDev(s.dOutSplatId);
+    if(c->opt.surface_info)
+    {
+      CU_TRY(c, cudaMalloc(&s.dOutNormals, sizeof(float4) * static_cast<size_t>(w) * h));
+      CU_TRY(c, cudaMalloc(&s.dOutDepthT, sizeof(float2) * static_cast<size_t>(w) * h));
+      CU_TRY(c, cudaMalloc(&s.dOutSplatId, sizeof(uint32_t) * static_cast<size_t>(w) * h));
+    }
     CU_TRY(c, cudaMalloc(&s.dImage, sizeof(float4) * static_cast<size_t>(w) * h));
     CU_TRY(c, cudaMalloc(&s.dRanges, 2 * sizeof(uint32_t) * tx * ty));
     s.imgW = w, s.imgH = h;
@@ -196,6 +205,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     pa.ids        = s.dIds[0];
     pa.records    = s.dRecords;
     pa.bboxes     = s.dBboxes;
+    pa.surface    = c->opt.surface_info ? s.dSurface : nullptr;
     pa.counters   = s.dCounters;
     pa.status     = s.dPreStatus + inst.tileOffset;
     pa.epoch      = nextEpoch(c);
@@ -247,7 +257,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   ba.status     = s.dBinStatus;
   ba.epoch      = nextEpoch(c);
   ba.ticketSlot = 5;
-  ba.debugFlags = c->opt._reserved[4];
+  ba.debugFlags = c->opt._reserved[3];
   launchBinEmit(ba, st);
   c->launches++;
   mark(VKGS_K_BIN_EMIT + 1);
@@ -297,7 +307,15 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   bl.frontToBack            = c->opt.front_to_back;
   bl.disableOpacityGaussian = c->opt.disable_opacity_gaussian;
   bl.transmittanceEpsilon   = c->opt.front_to_back ? c->opt.transmittance_epsilon : 0.0f;
-  bl.fragmentCounters       = (c->opt._reserved[4] & 128u) ? &s.dCounters->fragments[0] : nullptr;
+  bl.fragmentCounters       = (c->opt._reserved[3] & 128u) ? &s.dCounters->fragments[0] : nullptr;
+  if(c->opt.surface_info)
+  {
+    bl.surface           = s.dSurface;
+    bl.outNormals        = s.dOutNormals;
+    bl.outDepthT         = s.dOutDepthT;
+    bl.outSplatId        = s.dOutSplatId;
+    bl.depthIsoThreshold = fp.depth_iso_threshold;
+  }
   // the blend (and the copies to host) run on the slot's low-priority stream; the slot's main stream
   // waits for them, so frame completion / buffer reuse are still ordered on `st`
   CU_TRY(c, cudaEventRecord(s.evFront, st));
@@ -508,6 +526,7 @@ int vkgs_destroy(vkgs_ctx* c)
   for(auto& s : c->slots)
   {
     freeDev(s.dImage), freeDev(s.dRanges), freeDev(s.dCounters);
+    freeDev(s.dOutNormals), freeDev(s.dOutDepthT), freeDev(s.dOutSplatId);
     if(s.hCounters)
       cudaFreeHost(s.hCounters);
     for(auto& e : s.ev)
@@ -595,6 +614,8 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad frustum_culling_mode");
   if(opt.target_format > VKGS_FORMAT_UINT8)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad target_format");
+  if(opt.surface_info && !opt.front_to_back)
+    return fail(c, VKGS_ERR_UNSUPPORTED, "surface_info needs front_to_back (the reference only produces it in its FTB pass)");
   uint64_t total = 0;
   for(uint32_t k = 0; k < (instances ? instanceCount : 1u); k++)
   {
@@ -634,6 +655,9 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
     CU_TRY(c, up(st.dRgba, packed.rgba.data(), packed.rgba.size()));
     if(packed.shDegree)
       CU_TRY(c, up(st.dSh, packed.sh.data(), packed.sh.size()));
+    if(!packed.rotations.empty())
+      CU_TRY(c, up(st.dRotations, packed.rotations.data(), packed.rotations.size() * 4));
+    st.view.rotations  = static_cast<const float*>(st.dRotations);
     st.view.centers    = static_cast<const float*>(st.dCenters);
     st.view.cov6       = static_cast<const float*>(st.dCov);
     st.view.scales     = static_cast<const float*>(st.dScales);
@@ -666,6 +690,8 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
   c->totalSplats = offset;
   c->totalTiles  = tiles;
   c->opt         = opt;
+  for(auto& s : c->slots)  // (re)allocated with the next frame if the new options need them
+    freeDev(s.dOutNormals), freeDev(s.dOutDepthT), freeDev(s.dOutSplatId);
 
   // sorting / raster buffers (the reference allocates its sorting buffers with the splat set too,
   // src/splat_set_manager_vk.cpp:2426-2517), one set per frame in flight
@@ -804,6 +830,24 @@ int vkgs_read_records(vkgs_ctx* c, uint32_t* records12, uint64_t first, uint64_t
   FrameSlot& s = c->slots[c->lastSlot];
   CU_TRY(c, cudaStreamSynchronize(s.stream));
   CU_TRY(c, cudaMemcpy(records12, s.dRecords + first * RECORD_WORDS, count * RECORD_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return VKGS_OK;
+}
+
+int vkgs_read_surface_info(vkgs_ctx* c, float* normals, float* depth_transmittance, uint32_t* splat_id)
+{
+  if(!c)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(!c->uploaded || !c->opt.surface_info || c->lastSlot < 0 || !c->slots[c->lastSlot].dOutNormals)
+    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "no frame with options.surface_info rendered yet");
+  FrameSlot& s = c->slots[c->lastSlot];
+  CU_TRY(c, cudaStreamSynchronize(s.stream));
+  const size_t px = static_cast<size_t>(s.imgW) * s.imgH;
+  if(normals)
+    CU_TRY(c, cudaMemcpy(normals, s.dOutNormals, px * sizeof(float4), cudaMemcpyDeviceToHost));
+  if(depth_transmittance)
+    CU_TRY(c, cudaMemcpy(depth_transmittance, s.dOutDepthT, px * sizeof(float2), cudaMemcpyDeviceToHost));
+  if(splat_id)
+    CU_TRY(c, cudaMemcpy(splat_id, s.dOutSplatId, px * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return VKGS_OK;
 }
 

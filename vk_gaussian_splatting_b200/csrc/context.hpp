@@ -22,6 +22,10 @@ struct FrameSlot
   uint32_t *     dKeys[2] = {nullptr, nullptr}, *dIds[2] = {nullptr, nullptr};
   uint32_t*      dRecords    = nullptr;
   uint2*         dBboxes     = nullptr;
+  float4*        dSurface    = nullptr;  // surface-info only: per-splat world normal + NDC depth
+  float4*        dOutNormals = nullptr;  // surface-info only: side outputs of the frame
+  float2*        dOutDepthT  = nullptr;
+  uint32_t*      dOutSplatId = nullptr;
   FrameCounters* dCounters   = nullptr;
   FrameCounters* hCounters   = nullptr;  // pinned; first 32 bytes are copied back every frame
   uint64_t *     dPreStatus = nullptr, *dSortStatus = nullptr, *dBinStatus = nullptr, *dTileSortStatus = nullptr;
@@ -58,7 +62,7 @@ struct vkgs_ctx
   struct SetStorage
   {
     vkgs::DeviceSplatSet view{};
-    void *               dCenters = nullptr, *dCov = nullptr, *dScales = nullptr, *dRgba = nullptr, *dSh = nullptr;
+    void *               dCenters = nullptr, *dCov = nullptr, *dScales = nullptr, *dRgba = nullptr, *dSh = nullptr, *dRotations = nullptr;
   };
   struct Instance
   {

@@ -116,5 +116,7 @@ extern "C" int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t wi
   out->sh_degree               = 3;
   out->width                   = width;
   out->height                  = height;
+  out->depth_iso_threshold     = 0.7f;   // shaders/shaderio.h:311
+  out->thin_particle_threshold = 1e-6f;  // shaders/shaderio.h:316
   return VKGS_OK;
 }

@@ -164,6 +164,7 @@ int packSplatSet(const vkgs_splat_set_view& set, const vkgs_options& opt, uint64
   out.centers.assign(3 * pad, 0.0f);
   out.cov6.assign(6 * pad, 0.0f);
   out.scales.assign(3 * pad, 0.0f);
+  out.rotations.assign(opt.surface_info ? 4 * pad : 0, 0.0f);
   out.rgba.assign(4 * pad * formatSize(opt.rgba_format), 0);
   out.sh.assign(out.shDegree ? 45 * pad * formatSize(opt.sh_format) : 0, 0);
 
@@ -173,6 +174,8 @@ int packSplatSet(const vkgs_splat_set_view& set, const vkgs_options& opt, uint64
     {
       std::memcpy(&out.centers[3 * i], set.positions + 3 * i, 3 * sizeof(float));
       std::memcpy(&out.scales[3 * i], set.scale + 3 * i, 3 * sizeof(float));
+      if(opt.surface_info)
+        std::memcpy(&out.rotations[4 * i], set.rotation + 4 * i, 4 * sizeof(float));
       covariance6(set.scale + 3 * i, set.rotation + 4 * i, &out.cov6[6 * i]);
       const float* dc = set.f_dc + 3 * i;
       const float  c[4] = {std::clamp(0.5f + SH_C0 * dc[0], 0.0f, 1.0f), std::clamp(0.5f + SH_C0 * dc[1], 0.0f, 1.0f),

@@ -167,10 +167,13 @@ static_assert(BLEND_WARPS == 4, "the tile is split into 2x2 warp blocks of 8x8 p
 // transmittance update is ordered. Signs are arranged so that no negation is needed per hit:
 // the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
 // colour.
-template <bool FTB, bool NOGAUSS, bool COUNT>
-__global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_constant__ BlendArgs a)
+template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF>
+__global__ void __launch_bounds__(BLEND_THREADS, SURF ? 6 : 10) k_blend(const __grid_constant__ BlendArgs a)
 {
-  __shared__ __align__(16) unsigned char s_raw[2 * SMEM_REC + 2 * BLEND_WARPS * (BATCH / 32) * 4];
+  // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
+  constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
+  constexpr uint32_t SMEM_SID  = SMEM_SURF + 2 * BATCH * 16;
+  __shared__ __align__(16) unsigned char s_raw[SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF];
   const uint32_t sbase = smemBaseOpaque(s_raw);
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -193,6 +196,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
   const float eps       = a.transmittanceEpsilon;
   bool        warpDone  = __all_sync(FULL_MASK, !insideA && !insideB);
   uint32_t    nEvaluated = 0, nBlended = 0;  // COUNT only
+  // SURF only: MINUS the integrated normals, picked depth and last blended splat id of the two pixels
+  f32x2    sn0 = pk(0.f, 0.f), sn1 = sn0, sn2 = sn0;
+  float    depthA = 0.0f, depthB = 0.0f;
+  uint32_t sidA = 0xffffffffu, sidB = 0xffffffffu;
+  uint32_t surfBuf = 0;  // which ring buffer the blending loop is reading
 
   // asynchronous gather of this thread's entry of a batch into record buffer `buf`
   auto gather = [&](uint32_t id, uint32_t buf, uint32_t slot) {
@@ -201,6 +209,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
     cpAsync16(dst, src);
     cpAsync16(dst + 16, src + 16);
     cpAsync16(dst + 32, src + 32);
+    if(SURF)
+    {
+      cpAsync16(sbase + SMEM_SURF + (buf * BATCH + slot) * 16u, a.surface + id);
+      stsU32(sbase + SMEM_SID + (buf * BATCH + slot) * 4u, id);
+    }
   };
   // classify this thread's (landed) entry: per-warp-block hit bits -> per-warp hit masks
   auto classify = [&](bool have, uint32_t buf, uint32_t slot) {
@@ -251,9 +264,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
     f32x2  A2, n2;  // A of the two pixels; minus opacity (masked)
     float  gmin;
     float  r, g, b, alpha;
+    uint32_t addr;  // shared address of the staged record (SURF: locates the entry's normal / id)
   };
   auto evalFrag = [&](uint32_t addr) {
     Frag         f;
+    f.addr = addr;
     const float4 ra  = ldsV4(addr);       // cx cy w1x w1y
     const float4 rb  = ldsV4(addr + 16);  // w2x w2y r g
     const float2 rc  = ldsV2(addr + 32);  // b a
@@ -312,6 +327,32 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
       fma2acc(c1, nw2, pk(f.g, f.g));
       fma2acc(c2, nw2, pk(f.b, f.b));
       add2acc(acc, nw2);
+      if(SURF)
+      {
+        // threedgs_raster.frag.slang:316-350: normal * opacity under the same operator; first depth at
+        // which the transmittance drops below the iso threshold; id of the last fragment that was kept
+        const uint32_t slot = (f.addr - (sbase + surfBuf * SMEM_REC)) / REC_BYTES;
+        const float4   sv   = ldsV4(sbase + SMEM_SURF + (surfBuf * BATCH + slot) * 16u);
+        const uint32_t id   = ldsU32(sbase + SMEM_SID + (surfBuf * BATCH + slot) * 4u);
+        fma2acc(sn0, nw2, pk(sv.x, sv.x));
+        fma2acc(sn1, nw2, pk(sv.y, sv.y));
+        fma2acc(sn2, nw2, pk(sv.z, sv.z));
+        float mlo, mhi, Tlo, Thi;
+        upk(f.n2, mlo, mhi);
+        upk(acc, Tlo, Thi);
+        if(mlo != 0.0f)
+        {
+          sidA = id;
+          if(depthA == 0.0f && Tlo < a.depthIsoThreshold)
+            depthA = sv.w;
+        }
+        if(mhi != 0.0f)
+        {
+          sidB = id;
+          if(depthB == 0.0f && Thi < a.depthIsoThreshold)
+            depthB = sv.w;
+        }
+      }
     }
     else
     {
@@ -365,6 +406,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
       if(!warpDone)
       {
         const uint32_t recBase = sbase + buf * SMEM_REC;
+        surfBuf                = buf;
         const uint32_t hitBase = sbase + SMEM_HIT + (buf * BLEND_WARPS + warp) * (BATCH / 32) * 4u;
 #pragma unroll 1
         for(uint32_t chunk = 0; chunk < BATCH / 32; chunk++)
@@ -451,6 +493,16 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) k_blend(const __grid_consta
     // (0 - x, not -x: an untouched pixel must come out as +0)
     const float    c0f = __fsub_rn(0.0f, ca[p][0]), c1f = __fsub_rn(0.0f, ca[p][1]), c2f = __fsub_rn(0.0f, ca[p][2]);
     const float    al = FTB ? 1.0f - ca[p][3] : __fsub_rn(0.0f, ca[p][3]);
+    if(SURF)
+    {
+      float nx[2], ny[2], nz[2];
+      upk(sn0, nx[0], nx[1]);
+      upk(sn1, ny[0], ny[1]);
+      upk(sn2, nz[0], nz[1]);
+      a.outNormals[o] = make_float4(__fsub_rn(0.0f, nx[p]), __fsub_rn(0.0f, ny[p]), __fsub_rn(0.0f, nz[p]), al);
+      a.outDepthT[o]  = make_float2(p ? depthB : depthA, ca[p][3]);
+      a.outSplatId[o] = p ? sidB : sidA;
+    }
     if(a.targetFormat == VKGS_FORMAT_FLOAT32)
       static_cast<float4*>(a.image)[o] = make_float4(c0f, c1f, c2f, al);
     else if(a.targetFormat == VKGS_FORMAT_FLOAT16)
@@ -474,13 +526,22 @@ void launchBlend(const BlendArgs& args, cudaStream_t stream)
 {
   const uint32_t tiles = args.tilesX * args.tilesY;
   const bool count = args.fragmentCounters != nullptr;
+  if(args.outNormals)
+  {
+    // surface-info variant: front to back only (the context rejects other combinations)
+    if(args.disableOpacityGaussian)
+      k_blend<true, true, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+    else
+      k_blend<true, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+    return;
+  }
 #define VKGS_BLEND_LAUNCH(F, G)                                                                                                  \
   do                                                                                                                             \
   {                                                                                                                              \
     if(count)                                                                                                                    \
-      k_blend<F, G, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                            \
+      k_blend<F, G, true, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                            \
     else                                                                                                                         \
-      k_blend<F, G, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                           \
+      k_blend<F, G, false, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                           \
   } while(0)
   if(args.frontToBack)
   {

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   const uint32_t rgbaEl  = a.set.rgbaFormat == VKGS_FORMAT_FLOAT32 ? 4u : (a.set.rgbaFormat == VKGS_FORMAT_FLOAT16 ? 2u : 1u);
   const bool     hasSh   = a.set.sh != nullptr && a.set.shDegree > 0 && a.fp.sh_degree > 0;
   const bool     sizeCul = a.opt.size_culling_mode == VKGS_SIZE_CULLING_ENABLED;
-  const uint32_t ablate  = a.opt._reserved[4];
+  const bool     needScale = sizeCul || a.surface != nullptr;  // log-scales are staged with the centres
+  const uint32_t ablate  = a.opt._reserved[3];
   const uint32_t tiles   = (a.set.count + PRE_TILE - 1) / PRE_TILE;
 
   // claim a tile (ticket order == look-back order) and start its bulk copies. Stage A: what the
@@ -146,9 +147,9 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     else
     {
       const uint64_t f = static_cast<uint64_t>(t) * PRE_TILE;
-      mbar_arrive_expect_tx(&sm.mbarA, PRE_TILE * 3 * 4 * (sizeCul ? 2u : 1u));
+      mbar_arrive_expect_tx(&sm.mbarA, PRE_TILE * 3 * 4 * (needScale ? 2u : 1u));
       bulk_copy_g2s(sm.center, a.set.centers + f * 3, PRE_TILE * 3 * 4, &sm.mbarA);
-      if(sizeCul)
+      if(needScale)
         bulk_copy_g2s(sm.scale, a.set.scales + f * 3, PRE_TILE * 3 * 4, &sm.mbarA);
       mbar_arrive_expect_tx(&sm.mbarB, PRE_TILE * 6 * 4 + PRE_TILE * 4 * rgbaEl + (hasSh ? PRE_TILE * 45 * shElem : 0u));
       bulk_copy_g2s(sm.cov, a.set.cov6 + f * 6, PRE_TILE * 6 * 4, &sm.mbarB);
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   {
     float4   col   = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
     bool     valid = !(col.w < a.fp.alpha_cull_threshold);  // mesh.slang:165
-    float    cx = 0.f, cy = 0.f, w1x = 0.f, w1y = 0.f, w2x = 0.f, w2y = 0.f;
+    float    cx = 0.f, cy = 0.f, w1x = 0.f, w1y = 0.f, w2x = 0.f, w2y = 0.f, ndcDepth = 0.f;
     uint32_t bb0 = 1u, bb1 = 0u;  // empty: x1 < x0
     if(valid)
     {
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
 
           // quad centre in pixels + affine fragPos basis (mesh.slang:201,276-289)
           const float nz = clip[2] / clip[3];
+          ndcDepth       = nz;
           cx             = ((clip[0] / clip[3]) * 0.5f + 0.5f) * a.fp.viewport[0];
           cy             = ((clip[1] / clip[3]) * 0.5f + 0.5f) * a.fp.viewport[1];
           const float n1 = b1x * b1x + b1y * b1y, n2 = b2x * b2x + b2y * b2y;
@@ -410,6 +412,60 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     rec[1]      = make_float4(w2x, w2y, col.x, col.y);
     rec[2]      = make_float4(col.z, col.w, __uint_as_float(bb0), __uint_as_float(bb1));
     a.bboxes[a.idBase + id] = make_uint2(bb0, bb1);
+    }
+    if(a.surface && valid)
+    {
+      // NEED_SURFACE_INFO: world normal of the max-density plane (threedgs_raster.mesh.slang:209-233,
+      // computeEllipsoidNormalMaxDensityPlane threedgrt.h.slang:358-418), same operation order as
+      // orc_splat_normal; the NDC depth rides along for the depth pick of the fragment stage
+      const float4 rq   = *reinterpret_cast<const float4*>(a.set.rotations + 4 * id);  // w x y z
+      const float  scl[3] = {expf(sm.scale[3 * tid + 0]), expf(sm.scale[3 * tid + 1]), expf(sm.scale[3 * tid + 2])};
+      const float  rinv = 1.0f / sqrtf(((rq.x * rq.x + rq.y * rq.y) + rq.z * rq.z) + rq.w * rq.w);
+      const float  x = rq.y * rinv, y = rq.z * rinv, z = rq.w * rinv, w = rq.x * rinv;
+      const float  xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+      const float  inv[3][3] = {{1.0f - 2.0f * (yy + zz), 2.0f * (xy - wz), 2.0f * (xz + wy)},
+                                {2.0f * (xy + wz), 1.0f - 2.0f * (xx + zz), 2.0f * (yz - wx)},
+                                {2.0f * (xz - wy), 2.0f * (yz + wx), 1.0f - 2.0f * (xx + yy)}};
+      float dir[3] = {c[0] - a.camModel[0], c[1] - a.camModel[1], c[2] - a.camModel[2]};
+      const float dinv = 1.0f / sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+      dir[0] *= dinv, dir[1] *= dinv, dir[2] *= dinv;
+      const float local[3] = {a.camModel[0] - c[0], a.camModel[1] - c[1], a.camModel[2] - c[2]};
+      const float thr      = a.fp.thin_particle_threshold;
+      const int   s0 = scl[0] < thr, s1 = scl[1] < thr, s2 = scl[2] < thr, nsmall = s0 + s1 + s2;
+      float       n[3];
+      if(nsmall == 0)
+      {
+        float canon[3], scaled[3];
+#pragma unroll
+        for(int j = 0; j < 3; j++)
+          canon[j] = (local[0] * inv[0][j] + local[1] * inv[1][j]) + local[2] * inv[2][j];
+#pragma unroll
+        for(int j = 0; j < 3; j++)
+          scaled[j] = canon[j] * (1.0f / (scl[j] * scl[j]));
+#pragma unroll
+        for(int j = 0; j < 3; j++)
+          n[j] = (scaled[0] * inv[j][0] + scaled[1] * inv[j][1]) + scaled[2] * inv[j][2];
+        const float rs = 1.0f / sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+        n[0] *= rs, n[1] *= rs, n[2] *= rs;
+        if((n[0] * local[0] + n[1] * local[1]) + n[2] * local[2] < 0.0f)
+          n[0] = -n[0], n[1] = -n[1], n[2] = -n[2];
+      }
+      else if(nsmall == 1)
+      {
+        // row (axis) of the rotation matrix = column of its transpose; selects, not dynamic indexing
+        n[0] = s0 ? inv[0][0] : (s1 ? inv[0][1] : inv[0][2]);
+        n[1] = s0 ? inv[1][0] : (s1 ? inv[1][1] : inv[1][2]);
+        n[2] = s0 ? inv[2][0] : (s1 ? inv[2][1] : inv[2][2]);
+        if((n[0] * local[0] + n[1] * local[1]) + n[2] * local[2] < 0.0f)
+          n[0] = -n[0], n[1] = -n[1], n[2] = -n[2];
+      }
+      else
+        n[0] = -dir[0], n[1] = -dir[1], n[2] = -dir[2];
+      const float n4[4] = {n[0], n[1], n[2], 0.0f};
+      float       nw[4];
+      mulVecMat(n4, a.fp.model, nw);
+      const float winv = 1.0f / sqrtf((nw[0] * nw[0] + nw[1] * nw[1]) + nw[2] * nw[2]);
+      a.surface[a.idBase + id] = make_float4(nw[0] * winv, nw[1] * winv, nw[2] * winv, ndcDepth);
     }
   }
 

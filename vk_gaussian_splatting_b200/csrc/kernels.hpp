@@ -27,7 +27,7 @@ struct FrameCounters
   uint32_t overflow;           // set when D exceeded the tile-list capacity
   uint32_t sortSrc[4];         // [p]: which (key,id) buffer holds the output of depth-sort pass p (a pass
                                // whose digit is constant over all keys is skipped and does not flip it)
-  unsigned long long fragments[2];  // profiling only (vkgs_options._reserved[4] & 128): list entries evaluated by a
+  unsigned long long fragments[2];  // profiling only (vkgs_options._reserved[3] & 128): list entries evaluated by a
                                     // warp block (x64 pixels), and fragments that passed both discards and were blended
   uint32_t ticket[12];         // dynamic tile / partition tickets, one per kernel launch
   uint32_t depthHist[4][256];  // digit histograms of the depth keys (filled by the preprocess kernel)
@@ -38,7 +38,8 @@ struct DeviceSplatSet
 {
   const float* centers;  // 3 x f32, padded to PRE_TILE rows
   const float* cov6;     // 6 x f32
-  const float* scales;   // 3 x f32 (log), size culling only
+  const float* scales;   // 3 x f32 (log), size culling and surface-info normals
+  const float* rotations;// 4 x f32 raw quaternion (w,x,y,z), surface-info normals only (else null)
   const void*  rgba;     // 4 x {f32,f16,u8}
   const void*  sh;       // 45 x {f32,f16,u8} or nullptr
   uint32_t     count;
@@ -67,6 +68,7 @@ struct PreprocessArgs
   // reference's global index table, src/splat_set_manager_vk.cpp:2304-2360): global id = idBase +
   // local id; tickets already drawn by earlier launches of the frame (tiles + CTAs of each); and whether the append
   // continues after the pairs of earlier instances (base = counters->visible).
+  float4*           surface;     // [N] surface-info only (else null): world normal of the splat (xyz), NDC depth (w)
   uint32_t          idBase;
   uint32_t          ticketBase;
   uint32_t          chained;
@@ -145,6 +147,12 @@ struct BlendArgs
   uint32_t        disableOpacityGaussian;
   float           transmittanceEpsilon;
   unsigned long long* fragmentCounters;  // null in production: see FrameCounters::fragments
+  // surface-info side outputs (front to back only; all null when options.surface_info is off)
+  const float4*   surface;         // [N] per splat: world normal, NDC depth (written by the preprocess kernel)
+  float4*         outNormals;      // [H][W] integrated normal * opacity, a = 1 - T
+  float2*         outDepthT;       // [H][W] picked depth, transmittance
+  uint32_t*       outSplatId;      // [H][W] id of the last blended fragment
+  float           depthIsoThreshold;
 };
 
 void launchBlend(const BlendArgs& args, cudaStream_t stream);
