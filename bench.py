@@ -298,7 +298,7 @@ def main():
     r.set_profiling(False)
     # blend workload of this frame (separate, untimed frame with the counting variant of the blend kernel)
     copt = g.default_options(front_to_back=1, transmittance_epsilon=EPS)
-    copt._reserved[3] = 128
+    copt._reserved[0] = 128
     r.upload(scene, copt)
     r.render_async(fp)
     cst = r.last_frame_stats()

@@ -50,6 +50,10 @@ extern "C" {
 #define VKGS_FRUSTUM_CULLING_AT_RASTER 2
 #define VKGS_SIZE_CULLING_DISABLED 0
 #define VKGS_SIZE_CULLING_ENABLED 1
+#define VKGS_PIPELINE_3DGS 0
+#define VKGS_PIPELINE_3DGUT 1
+#define VKGS_EXTENT_EIGEN 0
+#define VKGS_EXTENT_CONIC 1
 
 typedef struct vkgs_ctx vkgs_ctx;
 
@@ -96,7 +100,14 @@ typedef struct vkgs_options
   uint32_t surface_info;             /* NEED_SURFACE_INFO (front_to_back only, like the reference: src/gaussian_splatting.cpp:2050):
                                         the frame also produces integrated normals, picked depth + transmittance and the
                                         splat id per pixel, see vkgs_read_surface_info */
-  uint32_t _reserved[4];             /* [3]: profiling flags (0 in production); bit 7 (128) = count blended fragments */
+  uint32_t pipeline;                 /* VKGS_PIPELINE_3DGS (default: PIPELINE_MESH / PIPELINE_VERT, VK3DGSR) or
+                                        VKGS_PIPELINE_3DGUT (PIPELINE_MESH_3DGUT, VK3DGUT: unscented-transform projection,
+                                        per-fragment ray / particle evaluation; pinhole camera) */
+  uint32_t extent_projection;        /* EXTENT_METHOD of the 3DGUT pipeline: VKGS_EXTENT_EIGEN or VKGS_EXTENT_CONIC (the
+                                        reference's default, src/parameters.h:190); vkgs_default_options sets CONIC */
+  uint32_t kernel_degree;            /* KERNEL_DEGREE of the 3DGUT particle response (shaders/shaderio.h:114-119);
+                                        vkgs_default_options sets 2 (quadratic = Gaussian) */
+  uint32_t _reserved[1];             /* [0]: profiling flags (0 in production); bit 7 (128) = count blended fragments */
 } vkgs_options;
 
 /* Per-frame parameters: the fields of shaderio::FrameInfo the path reads
@@ -123,6 +134,14 @@ typedef struct vkgs_frame_params
   uint32_t width, height;
   float    depth_iso_threshold;      /* FrameInfo.depthIsoThreshold, default 0.7 (surface_info only) */
   float    thin_particle_threshold;  /* FrameInfo.thinParticleThreshold, default 1e-6 (surface_info only) */
+  /* 3DGUT pipeline only (src/gaussian_splatting.cpp:1166-1169,1200,1254-1259; shaders/shaderio.h:241-248,271): */
+  float    view_inverse[16];         /* FrameInfo.viewInverse = glm::inverse(viewMatrix) */
+  float    proj_inverse[16];         /* FrameInfo.projInverse = glm::inverse(projectionMatrix) */
+  float    view_quat[4];             /* FrameInfo.viewQuat = glm::quat_cast(viewMatrix) as (x,y,z,w) */
+  float    view_trans[3];            /* FrameInfo.viewTrans = viewMatrix[3].xyz */
+  float    near_far[2];              /* FrameInfo.nearFar = camera clip planes */
+  float    alpha_clamp;              /* FrameInfo.alphaClamp, default 0.99 */
+  float    kernel_min_response;      /* KERNEL_MIN_RESPONSE, default 0.0113 (src/parameters.h:216) */
 } vkgs_frame_params;
 
 /* The fields of struct Camera (src/camera_set.h:44-63) the pinhole path uses. */

@@ -25,6 +25,9 @@ class Quad(C.Structure):
                 ("w2", C.c_float * 2), ("rgba", C.c_float * 4), ("ndc_z", C.c_float), ("valid", C.c_uint32)]
 
 
+GUT_QUAD_DTYPE = np.dtype([("center", "<f4", 2), ("extent", "<f4", 2), ("basis1", "<f4", 2), ("basis2", "<f4", 2), ("rgba", "<f4", 4),
+                           ("ndc_z", "<f4"), ("position", "<f4", 3), ("scale", "<f4", 3), ("inv_rot", "<f4", 9), ("valid", "<u4")])
+
 QUAD_DTYPE = np.dtype([("center", "<f4", 2), ("basis1", "<f4", 2), ("basis2", "<f4", 2), ("w1", "<f4", 2), ("w2", "<f4", 2),
                        ("rgba", "<f4", 4), ("ndc_z", "<f4"), ("valid", "<u4")])
 
@@ -79,6 +82,13 @@ def lib() -> C.CDLL:
         l.orc_render_scene.argtypes = [C.POINTER(OrcSet), C.c_uint32, C.POINTER(OrcInstance), C.c_uint32,
                                        C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p, u32p, u32p]
         l.orc_render_scene.restype = C.c_uint32
+        l.orc_render_gut.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams),
+                                     C.POINTER(A.Options), f32p, u32p, u32p, C.c_void_p]
+        l.orc_render_gut.restype = C.c_uint32
+        l.orc_gut_quad_size.restype = C.c_uint32
+        assert l.orc_gut_quad_size() == GUT_QUAD_DTYPE.itemsize
+        l.orc_gut_fragment.argtypes = [C.c_void_p, C.c_float, C.c_float, C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p]
+        l.orc_gut_fragment.restype = C.c_int
         l.orc_splat_normal.argtypes = [C.c_uint32, f32p, f32p, f32p, C.POINTER(A.FrameParams), f32p]
         l.orc_render_surface.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams),
                                          C.POINTER(A.Options), f32p, f32p, f32p, u32p, u32p]
@@ -179,6 +189,33 @@ def render_scene(packed_sets, instances, fp, opt):
     ids = np.empty(total, np.uint32)
     v = lib().orc_render_scene(sets, len(packed_sets), inst, len(instances), C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids))
     return img, keys[:v].copy(), ids[:v].copy()
+
+
+def default_gut_options(**kw) -> A.Options:
+    """Reference defaults of the 3DGUT pipeline restated independently (src/parameters.h:190,215)."""
+    o = default_options(pipeline=A.PIPELINE_3DGUT, extent_projection=A.EXTENT_CONIC, kernel_degree=2)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def render_gut(packed: Packed, rotation, fp, opt, want_quads=False):
+    """VK3DGUT oracle frame. Returns (image, sorted_keys, sorted_ids, quads or None)."""
+    img = np.zeros((fp.height, fp.width, 4), np.float32)
+    keys, ids = np.empty(packed.n, np.uint32), np.empty(packed.n, np.uint32)
+    quads = np.zeros(packed.n, GUT_QUAD_DTYPE) if want_quads else None
+    rot = np.ascontiguousarray(rotation, np.float32)
+    v = lib().orc_render_gut(_p(packed.centers), _p(packed.rgba), _p(packed.sh), _p(packed.scale), _p(rot), packed.n, packed.sh_degree,
+                             C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids), quads.ctypes.data_as(C.c_void_p) if want_quads else None)
+    return img, keys[:v].copy(), ids[:v].copy(), quads
+
+
+def gut_fragment(quad_record, px, py, fp, opt):
+    """(accepted, opacity) of one fragment of a 3DGUT quad (one element of the quads array)."""
+    op = np.zeros(1, np.float32)
+    rec = np.ascontiguousarray(quad_record)
+    ok = lib().orc_gut_fragment(rec.ctypes.data_as(C.c_void_p), float(px), float(py), C.byref(fp), C.byref(opt), _p(op))
+    return bool(ok), float(op[0])
 
 
 def splat_normal(packed: Packed, rotation, idx: int, fp) -> np.ndarray:

@@ -105,7 +105,7 @@ int main(int argc, char** argv)
       c.h     = 64 + uint32_t(splitmix64() % 2200);
       cams.push_back(c);
     }
-    std::vector<uint32_t> in, view, proj, focal;
+    std::vector<uint32_t> in, view, proj, focal, viewInv, projInv, viewQuat;
     for(const Cam& c : cams)
     {
       for(int k = 0; k < 3; k++)
@@ -136,12 +136,23 @@ int main(int argc, char** argv)
         proj.push_back(f2u(glm::value_ptr(P)[k]));
       focal.push_back(f2u(fx));
       focal.push_back(f2u(fy));
+      // 3DGUT camera pose: gaussian_splatting.cpp:1166 (viewInverse), :1200 (projInverse), :1254-1259 (viewQuat)
+      const glm::mat4 Vi = glm::inverse(V), Pi = glm::inverse(P);
+      const glm::quat q  = glm::quat_cast(V);
+      for(int k = 0; k < 16; k++)
+        viewInv.push_back(f2u(glm::value_ptr(Vi)[k]));
+      for(int k = 0; k < 16; k++)
+        projInv.push_back(f2u(glm::value_ptr(Pi)[k]));
+      viewQuat.push_back(f2u(q.x)), viewQuat.push_back(f2u(q.y)), viewQuat.push_back(f2u(q.z)), viewQuat.push_back(f2u(q.w));
     }
     std::fprintf(f, "  \"camera_count\": %zu,\n", cams.size());
     putArr(f, "camera_in", in);
     putArr(f, "camera_view", view);
     putArr(f, "camera_proj", proj);
     putArr(f, "camera_focal", focal);
+    putArr(f, "camera_view_inverse", viewInv);
+    putArr(f, "camera_proj_inverse", projInv);
+    putArr(f, "camera_view_quat", viewQuat);
   }
 
   // ---------------- pack: covariance + rgba ----------------------------------

@@ -461,7 +461,7 @@ def test_image_metrics_match_oracle(gpu_renderer):
 
 
 def test_fragment_counters_are_consistent_and_do_not_change_the_frame(gpu_renderer):
-    """Profiling variant of the blend kernel (options._reserved[3] & 128): same image bit for bit; every blended
+    """Profiling variant of the blend kernel (options._reserved[0] & 128): same image bit for bit; every blended
     fragment belongs to an evaluated (list entry, 8x8 block) pair; without early termination the number of blended
     fragments equals the number of non-discarded fragments of the oracle's rasterizer (alpha channel of a BTF frame
     rendered with rgb = 0, a = fragment count is not available, so the oracle count comes from its quads)."""
@@ -473,7 +473,7 @@ def test_fragment_counters_are_consistent_and_do_not_change_the_frame(gpu_render
     img0, st0, _, _ = r.render(fp)
     assert st0.fragments_blended == 0 and st0.list_entries_evaluated == 0
     opt = g.default_options(front_to_back=1)
-    opt._reserved[3] = 128
+    opt._reserved[0] = 128
     r.upload(s, opt)
     img1, st1, _, _ = r.render(fp)
     assert np.array_equal(img0, img1)

@@ -6,7 +6,7 @@ fp = g.frame_params(g.default_camera(), 1920, 1080)
 r = g.GaussianSplatting(0)
 for ab in [0,1,2,4,8,3,7,15]:
     opt = g.default_options(front_to_back=1, transmittance_epsilon=2.0**-15)
-    opt._reserved[3] = ab
+    opt._reserved[0] = ab
     r.upload(s, opt)
     r.set_profiling(True)
     acc=[]

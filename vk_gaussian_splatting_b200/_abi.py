@@ -24,6 +24,8 @@ VKGS_ERR_IO = -7
 FORMAT_FLOAT32, FORMAT_FLOAT16, FORMAT_UINT8 = 0, 1, 2
 FRUSTUM_CULLING_NONE, FRUSTUM_CULLING_AT_DIST, FRUSTUM_CULLING_AT_RASTER = 0, 1, 2
 SIZE_CULLING_DISABLED, SIZE_CULLING_ENABLED = 0, 1
+PIPELINE_3DGS, PIPELINE_3DGUT = 0, 1
+EXTENT_EIGEN, EXTENT_CONIC = 0, 1
 
 K_NAMES = ["preprocess", "sort_hist", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "bin_emit",
            "tile_hist", "tile_sort0", "tile_sort1", "tile_ranges", "blend"]
@@ -43,7 +45,8 @@ class Options(C.Structure):
                 ("ms_antialiasing", C.c_uint32), ("sh_format", C.c_uint32), ("rgba_format", C.c_uint32),
                 ("point_cloud_mode", C.c_uint32), ("show_sh_only", C.c_uint32), ("disable_opacity_gaussian", C.c_uint32),
                 ("transmittance_epsilon", C.c_float), ("target_format", C.c_uint32), ("surface_info", C.c_uint32),
-                ("_reserved", C.c_uint32 * 4)]
+                ("pipeline", C.c_uint32), ("extent_projection", C.c_uint32), ("kernel_degree", C.c_uint32),
+                ("_reserved", C.c_uint32 * 1)]
 
 
 class FrameParams(C.Structure):
@@ -52,7 +55,10 @@ class FrameParams(C.Structure):
                 ("viewport", C.c_float * 2), ("basis_viewport", C.c_float * 2), ("inverse_focal_adjustment", C.c_float),
                 ("splat_scale", C.c_float), ("frustum_dilation", C.c_float), ("alpha_cull_threshold", C.c_float),
                 ("size_culling_min_pixels", C.c_float), ("sh_degree", C.c_uint32), ("width", C.c_uint32),
-                ("height", C.c_uint32), ("depth_iso_threshold", C.c_float), ("thin_particle_threshold", C.c_float)]
+                ("height", C.c_uint32), ("depth_iso_threshold", C.c_float), ("thin_particle_threshold", C.c_float),
+                ("view_inverse", C.c_float * 16), ("proj_inverse", C.c_float * 16), ("view_quat", C.c_float * 4),
+                ("view_trans", C.c_float * 3), ("near_far", C.c_float * 2), ("alpha_clamp", C.c_float),
+                ("kernel_min_response", C.c_float)]
 
 
 class Camera(C.Structure):

@@ -257,7 +257,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   ba.status     = s.dBinStatus;
   ba.epoch      = nextEpoch(c);
   ba.ticketSlot = 5;
-  ba.debugFlags = c->opt._reserved[3];
+  ba.debugFlags = c->opt._reserved[0];
   launchBinEmit(ba, st);
   c->launches++;
   mark(VKGS_K_BIN_EMIT + 1);
@@ -307,7 +307,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   bl.frontToBack            = c->opt.front_to_back;
   bl.disableOpacityGaussian = c->opt.disable_opacity_gaussian;
   bl.transmittanceEpsilon   = c->opt.front_to_back ? c->opt.transmittance_epsilon : 0.0f;
-  bl.fragmentCounters       = (c->opt._reserved[3] & 128u) ? &s.dCounters->fragments[0] : nullptr;
+  bl.fragmentCounters       = (c->opt._reserved[0] & 128u) ? &s.dCounters->fragments[0] : nullptr;
   if(c->opt.surface_info)
   {
     bl.surface           = s.dSurface;

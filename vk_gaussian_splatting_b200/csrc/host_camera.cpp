@@ -26,6 +26,72 @@ inline V3    normalize(V3 v)
   return {v.x * inv, v.y * inv, v.z * inv};
 }
 
+// glm::inverse(mat4) with glm's operation order (glm/detail/func_matrix.inl, compute_inverse<4,4>);
+// m and out are column-major float[16], m[c][r] = m[4*c + r].
+void inverse4(const float* a, float* out)
+{
+#define M(c, r) a[4 * (c) + (r)]
+  const float Coef00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3), Coef02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3), Coef03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+  const float Coef04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3), Coef06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3), Coef07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+  const float Coef08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2), Coef10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2), Coef11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+  const float Coef12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3), Coef14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3), Coef15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+  const float Coef16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2), Coef18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2), Coef19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+  const float Coef20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1), Coef22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1), Coef23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+  const float Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07}, Fac2[4] = {Coef08, Coef08, Coef10, Coef11};
+  const float Fac3[4] = {Coef12, Coef12, Coef14, Coef15}, Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+  const float Vec0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, Vec1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+  const float Vec2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, Vec3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+  const float SignA[4] = {+1, -1, +1, -1}, SignB[4] = {-1, +1, -1, +1};
+  float       inv[16];
+  for(int k = 0; k < 4; k++)
+  {
+    inv[4 * 0 + k] = ((Vec1[k] * Fac0[k] - Vec2[k] * Fac1[k]) + Vec3[k] * Fac2[k]) * SignA[k];
+    inv[4 * 1 + k] = ((Vec0[k] * Fac0[k] - Vec2[k] * Fac3[k]) + Vec3[k] * Fac4[k]) * SignB[k];
+    inv[4 * 2 + k] = ((Vec0[k] * Fac1[k] - Vec1[k] * Fac3[k]) + Vec3[k] * Fac5[k]) * SignA[k];
+    inv[4 * 3 + k] = ((Vec0[k] * Fac2[k] - Vec1[k] * Fac4[k]) + Vec2[k] * Fac5[k]) * SignB[k];
+  }
+  const float d0 = M(0, 0) * inv[0], d1 = M(0, 1) * inv[4], d2 = M(0, 2) * inv[8], d3 = M(0, 3) * inv[12];
+  const float oneOverDet = 1.0f / ((d0 + d1) + (d2 + d3));
+  for(int k = 0; k < 16; k++)
+    out[k] = inv[k] * oneOverDet;
+#undef M
+}
+
+// glm::quat_cast(mat3(m)) (glm/gtc/quaternion.inl:81-123), returned as (x, y, z, w)
+void quatCast(const float* a, float q[4])
+{
+#define M(c, r) a[4 * (c) + (r)]
+  const float fourX = M(0, 0) - M(1, 1) - M(2, 2), fourY = M(1, 1) - M(0, 0) - M(2, 2), fourZ = M(2, 2) - M(0, 0) - M(1, 1),
+              fourW = M(0, 0) + M(1, 1) + M(2, 2);
+  int   biggest = 0;
+  float big     = fourW;
+  if(fourX > big)
+    big = fourX, biggest = 1;
+  if(fourY > big)
+    big = fourY, biggest = 2;
+  if(fourZ > big)
+    big = fourZ, biggest = 3;
+  const float val = std::sqrt(big + 1.0f) * 0.5f, mult = 0.25f / val;
+  float       w, x, y, z;
+  switch(biggest)
+  {
+    case 0:
+      w = val, x = (M(1, 2) - M(2, 1)) * mult, y = (M(2, 0) - M(0, 2)) * mult, z = (M(0, 1) - M(1, 0)) * mult;
+      break;
+    case 1:
+      w = (M(1, 2) - M(2, 1)) * mult, x = val, y = (M(0, 1) + M(1, 0)) * mult, z = (M(2, 0) + M(0, 2)) * mult;
+      break;
+    case 2:
+      w = (M(2, 0) - M(0, 2)) * mult, x = (M(0, 1) + M(1, 0)) * mult, y = val, z = (M(1, 2) + M(2, 1)) * mult;
+      break;
+    default:
+      w = (M(0, 1) - M(1, 0)) * mult, x = (M(2, 0) + M(0, 2)) * mult, y = (M(1, 2) + M(2, 1)) * mult, z = val;
+      break;
+  }
+  q[0] = x, q[1] = y, q[2] = z, q[3] = w;
+#undef M
+}
+
 void setIdentity(float* m)
 {
   std::memset(m, 0, 16 * sizeof(float));
@@ -59,6 +125,9 @@ extern "C" void vkgs_default_options(vkgs_options* opt)
   opt->sh_format            = VKGS_FORMAT_FLOAT32;
   opt->rgba_format          = VKGS_FORMAT_FLOAT32;
   opt->transmittance_epsilon = 0.0f;
+  opt->pipeline              = VKGS_PIPELINE_3DGS;
+  opt->extent_projection     = VKGS_EXTENT_CONIC;  // src/parameters.h:190 (only the 3DGUT pipeline reads it)
+  opt->kernel_degree         = 2;                  // KERNEL_DEGREE_QUADRATIC, src/parameters.h:215
 }
 
 extern "C" int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t width, uint32_t height, vkgs_frame_params* out)
@@ -116,6 +185,14 @@ extern "C" int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t wi
   out->sh_degree               = 3;
   out->width                   = width;
   out->height                  = height;
+  // 3DGUT pipeline: camera pose and inverse matrices (src/gaussian_splatting.cpp:1166-1169,1200,1254-1259)
+  inverse4(out->view, out->view_inverse);
+  inverse4(out->proj, out->proj_inverse);
+  quatCast(out->view, out->view_quat);
+  out->view_trans[0] = out->view[12], out->view_trans[1] = out->view[13], out->view_trans[2] = out->view[14];
+  out->near_far[0] = cam->znear, out->near_far[1] = cam->zfar;
+  out->alpha_clamp         = 0.99f;    // shaders/shaderio.h:271
+  out->kernel_min_response = 0.0113f;  // src/parameters.h:216
   out->depth_iso_threshold     = 0.7f;   // shaders/shaderio.h:311
   out->thin_particle_threshold = 1e-6f;  // shaders/shaderio.h:316
   return VKGS_OK;

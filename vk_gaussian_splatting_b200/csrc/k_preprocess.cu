@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   const bool     hasSh   = a.set.sh != nullptr && a.set.shDegree > 0 && a.fp.sh_degree > 0;
   const bool     sizeCul = a.opt.size_culling_mode == VKGS_SIZE_CULLING_ENABLED;
   const bool     needScale = sizeCul || a.surface != nullptr;  // log-scales are staged with the centres
-  const uint32_t ablate  = a.opt._reserved[3];
+  const uint32_t ablate  = a.opt._reserved[0];
   const uint32_t tiles   = (a.set.count + PRE_TILE - 1) / PRE_TILE;
 
   // claim a tile (ticket order == look-back order) and start its bulk copies. Stage A: what the

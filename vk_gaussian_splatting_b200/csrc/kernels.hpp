@@ -27,7 +27,7 @@ struct FrameCounters
   uint32_t overflow;           // set when D exceeded the tile-list capacity
   uint32_t sortSrc[4];         // [p]: which (key,id) buffer holds the output of depth-sort pass p (a pass
                                // whose digit is constant over all keys is skipped and does not flip it)
-  unsigned long long fragments[2];  // profiling only (vkgs_options._reserved[3] & 128): list entries evaluated by a
+  unsigned long long fragments[2];  // profiling only (vkgs_options._reserved[0] & 128): list entries evaluated by a
                                     // warp block (x64 pixels), and fragments that passed both discards and were blended
   uint32_t ticket[12];         // dynamic tile / partition tickets, one per kernel launch
   uint32_t depthHist[4][256];  // digit histograms of the depth keys (filled by the preprocess kernel)
