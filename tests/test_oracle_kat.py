@@ -340,3 +340,46 @@ def test_surface_outputs_single_splat():
     assert picked.any() and np.all(dt[picked, 0] == np.float32(q.ndc_z)) and np.all(dt[picked, 1] < 0.7) and np.all(dt[hit & ~picked, 1] >= 0.7)
     n = O.splat_normal(pk, s.rotation, 0, fp)
     assert np.allclose(nrm[hit, :3], n[None, :] * img[hit, 3:4], atol=1e-6)
+
+
+def test_3dgut_known_answers():
+    """VK3DGUT restatement: (i) the unscented transform of an isotropic splat on the optical axis projects to the
+    image centre with covariance (f s / z)^2 to first order; (ii) the particle response along the ray through the
+    splat centre is 1 (clamped to alphaClamp * density), and exp(-d^2/2) at canonical distance d; (iii) kernel degrees."""
+    cam = g.make_camera((0, 0, 3.0))
+    fp = O.frame_params(cam, 400, 400)
+    sc = 0.01
+    s = g.SplatSet(np.zeros((1, 3)), np.zeros((1, 3)), np.zeros((1, 0)), np.array([8.0]), np.log(np.full((1, 3), sc, np.float32)),
+                   np.array([[1, 0, 0, 0]], np.float32))
+    pk = O.Packed(s)
+    opt = O.default_gut_options(front_to_back=1)
+    img, keys, ids, quads = O.render_gut(pk, s.rotation, fp, opt, want_quads=True)
+    q = quads[0]
+    assert q["valid"] == 1 and np.allclose(q["center"], [200, 200], atol=1e-3)
+    f = abs(fp.focal[0])
+    sigma_px = f * sc / 3.0
+    # conic extent: min(3.33, sqrt(2 ln(a/0.01))) * sqrt(sigma^2 + 0.3)
+    a = 1 / (1 + math.exp(-8.0))
+    ef = min(3.33, math.sqrt(2 * math.log(a / 0.01)))
+    assert np.allclose(q["extent"], ef * math.sqrt(sigma_px ** 2 + 0.3), rtol=2e-3)
+    assert np.allclose(q["inv_rot"].reshape(3, 3), np.eye(3), atol=1e-7) and np.allclose(q["scale"], sc, rtol=1e-6)
+    # the ray generator adds 0.5 to SV_Position.xy (restated as written): the ray through the splat centre belongs to
+    # the fragment at (199.5, 199.5)
+    ok, op = O.gut_fragment(q, 199.5, 199.5, fp, opt)
+    assert ok and op == pytest.approx(min(0.99, a), rel=1e-6)
+    # one pixel to the right: canonical distance = (3 / f) / sc * cos-ish -> exp(-d^2 / 2)
+    ok, op1 = O.gut_fragment(q, 200.5, 199.5, fp, opt)
+    d = (3.0 / f) / sc
+    assert ok and op1 == pytest.approx(a * math.exp(-0.5 * d * d), rel=2e-3)
+    # response below KERNEL_MIN_RESPONSE (0.0113) or alpha <= 1/255 is rejected
+    far = 199.5 + math.sqrt(-2 * math.log(0.0113)) / d + 1.5
+    assert not O.gut_fragment(q, far, 199.5, fp, opt)[0]
+    # kernel degrees at the same fragment: generalized Gaussians of threedgrt.h.slang:83-127
+    dist = d * d
+    for deg, want in ((0, max(1 - 0.329630334487 * math.sqrt(dist), 0)), (1, math.exp(-1.5 * math.sqrt(dist))),
+                      (3, math.exp(-0.166666666667 * dist * math.sqrt(dist))), (4, math.exp(-0.0555555555556 * dist * dist)),
+                      (5, math.exp(-0.0185185185185 * dist * dist * math.sqrt(dist))), (8, math.exp(-0.000685871056241 * dist ** 4))):
+        ok, o = O.gut_fragment(q, 200.5, 199.5, fp, O.default_gut_options(front_to_back=1, kernel_degree=deg))
+        assert ok and o == pytest.approx(min(0.99, a * want), rel=3e-3), deg
+    # the frame: alpha at the centre pixel = clamped opacity
+    assert img[199, 199, 3] == pytest.approx(min(0.99, a), rel=1e-6)

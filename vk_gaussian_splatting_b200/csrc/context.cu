@@ -81,7 +81,8 @@ int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n, uint64_t preTiles)
     CU_TRY(c, cudaMalloc(&s.dKeys[i], n * sizeof(uint32_t)));
     CU_TRY(c, cudaMalloc(&s.dIds[i], n * sizeof(uint32_t)));
   }
-  CU_TRY(c, cudaMalloc(&s.dRecords, n * RECORD_WORDS * sizeof(uint32_t)));
+  const uint64_t recordWords = c->opt.pipeline == VKGS_PIPELINE_3DGUT ? GUT_RECORD_WORDS : RECORD_WORDS;
+  CU_TRY(c, cudaMalloc(&s.dRecords, n * recordWords * sizeof(uint32_t)));
   CU_TRY(c, cudaMalloc(&s.dBboxes, n * sizeof(uint2)));
   if(c->opt.surface_info)
     CU_TRY(c, cudaMalloc(&s.dSurface, n * sizeof(float4)));
@@ -144,8 +145,16 @@ uint32_t nextEpoch(vkgs_ctx* c)
 }
 
 // host-side per-frame constants, evaluated in the oracle's operation order
-void frameConstants(const vkgs_frame_params& fp, float mv[16], float camModel[3])
+void frameConstants(const vkgs_frame_params& fp, float mv[16], float camModel[3], float gutOrigin[3])
 {
+  // 3DGUT ray origin: mul(float4(0,0,0,1), viewInverse).xyz = viewInverse[3].xyz, then into model space
+  // (cameras.h.slang:40, threedgut_raster.frag.slang:117)
+  {
+    const float o[4] = {fp.view_inverse[12], fp.view_inverse[13], fp.view_inverse[14], 1.0f};
+    for(int j = 0; j < 3; j++)
+      gutOrigin[j] = ((o[0] * fp.model_inverse[0 + j] + o[1] * fp.model_inverse[4 + j]) + o[2] * fp.model_inverse[8 + j])
+                     + o[3] * fp.model_inverse[12 + j];
+  }
   // (fp.model / fp.model_inverse hold the transform of the instance being launched)
   for(int i = 0; i < 4; i++)
     for(int j = 0; j < 4; j++)
@@ -200,7 +209,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
       std::memcpy(pa.fp.model_inverse, inst.transformInverse, sizeof(pa.fp.model_inverse));
     }
     pa.opt = c->opt;
-    frameConstants(pa.fp, pa.mv, pa.camModel);
+    frameConstants(pa.fp, pa.mv, pa.camModel, pa.gutOrigin);
     pa.keys       = s.dKeys[0];
     pa.ids        = s.dIds[0];
     pa.records    = s.dRecords;
@@ -308,6 +317,19 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   bl.disableOpacityGaussian = c->opt.disable_opacity_gaussian;
   bl.transmittanceEpsilon   = c->opt.front_to_back ? c->opt.transmittance_epsilon : 0.0f;
   bl.fragmentCounters       = (c->opt._reserved[0] & 128u) ? &s.dCounters->fragments[0] : nullptr;
+  if(c->opt.pipeline == VKGS_PIPELINE_3DGUT)
+  {
+    const vkgs_ctx::Instance& inst = c->instances[0];
+    bl.gut.enabled      = 1;
+    bl.gut.kernelDegree = c->opt.kernel_degree;
+    std::memcpy(bl.gut.viewInverse, fp.view_inverse, sizeof(bl.gut.viewInverse));
+    std::memcpy(bl.gut.projInverse, fp.proj_inverse, sizeof(bl.gut.projInverse));
+    std::memcpy(bl.gut.modelInverse, inst.frameModel ? fp.model_inverse : inst.transformInverse, sizeof(bl.gut.modelInverse));
+    bl.gut.viewport[0] = fp.viewport[0], bl.gut.viewport[1] = fp.viewport[1];
+    bl.gut.alphaClamp         = fp.alpha_clamp;
+    bl.gut.kernelMinResponse  = fp.kernel_min_response;
+    bl.gut.alphaCullThreshold = fp.alpha_cull_threshold;
+  }
   if(c->opt.surface_info)
   {
     bl.surface           = s.dSurface;
@@ -614,6 +636,11 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad frustum_culling_mode");
   if(opt.target_format > VKGS_FORMAT_UINT8)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad target_format");
+  if(opt.pipeline > VKGS_PIPELINE_3DGUT)
+    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad pipeline");
+  if(opt.pipeline == VKGS_PIPELINE_3DGUT
+     && (opt.extent_projection != VKGS_EXTENT_CONIC || opt.surface_info || (instances && instanceCount > 1)))
+    return fail(c, VKGS_ERR_UNSUPPORTED, "the 3DGUT pipeline is built for EXTENT_CONIC, one instance, no surface info");
   if(opt.surface_info && !opt.front_to_back)
     return fail(c, VKGS_ERR_UNSUPPORTED, "surface_info needs front_to_back (the reference only produces it in its FTB pass)");
   uint64_t total = 0;

@@ -193,6 +193,26 @@ __device__ __forceinline__ unsigned match_digit(unsigned active, uint32_t digit)
   return peers;
 }
 
+// Same operation sequence as orc_expf (oracle/vkgs_oracle.c): Cody-Waite + Cephes polynomial.
+__device__ __forceinline__ float expfExact(float x)
+{
+  x              = fminf(fmaxf(x, -87.0f), 88.0f);
+  const float kf = rintf(__fmul_rn(x, 1.44269504088896341f));
+  float       r  = __fmaf_rn(-kf, 0.693359375f, x);
+  r              = __fmaf_rn(-kf, -2.12194440e-4f, r);
+  float p        = 1.9875691500e-4f;
+  p              = __fmaf_rn(p, r, 1.3981999507e-3f);
+  p              = __fmaf_rn(p, r, 8.3334519073e-3f);
+  p              = __fmaf_rn(p, r, 4.1665795894e-2f);
+  p              = __fmaf_rn(p, r, 1.6666665459e-1f);
+  p              = __fmaf_rn(p, r, 5.0000001201e-1f);
+  const float r2 = __fmul_rn(r, r);
+  float       e  = __fmaf_rn(p, r2, r);
+  e              = __fadd_rn(e, 1.0f);
+  const int   k  = static_cast<int>(kf);
+  return __fmul_rn(e, __uint_as_float(static_cast<uint32_t>(k + 127) << 23));
+}
+
 // ---------------------------------------------------------------------------------------------
 // scans
 

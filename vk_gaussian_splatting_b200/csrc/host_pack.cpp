@@ -164,7 +164,8 @@ int packSplatSet(const vkgs_splat_set_view& set, const vkgs_options& opt, uint64
   out.centers.assign(3 * pad, 0.0f);
   out.cov6.assign(6 * pad, 0.0f);
   out.scales.assign(3 * pad, 0.0f);
-  out.rotations.assign(opt.surface_info ? 4 * pad : 0, 0.0f);
+  const bool needRot = opt.surface_info || opt.pipeline == VKGS_PIPELINE_3DGUT;
+  out.rotations.assign(needRot ? 4 * pad : 0, 0.0f);
   out.rgba.assign(4 * pad * formatSize(opt.rgba_format), 0);
   out.sh.assign(out.shDegree ? 45 * pad * formatSize(opt.sh_format) : 0, 0);
 
@@ -174,7 +175,7 @@ int packSplatSet(const vkgs_splat_set_view& set, const vkgs_options& opt, uint64
     {
       std::memcpy(&out.centers[3 * i], set.positions + 3 * i, 3 * sizeof(float));
       std::memcpy(&out.scales[3 * i], set.scale + 3 * i, 3 * sizeof(float));
-      if(opt.surface_info)
+      if(needRot)
         std::memcpy(&out.rotations[4 * i], set.rotation + 4 * i, 4 * sizeof(float));
       covariance6(set.scale + 3 * i, set.rotation + 4 * i, &out.cov6[6 * i]);
       const float* dc = set.f_dc + 3 * i;

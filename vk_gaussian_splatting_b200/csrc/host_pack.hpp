@@ -18,7 +18,7 @@ struct PackedSplatSet
   std::vector<float>   centers;          // 3 * padded
   std::vector<float>   cov6;             // 6 * padded
   std::vector<float>   scales;           // 3 * padded (log-space, read by size culling and the surface-info normals)
-  std::vector<float>   rotations;        // 4 * padded raw quaternions (w,x,y,z), filled for options.surface_info only
+  std::vector<float>   rotations;        // 4 * padded raw quaternions (w,x,y,z), filled for options.surface_info / the 3DGUT pipeline only
   std::vector<uint8_t> rgba;             // 4 * padded * formatSize
   std::vector<uint8_t> sh;               // 45 * padded * formatSize (empty for degree 0)
 };

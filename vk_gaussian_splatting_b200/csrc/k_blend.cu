@@ -26,26 +26,6 @@ namespace vkgs {
 
 namespace {
 
-// Same operation sequence as orc_expf (oracle/vkgs_oracle.c): Cody-Waite + Cephes polynomial.
-__device__ __forceinline__ float expfExact(float x)
-{
-  x              = fminf(fmaxf(x, -87.0f), 88.0f);
-  const float kf = rintf(__fmul_rn(x, 1.44269504088896341f));
-  float       r  = __fmaf_rn(-kf, 0.693359375f, x);
-  r              = __fmaf_rn(-kf, -2.12194440e-4f, r);
-  float p        = 1.9875691500e-4f;
-  p              = __fmaf_rn(p, r, 1.3981999507e-3f);
-  p              = __fmaf_rn(p, r, 8.3334519073e-3f);
-  p              = __fmaf_rn(p, r, 4.1665795894e-2f);
-  p              = __fmaf_rn(p, r, 1.6666665459e-1f);
-  p              = __fmaf_rn(p, r, 5.0000001201e-1f);
-  const float r2 = __fmul_rn(r, r);
-  float       e  = __fmaf_rn(p, r2, r);
-  e              = __fadd_rn(e, 1.0f);
-  const int   k  = static_cast<int>(kf);
-  return __fmul_rn(e, __uint_as_float(static_cast<uint32_t>(k + 127) << 23));
-}
-
 // Slow path of the blend loop: the SFU opacity landed within the guard band of the discard
 // threshold, so the fragment is re-evaluated with the oracle's exp. `negAlpha` is MINUS the splat
 // alpha; returns MINUS the fragment opacity, or 0 when the fragment is discarded.
@@ -142,12 +122,10 @@ __device__ __forceinline__ void cpAsyncWaitAll()
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr uint32_t REC_BYTES   = RECORD_WORDS * 4;  // record, 48 B: cx cy w1x w1y | w2x w2y r g | b a bbox bbox
+// record, 48 B: cx cy w1x w1y | w2x w2y r g | b a bbox bbox   (3DGUT: 96 B, see k_preprocess.cu)
 constexpr int      BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int      EPT         = 1;                  // list entries gathered + classified per thread per round
 constexpr int      BATCH       = EPT * BLEND_THREADS;  // list entries staged per round
-constexpr uint32_t SMEM_REC    = BATCH * REC_BYTES; // bytes of one record buffer
-constexpr uint32_t SMEM_HIT    = 2 * SMEM_REC;      // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
 static_assert(BLEND_WARPS == 4, "the tile is split into 2x2 warp blocks of 8x8 pixels");
 
 // One CTA (4 warps) per 16x16 tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
@@ -167,10 +145,13 @@ static_assert(BLEND_WARPS == 4, "the tile is split into 2x2 warp blocks of 8x8 p
 // transmittance update is ordered. Signs are arranged so that no negation is needed per hit:
 // the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
 // colour.
-template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF>
-__global__ void __launch_bounds__(BLEND_THREADS, SURF ? 6 : 10) k_blend(const __grid_constant__ BlendArgs a)
+template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT>
+__global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend(const __grid_constant__ BlendArgs a)
 {
   // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
+  constexpr uint32_t REC_BYTES = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
+  constexpr uint32_t SMEM_REC  = BATCH * REC_BYTES;  // bytes of one record buffer
+  constexpr uint32_t SMEM_HIT  = 2 * SMEM_REC;       // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
   constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
   constexpr uint32_t SMEM_SID  = SMEM_SURF + 2 * BATCH * 16;
   __shared__ __align__(16) unsigned char s_raw[SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF];
@@ -185,6 +166,45 @@ __global__ void __launch_bounds__(BLEND_THREADS, SURF ? 6 : 10) k_blend(const __
   const float    nfx = -(static_cast<float>(px) + 0.5f);
   const f32x2    nfy2 = pk(-(static_cast<float>(pyA) + 0.5f), -(static_cast<float>(pyB) + 0.5f));
   const float    tileCx = static_cast<float>(tileX0) + 4.0f, tileCy = static_cast<float>(tileY0) + 4.0f;  // centre of warp block 0
+  // 3DGUT: the model-space ray directions of this thread's two pixels (generatePinholeRay, cameras.h.slang:27-44,
+  // called with SV_Position.xy AND a sub-pixel offset of 0.5, threedgut_raster.frag.slang:92 — restated as written;
+  // then threedgut_raster.frag.slang:117-121), in the operation order of orc_gut_fragment
+  float gutDirA[3] = {0.f, 0.f, 0.f}, gutDirB[3] = {0.f, 0.f, 0.f};
+  const float gutPyA = static_cast<float>(pyA) + 0.5f, gutPyB = static_cast<float>(pyB) + 0.5f;
+  if(GUT)
+  {
+#pragma unroll
+    for(int p = 0; p < 2; p++)
+    {
+      const float pcx = __fadd_rn(static_cast<float>(px) + 0.5f, 0.5f), pcy = __fadd_rn(p ? gutPyB : gutPyA, 0.5f);
+      const float dx = __fsub_rn(__fmul_rn(__fdiv_rn(pcx, a.gut.viewport[0]), 2.0f), 1.0f);
+      const float dy = __fsub_rn(__fmul_rn(__fdiv_rn(pcy, a.gut.viewport[1]), 2.0f), 1.0f);
+      const float t4[4] = {dx, dy, 1.0f, 1.0f};
+      float       tgt[4], dir[4];
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+        tgt[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t4[0], a.gut.projInverse[0 + j]), __fmul_rn(t4[1], a.gut.projInverse[4 + j])),
+                                     __fmul_rn(t4[2], a.gut.projInverse[8 + j])),
+                           __fmul_rn(t4[3], a.gut.projInverse[12 + j]));
+#pragma unroll
+      for(int j = 0; j < 4; j++)
+        dir[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tgt[0], a.gut.viewInverse[0 + j]), __fmul_rn(tgt[1], a.gut.viewInverse[4 + j])),
+                                     __fmul_rn(tgt[2], a.gut.viewInverse[8 + j])),
+                           __fmul_rn(0.0f, a.gut.viewInverse[12 + j]));
+      const float dn = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])), __fmul_rn(dir[2], dir[2])),
+                                                           __fmul_rn(dir[3], dir[3]))));
+      const float rd[3] = {__fmul_rn(dir[0], dn), __fmul_rn(dir[1], dn), __fmul_rn(dir[2], dn)};
+      float       dm[3];
+#pragma unroll
+      for(int j = 0; j < 3; j++)
+        dm[j] = __fadd_rn(__fadd_rn(__fmul_rn(rd[0], a.gut.modelInverse[0 + j]), __fmul_rn(rd[1], a.gut.modelInverse[4 + j])),
+                          __fmul_rn(rd[2], a.gut.modelInverse[8 + j]));
+      const float dmn = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dm[0], dm[0]), __fmul_rn(dm[1], dm[1])), __fmul_rn(dm[2], dm[2]))));
+#pragma unroll
+      for(int j = 0; j < 3; j++)
+        (p ? gutDirB : gutDirA)[j] = __fmul_rn(dm[j], dmn);
+    }
+  }
 
   const uint2 range = make_uint2(a.rangeBegin[tile], a.rangeEnd[tile]);  // empty tile: begin > end
   f32x2       c0 = pk(0.f, 0.f), c1 = c0, c2 = c0;            // MINUS the colour accumulators of the two pixels
@@ -204,11 +224,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, SURF ? 6 : 10) k_blend(const __
 
   // asynchronous gather of this thread's entry of a batch into record buffer `buf`
   auto gather = [&](uint32_t id, uint32_t buf, uint32_t slot) {
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.records + static_cast<uint64_t>(id) * RECORD_WORDS);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(a.records) + static_cast<uint64_t>(id) * REC_BYTES;
     const uint32_t       dst = sbase + buf * SMEM_REC + slot * REC_BYTES;
-    cpAsync16(dst, src);
-    cpAsync16(dst + 16, src + 16);
-    cpAsync16(dst + 32, src + 32);
+#pragma unroll
+    for(uint32_t k = 0; k < REC_BYTES; k += 16)
+      cpAsync16(dst + k, src + k);
     if(SURF)
     {
       cpAsync16(sbase + SMEM_SURF + (buf * BATCH + slot) * 16u, a.surface + id);
@@ -218,7 +238,20 @@ __global__ void __launch_bounds__(BLEND_THREADS, SURF ? 6 : 10) k_blend(const __
   // classify this thread's (landed) entry: per-warp-block hit bits -> per-warp hit masks
   auto classify = [&](bool have, uint32_t buf, uint32_t slot) {
     uint32_t bits = 0;
-    if(have)
+    if(have && GUT)
+    {
+      // 3DGUT quad: axis-aligned rectangle centre +- extent (EXTENT_CONIC); a block of pixel centres
+      // [x0+0.5, x0+7.5] overlaps it iff |block centre - c| <= extent + 3.5 on both axes
+      const float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * REC_BYTES);  // cx cy ex ey
+#pragma unroll
+      for(uint32_t b = 0; b < 4; b++)
+      {
+        const float ddx = tileCx + static_cast<float>(8u * (b & 1u)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b >> 1)) - r0.y;
+        if(fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + 3.501f)
+          bits |= 1u << b;
+      }
+    }
+    else if(have)
     {
       const uint32_t src = sbase + buf * SMEM_REC + slot * REC_BYTES;
       const float4   r0 = ldsV4(src), r1 = ldsV4(src + 16), r2 = ldsV4(src + 32);
@@ -269,6 +302,68 @@ __global__ void __launch_bounds__(BLEND_THREADS, SURF ? 6 : 10) k_blend(const __
   auto evalFrag = [&](uint32_t addr) {
     Frag         f;
     f.addr = addr;
+    if(GUT)
+    {
+      // threedgut_raster.frag.slang:87-191 + particleProcessHitGut (threedgrt.h.slang:238-278), in the
+      // operation order of orc_gut_fragment; exp through the oracle's fixed sequence: decisions are exact
+      const float4 q0 = ldsV4(addr);       // cx cy ex ey
+      const float4 q1 = ldsV4(addr + 16);  // r g b a
+      const float4 q2 = ldsV4(addr + 32);  // canonical ray origin
+      const float4 q3 = ldsV4(addr + 48);  // 1/scale.xyz, R00
+      const float4 q4 = ldsV4(addr + 64);  // R01 R02 R10 R11
+      const float4 q5 = ldsV4(addr + 80);  // R12 R20 R21 R22
+      f.r = q1.x, f.g = q1.y, f.b = q1.z, f.alpha = q1.w;
+      f.gmin = 1.0f;
+      f.A2   = pk(0.f, 0.f);
+      float nOp[2];
+#pragma unroll
+      for(int p = 0; p < 2; p++)
+      {
+        const float pxc = -nfx, pyc = p ? gutPyB : gutPyA;
+        const float* dm = p ? gutDirB : gutDirA;
+        bool  ok = fabsf(__fsub_rn(pxc, q0.x)) <= q0.z && fabsf(__fsub_rn(pyc, q0.y)) <= q0.w && !(q1.w <= a.gut.alphaCullThreshold);
+        const float rd0 = __fmul_rn(q3.x, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q3.w), __fmul_rn(dm[1], q4.z)), __fmul_rn(dm[2], q5.y)));
+        const float rd1 = __fmul_rn(q3.y, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.x), __fmul_rn(dm[1], q4.w)), __fmul_rn(dm[2], q5.z)));
+        const float rd2 = __fmul_rn(q3.z, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.y), __fmul_rn(dm[1], q5.x)), __fmul_rn(dm[2], q5.w)));
+        const float rn  = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rd0, rd0), __fmul_rn(rd1, rd1)), __fmul_rn(rd2, rd2))));
+        const float d0 = __fmul_rn(rd0, rn), d1 = __fmul_rn(rd1, rn), d2 = __fmul_rn(rd2, rn);
+        const float c0x = __fsub_rn(__fmul_rn(d1, q2.z), __fmul_rn(d2, q2.y)), c1x = __fsub_rn(__fmul_rn(d2, q2.x), __fmul_rn(d0, q2.z)),
+                    c2x = __fsub_rn(__fmul_rn(d0, q2.y), __fmul_rn(d1, q2.x));
+        const float dist = __fadd_rn(__fadd_rn(__fmul_rn(c0x, c0x), __fmul_rn(c1x, c1x)), __fmul_rn(c2x, c2x));
+        float       resp;
+        switch(a.gut.kernelDegree)
+        {
+          case 8: {
+            const float d2s = __fmul_rn(dist, dist);
+            resp            = expfExact(__fmul_rn(__fmul_rn(-0.000685871056241f, d2s), d2s));
+            break;
+          }
+          case 5:
+            resp = expfExact(__fmul_rn(__fmul_rn(__fmul_rn(-0.0185185185185f, dist), dist), __fsqrt_rn(dist)));
+            break;
+          case 4:
+            resp = expfExact(__fmul_rn(__fmul_rn(-0.0555555555556f, dist), dist));
+            break;
+          case 3:
+            resp = expfExact(__fmul_rn(__fmul_rn(-0.166666666667f, dist), __fsqrt_rn(dist)));
+            break;
+          case 1:
+            resp = expfExact(__fmul_rn(-1.5f, __fsqrt_rn(dist)));
+            break;
+          case 0:
+            resp = fmaxf(__fadd_rn(1.0f, __fmul_rn(-0.329630334487f, __fsqrt_rn(dist))), 0.0f);
+            break;
+          default:
+            resp = expfExact(__fmul_rn(-0.5f, dist));
+            break;
+        }
+        const float alpha = fminf(a.gut.alphaClamp, __fmul_rn(resp, q1.w));
+        ok                = ok && alpha > 1.0f / 255.0f && resp > a.gut.kernelMinResponse;
+        nOp[p]            = ok ? (NOGAUSS ? -1.0f : -alpha) : 0.0f;
+      }
+      f.n2 = pk(nOp[0], nOp[1]);
+      return f;
+    }
     const float4 ra  = ldsV4(addr);       // cx cy w1x w1y
     const float4 rb  = ldsV4(addr + 16);  // w2x w2y r g
     const float2 rc  = ldsV2(addr + 32);  // b a
@@ -530,18 +625,37 @@ void launchBlend(const BlendArgs& args, cudaStream_t stream)
   {
     // surface-info variant: front to back only (the context rejects other combinations)
     if(args.disableOpacityGaussian)
-      k_blend<true, true, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      k_blend<true, true, false, true, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);
     else
-      k_blend<true, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      k_blend<true, false, false, true, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+    return;
+  }
+  if(args.gut.enabled)
+  {
+    // VK3DGUT fragment stage (no fragment counters / surface info in this variant)
+    if(args.frontToBack)
+    {
+      if(args.disableOpacityGaussian)
+        k_blend<true, true, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      else
+        k_blend<true, false, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+    }
+    else
+    {
+      if(args.disableOpacityGaussian)
+        k_blend<false, true, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      else
+        k_blend<false, false, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+    }
     return;
   }
 #define VKGS_BLEND_LAUNCH(F, G)                                                                                                  \
   do                                                                                                                             \
   {                                                                                                                              \
     if(count)                                                                                                                    \
-      k_blend<F, G, true, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                            \
+      k_blend<F, G, true, false, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                            \
     else                                                                                                                         \
-      k_blend<F, G, false, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                           \
+      k_blend<F, G, false, false, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                           \
   } while(0)
   if(args.frontToBack)
   {

@@ -118,7 +118,150 @@ __device__ __forceinline__ void shRadiance(const void* row, int rowBase, uint32_
   }
 }
 
-template <int SHFMT>
+// ---- VK3DGUT per-splat stage (threedgut_raster.mesh.slang:97-255; pinhole camera, EXTENT_CONIC) ----------
+// Same operation order as orc_gut_project_splat / gut_project_point in oracle/vkgs_oracle.c.
+
+// projectPointWithShutter (global shutter) + projectPointPinhole with zero distortion coefficients
+// (threedgut_camera_projections.h.slang:87-139,186-203)
+__device__ __forceinline__ int gutProjectPoint(const float world[3], const vkgs_frame_params& fp, float projected[2])
+{
+  const float t[3]  = {fp.view_trans[0] * 1.0f, fp.view_trans[1] * 1.0f, fp.view_trans[2] * -1.0f};
+  const float q[4]  = {fp.view_quat[0] * -1.0f, fp.view_quat[1] * -1.0f, fp.view_quat[2] * 1.0f, fp.view_quat[3] * 1.0f};
+  const float pf[3] = {world[0] * 1.0f, world[1] * 1.0f, world[2] * -1.0f};
+  const float tt[3] = {2.0f * (q[1] * pf[2] - q[2] * pf[1]), 2.0f * (q[2] * pf[0] - q[0] * pf[2]), 2.0f * (q[0] * pf[1] - q[1] * pf[0])};
+  const float r[3]  = {(pf[0] + q[3] * tt[0]) + (q[1] * tt[2] - q[2] * tt[1]), (pf[1] + q[3] * tt[1]) + (q[2] * tt[0] - q[0] * tt[2]),
+                       (pf[2] + q[3] * tt[2]) + (q[0] * tt[1] - q[1] * tt[0])};
+  const float pos[3] = {r[0] + t[0], r[1] + t[1], r[2] + t[2]};
+  if(pos[2] <= 0.0f)
+  {
+    projected[0] = projected[1] = 0.0f;
+    return 0;
+  }
+  const float u = pos[0] / pos[2], v = pos[1] / pos[2];
+  const float u2 = u * u, v2 = v * v, r2 = u2 + v2, a1 = (2.0f * u) * v, a2 = r2 + 2.0f * u2, a3 = r2 + 2.0f * v2;
+  const float icDn = 1.0f + r2 * (0.0f + r2 * (0.0f + r2 * 0.0f)), icDd = 1.0f + r2 * (0.0f + r2 * (0.0f + r2 * 0.0f));
+  const float icD  = icDn / icDd;
+  const float dx = (0.0f * a1 + 0.0f * a2) + r2 * (0.0f + r2 * 0.0f), dy = (0.0f * a3 + 0.0f * a1) + r2 * (0.0f + r2 * 0.0f);
+  const float und = icD * u + dx, vnd = icD * v + dy;
+  const int   validRadial = (icD > 0.8f) && (icD < 1.2f);
+  const float ppx = fp.viewport[0] / 2.0f, ppy = fp.viewport[1] / 2.0f;
+  projected[0] = und * fp.focal[0] + ppx;
+  projected[1] = vnd * fp.focal[1] + ppy;
+  const float tolx = fp.viewport[0] * 0.1f, toly = fp.viewport[1] * 0.1f;
+  return validRadial && (projected[0] > -tolx) && (projected[1] > -toly) && (projected[0] < fp.viewport[0] + tolx)
+         && (projected[1] < fp.viewport[1] + toly);
+}
+
+// Unscented-transform projection + conic extent of one splat. Writes the 24-word 3DGUT record
+//   cx cy ex ey | r g b a | ro.xyz - | 1/scale.xyz R00 | R01 R02 R10 R11 | R12 R20 R21 R22
+// (R = inverse rotation, ro = canonical ray origin: the ray origin is the camera for every pixel, so
+// particleCannonicalRay's origin half is evaluated once per splat) and returns the pixel bounding box.
+__device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const float c[4], const float4 rq, const float* scaleLog,
+                                               float4 col, float4 rec[6], uint32_t& bb0, uint32_t& bb1)
+{
+  const vkgs_frame_params& fp = a.fp;
+  const float scale[3] = {expfExact(scaleLog[0]), expfExact(scaleLog[1]), expfExact(scaleLog[2])};
+  const float rinv = 1.0f / sqrtf(((rq.y * rq.y + rq.z * rq.z) + rq.w * rq.w) + rq.x * rq.x);
+  const float x = rq.y * rinv, y = rq.z * rinv, z = rq.w * rinv, w = rq.x * rinv;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  const float rot[3][3] = {{1.0f - 2.0f * (yy + zz), 2.0f * (xy + wz), 2.0f * (xz - wy)},
+                           {2.0f * (xy - wz), 1.0f - 2.0f * (xx + zz), 2.0f * (yz + wx)},
+                           {2.0f * (xz + wy), 2.0f * (yz - wx), 1.0f - 2.0f * (xx + yy)}};
+  if(col.w < fp.alpha_cull_threshold)
+    return false;
+  const float GUT_DELTA = 1.73205080757f, GUT_LAMBDA = 0.0f, GUT_D = 3.0f;
+  float       sp[7][2];
+  int         nvalid = 0;
+  float       world[4], pt[4];
+  mulVecMat(c, fp.model, world);
+  nvalid += gutProjectPoint(world, fp, sp[0]);
+  const float w0c   = GUT_LAMBDA / (GUT_D + GUT_LAMBDA);
+  float       pc[2] = {sp[0][0] * w0c, sp[0][1] * w0c};
+  const float wi    = 1.0f / (2.0f * (GUT_D + GUT_LAMBDA));
+#pragma unroll
+  for(int i = 0; i < 3; i++)
+  {
+    const float dl[3] = {(GUT_DELTA * scale[i]) * rot[i][0], (GUT_DELTA * scale[i]) * rot[i][1], (GUT_DELTA * scale[i]) * rot[i][2]};
+    pt[0] = c[0] + dl[0], pt[1] = c[1] + dl[1], pt[2] = c[2] + dl[2], pt[3] = 1.0f;
+    mulVecMat(pt, fp.model, world);
+    nvalid += gutProjectPoint(world, fp, sp[i + 1]);
+    pc[0] += wi * sp[i + 1][0], pc[1] += wi * sp[i + 1][1];
+    pt[0] = c[0] - dl[0], pt[1] = c[1] - dl[1], pt[2] = c[2] - dl[2];
+    mulVecMat(pt, fp.model, world);
+    nvalid += gutProjectPoint(world, fp, sp[i + 4]);
+    pc[0] += wi * sp[i + 4][0], pc[1] += wi * sp[i + 4][1];
+  }
+  if(nvalid == 0)
+    return false;
+  float cov[3];
+  {
+    const float cx = sp[0][0] - pc[0], cy = sp[0][1] - pc[1];
+    const float w0 = GUT_LAMBDA / (GUT_D + GUT_LAMBDA) + ((1.0f - 1.0f * 1.0f) + 2.0f);
+    cov[0] = w0 * (cx * cx), cov[1] = w0 * (cx * cy), cov[2] = w0 * (cy * cy);
+  }
+#pragma unroll
+  for(int i = 0; i < 6; i++)
+  {
+    const float cx = sp[i + 1][0] - pc[0], cy = sp[i + 1][1] - pc[1];
+    cov[0] += wi * (cx * cx), cov[1] += wi * (cx * cy), cov[2] += wi * (cy * cy);
+  }
+  // threedgutProjectedExtentConicOpacity (threedgut.h.slang:118-163)
+  const float dc[3] = {cov[0] + 0.3f, cov[1], cov[2] + 0.3f};
+  const float ddet  = dc[0] * dc[2] - dc[1] * dc[1];
+  if(ddet == 0.0f)
+    return false;
+  float conicW = col.w;
+  if(a.opt.ms_antialiasing)
+  {
+    const float det = cov[0] * cov[2] - cov[1] * cov[1];
+    conicW          = col.w * sqrtf(fmaxf(0.000025f, det / ddet));
+  }
+  if(conicW < 0.01f)
+    return false;
+  const float maxPower = logf(conicW / 0.01f);
+  const float ef       = fminf(3.33f, sqrtf(2.0f * maxPower));
+  const float mid      = 0.5f * (dc[0] + dc[2]);
+  const float lambda   = mid + sqrtf(fmaxf(0.01f, mid * mid - ddet));
+  const float radius   = ef * sqrtf(lambda);
+  const float ex = fminf(ef * sqrtf(dc[0]), radius), ey = fminf(ef * sqrtf(dc[2]), radius);
+  if(!(radius > 0.0f))
+    return false;
+  if(a.opt.ms_antialiasing)
+    col.w = conicW;
+  float wc[4], vc[4], cc[4];
+  mulVecMat(c, fp.model, wc);
+  mulVecMat(wc, fp.view, vc);
+  mulVecMat(vc, fp.proj, cc);
+  const float nz = cc[2] / cc[3];
+  if(!(nz >= 0.0f && nz <= 1.0f) || !isfinite(pc[0]) || !isfinite(pc[1]) || !(ex < 1e7f) || !(ey < 1e7f))
+    return false;
+  // canonical ray origin: giscl * mul(camModel - position, invRotation) (threedgrt.h.slang:65-69)
+  const float giscl[3] = {1.0f / scale[0], 1.0f / scale[1], 1.0f / scale[2]};
+  const float gposc[3] = {a.gutOrigin[0] - c[0], a.gutOrigin[1] - c[1], a.gutOrigin[2] - c[2]};
+  float       ro[3];
+#pragma unroll
+  for(int j = 0; j < 3; j++)  // invRotation[i][j] = rot[j][i]
+    ro[j] = giscl[j] * ((gposc[0] * rot[j][0] + gposc[1] * rot[j][1]) + gposc[2] * rot[j][2]);
+  rec[0] = make_float4(pc[0], pc[1], ex, ey);
+  rec[1] = col;
+  rec[2] = make_float4(ro[0], ro[1], ro[2], 0.0f);
+  rec[3] = make_float4(giscl[0], giscl[1], giscl[2], rot[0][0]);        // invRot row 0 = (rot[0][0], rot[1][0], rot[2][0])
+  rec[4] = make_float4(rot[1][0], rot[2][0], rot[0][1], rot[1][1]);      // invRot[0][1..2], invRot[1][0..1]
+  rec[5] = make_float4(rot[2][1], rot[0][2], rot[1][2], rot[2][2]);      // invRot[1][2], invRot[2][0..2]
+  // pixel bounding box of the quad, one pixel of slack (the blend applies the exact |d| <= extent test)
+  const float W = fp.viewport[0], H = fp.viewport[1];
+  const float fx0 = floorf(pc[0] - ex - 1.0f), fx1 = ceilf(pc[0] + ex + 1.0f);
+  const float fy0 = floorf(pc[1] - ey - 1.0f), fy1 = ceilf(pc[1] + ey + 1.0f);
+  if(fx1 < 0.0f || fy1 < 0.0f || fx0 > W - 1.0f || fy0 > H - 1.0f)
+    return false;
+  const uint32_t x0 = static_cast<uint32_t>(fmaxf(fx0, 0.0f)), x1 = static_cast<uint32_t>(fminf(fx1, W - 1.0f));
+  const uint32_t y0 = static_cast<uint32_t>(fmaxf(fy0, 0.0f)), y1 = static_cast<uint32_t>(fminf(fy1, H - 1.0f));
+  bb0 = x0 | (y0 << 16);
+  bb1 = x1 | (y1 << 16);
+  return true;
+}
+
+template <int SHFMT, bool GUT>
 __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__ PreprocessArgs a)
 {
   extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -130,7 +273,8 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   const uint32_t rgbaEl  = a.set.rgbaFormat == VKGS_FORMAT_FLOAT32 ? 4u : (a.set.rgbaFormat == VKGS_FORMAT_FLOAT16 ? 2u : 1u);
   const bool     hasSh   = a.set.sh != nullptr && a.set.shDegree > 0 && a.fp.sh_degree > 0;
   const bool     sizeCul = a.opt.size_culling_mode == VKGS_SIZE_CULLING_ENABLED;
-  const bool     needScale = sizeCul || a.surface != nullptr;  // log-scales are staged with the centres
+  constexpr bool gut       = GUT;  // separate instantiation: the 3DGUT code must not cost the 3DGS path registers
+  const bool     needScale = sizeCul || a.surface != nullptr || gut;  // log-scales are staged with the centres
   const uint32_t ablate  = a.opt._reserved[0];
   const uint32_t tiles   = (a.set.count + PRE_TILE - 1) / PRE_TILE;
 
@@ -270,7 +414,37 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     a.ids[slot]         = pendId;
   }
   mbar_wait(&sm.mbarB, phase);
-  if(keep)
+  if(GUT && keep)
+  {
+    // VK3DGUT: colour (+ SH) first, then the unscented-transform projection (threedgut_raster.mesh.slang:115-218)
+    float4 col = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
+    if(a.opt.show_sh_only)
+      col.x = col.y = col.z = 0.5f;
+    if(hasSh)
+    {
+      float       d[3] = {c[0] - a.camModel[0], c[1] - a.camModel[1], c[2] - a.camModel[2]};
+      const float dinv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      d[0] *= dinv, d[1] *= dinv, d[2] *= dinv;
+      float rad[3];
+      shRadiance<SHFMT>(sm.sh, 45 * static_cast<int>(tid), min(a.set.shDegree, a.fp.sh_degree), d[0], d[1], d[2], rad);
+      col.x += rad[0], col.y += rad[1], col.z += rad[2];
+    }
+    float4         rec6[6];
+    uint32_t       bb0 = 1u, bb1 = 0u;
+    const float4   rq  = *reinterpret_cast<const float4*>(a.set.rotations + 4 * id);
+    const bool     ok  = gutProjectSplat(a, c, rq, sm.scale + 3 * tid, col, rec6, bb0, bb1);
+    if(!ok)
+      bb0 = 1u, bb1 = 0u;
+    else
+    {
+      float4* rec = reinterpret_cast<float4*>(a.records + (a.idBase + id) * GUT_RECORD_WORDS);
+#pragma unroll
+      for(int k = 0; k < 6; k++)
+        rec[k] = rec6[k];
+    }
+    a.bboxes[a.idBase + id] = make_uint2(bb0, bb1);
+  }
+  else if(!GUT && keep)
   {
     float4   col   = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
     bool     valid = !(col.w < a.fp.alpha_cull_threshold);  // mesh.slang:165
@@ -531,15 +705,18 @@ int g_preCapEnv = 0;                          // VKGS_PRE_CTAS_PER_SM (tuning ex
 void initPreprocessKernels()
 {
   const int smem = static_cast<int>(sizeof(PreSmem));
-  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_UINT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_UINT8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_FLOAT16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_preprocess<VKGS_FORMAT_UINT8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_preSms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[0], k_preprocess<VKGS_FORMAT_FLOAT32>, PRE_TILE, smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[1], k_preprocess<VKGS_FORMAT_FLOAT16>, PRE_TILE, smem);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[2], k_preprocess<VKGS_FORMAT_UINT8>, PRE_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[0], k_preprocess<VKGS_FORMAT_FLOAT32, false>, PRE_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[1], k_preprocess<VKGS_FORMAT_FLOAT16, false>, PRE_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_prePerSm[2], k_preprocess<VKGS_FORMAT_UINT8, false>, PRE_TILE, smem);
   if(const char* e = getenv("VKGS_PRE_CTAS_PER_SM"))
     g_preCapEnv = atoi(e);
 }
@@ -562,16 +739,26 @@ void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream)
   if(grid == 0)
     return;
   const size_t smem = sizeof(PreSmem);
+  const bool   gut  = args.opt.pipeline == VKGS_PIPELINE_3DGUT;
   switch(args.set.shFormat)
   {
     case VKGS_FORMAT_FLOAT16:
-      k_preprocess<VKGS_FORMAT_FLOAT16><<<grid, PRE_TILE, smem, stream>>>(args);
+      if(gut)
+        k_preprocess<VKGS_FORMAT_FLOAT16, true><<<grid, PRE_TILE, smem, stream>>>(args);
+      else
+        k_preprocess<VKGS_FORMAT_FLOAT16, false><<<grid, PRE_TILE, smem, stream>>>(args);
       break;
     case VKGS_FORMAT_UINT8:
-      k_preprocess<VKGS_FORMAT_UINT8><<<grid, PRE_TILE, smem, stream>>>(args);
+      if(gut)
+        k_preprocess<VKGS_FORMAT_UINT8, true><<<grid, PRE_TILE, smem, stream>>>(args);
+      else
+        k_preprocess<VKGS_FORMAT_UINT8, false><<<grid, PRE_TILE, smem, stream>>>(args);
       break;
     default:
-      k_preprocess<VKGS_FORMAT_FLOAT32><<<grid, PRE_TILE, smem, stream>>>(args);
+      if(gut)
+        k_preprocess<VKGS_FORMAT_FLOAT32, true><<<grid, PRE_TILE, smem, stream>>>(args);
+      else
+        k_preprocess<VKGS_FORMAT_FLOAT32, false><<<grid, PRE_TILE, smem, stream>>>(args);
       break;
   }
 }

@@ -10,6 +10,7 @@ namespace vkgs {
 // ---- geometry of the per-frame pipeline ------------------------------------------------------
 constexpr int      PRE_TILE        = 256;   // splats per preprocess tile (= block size)
 constexpr int      RECORD_WORDS    = 12;    // per-splat record, 48 B
+constexpr int      GUT_RECORD_WORDS = 24;   // 3DGUT pipeline: 96 B, see k_preprocess.cu
 constexpr int      SORT_THREADS    = 512;
 constexpr int      SORT_ITEMS      = 8;     // keys per thread
 constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per partition
@@ -55,6 +56,7 @@ struct PreprocessArgs
   vkgs_options      opt;
   float             mv[16];      // mul(transform, viewMatrix), evaluated once per frame on the host
   float             camModel[3]; // camera position in model space
+  float             gutOrigin[3];// 3DGUT: ray origin (viewInverse translation) in model space
   uint32_t*         keys;        // [V] compacted, ascending splat id
   uint32_t*         ids;         // [V]
   uint32_t*         records;     // [N][RECORD_WORDS], indexed by splat id
@@ -134,6 +136,16 @@ struct BinArgs
 void launchBinEmit(const BinArgs& args, cudaStream_t stream);
 
 
+// per-frame constants of the VK3DGUT fragment stage (FrameInfo + SplatSetDesc fields it reads)
+struct GutFrameConstants
+{
+  uint32_t enabled;
+  uint32_t kernelDegree;
+  float    viewInverse[16], projInverse[16], modelInverse[16];
+  float    viewport[2];
+  float    alphaClamp, kernelMinResponse, alphaCullThreshold;
+};
+
 struct BlendArgs
 {
   const uint32_t* tileVals;  // tile-sorted splat ids
@@ -153,6 +165,7 @@ struct BlendArgs
   float2*         outDepthT;       // [H][W] picked depth, transmittance
   uint32_t*       outSplatId;      // [H][W] id of the last blended fragment
   float           depthIsoThreshold;
+  GutFrameConstants gut;           // gut.enabled = 0 for the 3DGS pipeline
 };
 
 void launchBlend(const BlendArgs& args, cudaStream_t stream);
