@@ -9,12 +9,12 @@ PEAK = 6538.6
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 r = g.GaussianSplatting(0, stream=stream.cuda_stream)
 
-def run(name, n, w, h, seed, steps=100):
+def run(name, n, w, h, seed, steps=100, **optkw):
     t0 = time.time()
     s = g.synth_scene(n, 3, seed)
     t_gen = time.time() - t0
     t0 = time.time()
-    r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0 ** -15))
+    r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0 ** -15, **optkw))
     t_up = time.time() - t0
     fp = g.frame_params(g.default_camera(), w, h)
     r.set_frames_in_flight(2)
@@ -42,6 +42,8 @@ which = sys.argv[1:] or ["2", "3", "5", "sort"]
 if "2" in which: run("cfg2 1M SH3 1080p", 1_000_000, 1920, 1080, 0x3D650001, 200)
 if "3" in which: run("cfg3 6M SH3 4K", 6_000_000, 3840, 2160, 0x3D650002, 50)
 if "5" in which: run("cfg5 30M SH3 1080p", 30_000_000, 1920, 1080, 0x3D650004, 20)
+if "gut" in which: run("cfg2 1M SH3 1080p VK3DGUT pipeline", 1_000_000, 1920, 1080, 0x3D650001, 100, pipeline=1)
+if "surf" in which: run("cfg2 1M SH3 1080p + surface info", 1_000_000, 1920, 1080, 0x3D650001, 100, surface_info=1)
 if "sort" in which:
     rng = np.random.default_rng(5)
     for n in (1, 2, 4, 8, 16, 30):
