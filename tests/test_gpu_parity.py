@@ -558,6 +558,8 @@ def test_3dgut_pipeline_matches_oracle(gpu_renderer):
     for deg in (0, 1, 3, 4, 5, 8):
         _compare_gut_frame(r, g.synth_scene(8_000, 0, 0x3D650102), cam, 256, 144, front_to_back=1, kernel_degree=deg)
     _compare_gut_frame(r, s, g.orbit_camera(3, 8), 400, 300, front_to_back=1, disable_opacity_gaussian=1)
+    # a larger frame: millions of fragments, so the guard bands around the two discard thresholds get exercised
+    _compare_gut_frame(r, g.synth_scene(120_000, 3, 0x3D650103), g.orbit_camera(5, 8), 960, 540, front_to_back=1)
     # not the same estimator as the 3DGS pipeline, but the same picture
     r.upload(s, g.default_options(front_to_back=1))
     img3, _, _, _ = r.render(g.frame_params(cam, 480, 270))

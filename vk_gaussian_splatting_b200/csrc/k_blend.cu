@@ -315,10 +315,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend
       f.r = q1.x, f.g = q1.y, f.b = q1.z, f.alpha = q1.w;
       f.gmin = 1.0f;
       f.A2   = pk(0.f, 0.f);
-      float nOp[2];
-#pragma unroll
-      for(int p = 0; p < 2; p++)
-      {
+      // exact evaluation of one pixel (the oracle's operation order and exp): the reference path for every kernel
+      // degree, and the arbiter of the fast path below
+      auto exactPixel = [&](int p) -> float {
         const float pxc = -nfx, pyc = p ? gutPyB : gutPyA;
         const float* dm = p ? gutDirB : gutDirA;
         bool  ok = fabsf(__fsub_rn(pxc, q0.x)) <= q0.z && fabsf(__fsub_rn(pyc, q0.y)) <= q0.w && !(q1.w <= a.gut.alphaCullThreshold);
@@ -359,7 +358,52 @@ __global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend
         }
         const float alpha = fminf(a.gut.alphaClamp, __fmul_rn(resp, q1.w));
         ok                = ok && alpha > 1.0f / 255.0f && resp > a.gut.kernelMinResponse;
-        nOp[p]            = ok ? (NOGAUSS ? -1.0f : -alpha) : 0.0f;
+        return ok ? (NOGAUSS ? -1.0f : -alpha) : 0.0f;
+      };
+      float nOp[2];
+      if(a.gut.kernelDegree != 2u)
+      {
+        nOp[0] = exactPixel(0);
+        nOp[1] = exactPixel(1);
+      }
+      else
+      {
+        // Fast path of the default (quadratic = Gaussian) kernel, both pixels with packed fp32:
+        // dist = |rd x ro|^2 / |rd|^2 without normalising rd first, reciprocal and exp on the SFU. Within
+        // The canonical origin is hundreds of units long (distance / scale), so the cross product cancels and the
+        // two evaluation orders differ by up to ~1e-4 relative in dist; a pixel whose alpha or response lands
+        // within 2e-3 (relative) of its discard threshold is re-evaluated exactly, so accept / reject decisions
+        // never differ from the oracle.
+        const f32x2 m0 = pk(gutDirA[0], gutDirB[0]), m1 = pk(gutDirA[1], gutDirB[1]), m2 = pk(gutDirA[2], gutDirB[2]);
+        const f32x2 r0 = mul2(fma2(m2, pk(q5.y, q5.y), fma2(m1, pk(q4.z, q4.z), mul2(m0, pk(q3.w, q3.w)))), pk(q3.x, q3.x));
+        const f32x2 r1 = mul2(fma2(m2, pk(q5.z, q5.z), fma2(m1, pk(q4.w, q4.w), mul2(m0, pk(q4.x, q4.x)))), pk(q3.y, q3.y));
+        const f32x2 r2 = mul2(fma2(m2, pk(q5.w, q5.w), fma2(m1, pk(q5.x, q5.x), mul2(m0, pk(q4.y, q4.y)))), pk(q3.z, q3.z));
+        const float nox = -q2.x, noy = -q2.y, noz = -q2.z;
+        const f32x2 cx = fma2(r1, pk(q2.z, q2.z), mul2(r2, pk(noy, noy)));
+        const f32x2 cy = fma2(r2, pk(q2.x, q2.x), mul2(r0, pk(noz, noz)));
+        const f32x2 cz = fma2(r0, pk(q2.y, q2.y), mul2(r1, pk(nox, nox)));
+        const f32x2 num = fma2(cz, cz, fma2(cy, cy, mul2(cx, cx)));
+        const f32x2 den = fma2(r2, r2, fma2(r1, r1, mul2(r0, r0)));
+        float       nlo, nhi, dlo, dhi;
+        upk(num, nlo, nhi);
+        upk(den, dlo, dhi);
+        const float distA = __fdividef(nlo, dlo), distB = __fdividef(nhi, dhi);
+        const float respA = ex2Approx(distA * -0.72134752044448170368f), respB = ex2Approx(distB * -0.72134752044448170368f);
+        const float alA = fminf(a.gut.alphaClamp, respA * q1.w), alB = fminf(a.gut.alphaClamp, respB * q1.w);
+        const bool  inX = fabsf(__fsub_rn(-nfx, q0.x)) <= q0.z && !(q1.w <= a.gut.alphaCullThreshold);
+        const bool  inA = inX && fabsf(__fsub_rn(gutPyA, q0.y)) <= q0.w, inB = inX && fabsf(__fsub_rn(gutPyB, q0.y)) <= q0.w;
+        const float THR = 1.0f / 255.0f, MINR = a.gut.kernelMinResponse;
+        nOp[0] = (inA && alA > THR && respA > MINR) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
+        nOp[1] = (inB && alB > THR && respB > MINR) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
+        const bool nearA = inA && (fabsf(alA - THR) <= 2e-3f * THR || fabsf(respA - MINR) <= 2e-3f * MINR);
+        const bool nearB = inB && (fabsf(alB - THR) <= 2e-3f * THR || fabsf(respB - MINR) <= 2e-3f * MINR);
+        if(nearA || nearB)
+        {
+          if(nearA)
+            nOp[0] = exactPixel(0);
+          if(nearB)
+            nOp[1] = exactPixel(1);
+        }
       }
       f.n2 = pk(nOp[0], nOp[1]);
       return f;
