@@ -174,7 +174,7 @@ def test_tile_list_overflow_regrows(gpu_renderer):
 
 # ---- stand-alone radix sort (vrdx replacement) -------------------------------------------------------
 
-@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 8191, 100_003, 1_000_000])
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 8191, 8192, 8193, 16385, 100_003, 1_000_000])
 def test_sort_pairs_bit_exact(gpu_renderer, n):
     rng = np.random.default_rng(n + 1)
     keys = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)

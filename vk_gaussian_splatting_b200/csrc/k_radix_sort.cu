@@ -5,7 +5,7 @@
 // upsweep/spine/downsweep.slang). Same contract: ascending, stable, pair count read on the device.
 // vrdx is reduce-then-scan (3 dispatches and ~20 B/pair per pass). This is a single-pass
 // ("onesweep") design instead: the digit histograms of all passes are produced by whichever
-// kernel wrote the keys, and each pass is ONE kernel that ranks a 4096-pair partition in shared
+// kernel wrote the keys, and each pass is ONE kernel that ranks an 8192-pair partition in shared
 // memory, resolves its global digit offsets with a decoupled look-back over earlier partitions
 // (epoch-stamped 64-bit status words: nothing is cleared between passes or frames) and scatters
 // through shared memory so global writes leave in digit-contiguous runs. Traffic per pass is one
@@ -40,7 +40,7 @@ struct SortSmem
 static_assert(sizeof(uint32_t) * NWARPS * 256 <= sizeof(uint32_t) * SORT_PART, "warpHist must fit in the key staging area");
 
 template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS, 3) k_sort_pass(const __grid_constant__ SortPassArgs a)
+__global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_constant__ SortPassArgs a)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   SortSmem&      sm   = *reinterpret_cast<SortSmem*>(smemRaw);
