@@ -126,7 +126,9 @@ __device__ __forceinline__ void cpAsyncWaitAll()
 constexpr int      BLEND_WARPS = BLEND_THREADS / 32;
 constexpr int      EPT         = 1;                  // list entries gathered + classified per thread per round
 constexpr int      BATCH       = EPT * BLEND_THREADS;  // list entries staged per round
-static_assert(BLEND_WARPS == 4, "the tile is split into 2x2 warp blocks of 8x8 pixels");
+constexpr int      BLOCKS_X    = TILE_W / 8;  // the tile is split into BLOCKS_X x BLOCKS_Y warp blocks of 8x8 pixels
+constexpr int      BLOCKS_Y    = TILE_H / 8;
+static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && TILE_H % 8 == 0, "one warp per 8x8 pixel block");
 
 // One CTA (4 warps) per 16x16 tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
 // it (same column, rows ly and ly+4), evaluated together with packed fp32 instructions: the loads,
@@ -146,7 +148,7 @@ static_assert(BLEND_WARPS == 4, "the tile is split into 2x2 warp blocks of 8x8 p
 // the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
 // colour.
 template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT>
-__global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend(const __grid_constant__ BlendArgs a)
+__global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
 {
   // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
   constexpr uint32_t REC_BYTES = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend
   const uint32_t tile = blockIdx.x;
   const uint32_t tx = tile % a.tilesX, ty = tile / a.tilesX;
   const uint32_t tileX0 = tx * TILE_W, tileY0 = ty * TILE_H;
-  const uint32_t px = tileX0 + (warp & 1u) * 8u + (lane & 7u), pyA = tileY0 + (warp >> 1) * 8u + (lane >> 3), pyB = pyA + 4u;
+  const uint32_t px = tileX0 + (warp % BLOCKS_X) * 8u + (lane & 7u), pyA = tileY0 + (warp / BLOCKS_X) * 8u + (lane >> 3), pyB = pyA + 4u;
   const bool     insideA = px < a.width && pyA < a.height, insideB = px < a.width && pyB < a.height;
   const float    nfx = -(static_cast<float>(px) + 0.5f);
   const f32x2    nfy2 = pk(-(static_cast<float>(pyA) + 0.5f), -(static_cast<float>(pyB) + 0.5f));
@@ -244,9 +246,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend
       // [x0+0.5, x0+7.5] overlaps it iff |block centre - c| <= extent + 3.5 on both axes
       const float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * REC_BYTES);  // cx cy ex ey
 #pragma unroll
-      for(uint32_t b = 0; b < 4; b++)
+      for(uint32_t b = 0; b < BLEND_WARPS; b++)
       {
-        const float ddx = tileCx + static_cast<float>(8u * (b & 1u)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b >> 1)) - r0.y;
+        const float ddx = tileCx + static_cast<float>(8u * (b % BLOCKS_X)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b / BLOCKS_X)) - r0.y;
         if(fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + 3.501f)
           bits |= 1u << b;
       }
@@ -257,11 +259,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend
       const float4   r0 = ldsV4(src), r1 = ldsV4(src + 16), r2 = ldsV4(src + 32);
       const uint32_t bb0 = __float_as_uint(r2.z), bb1 = __float_as_uint(r2.w);
       const uint32_t x0 = bb0 & 0xffffu, y0 = bb0 >> 16, x1 = bb1 & 0xffffu, y1 = bb1 >> 16;
-      const uint32_t colL = (x0 <= tileX0 + 7u && x1 >= tileX0) ? 0x5u : 0u;        // warps 0,2
-      const uint32_t colR = (x0 <= tileX0 + 15u && x1 >= tileX0 + 8u) ? 0xau : 0u;  // warps 1,3
-      const uint32_t rowT = (y0 <= tileY0 + 7u && y1 >= tileY0) ? 0x3u : 0u;        // warps 0,1
-      const uint32_t rowB = (y0 <= tileY0 + 15u && y1 >= tileY0 + 8u) ? 0xcu : 0u;  // warps 2,3
-      bits                = (colL | colR) & (rowT | rowB);
+      // warp blocks whose 8x8 pixels the pixel bbox overlaps (bit b = block (b % BLOCKS_X, b / BLOCKS_X))
+#pragma unroll
+      for(uint32_t b = 0; b < BLEND_WARPS; b++)
+      {
+        const uint32_t bx = tileX0 + 8u * (b % BLOCKS_X), by = tileY0 + 8u * (b / BLOCKS_X);
+        if(x0 <= bx + 7u && x1 >= bx && y0 <= by + 7u && y1 >= by)
+          bits |= 1u << b;
+      }
       // Separating-axis test along the splat's own axes: over an 8x8 block of pixel centres (half
       // extents 3.5) the fragPos component f_i = dot(p - c, w_i) stays within f_i(centre) +- e_i, and
       // |f_i| > L everywhere means A > L^2 everywhere. A fragment survives only if A <= 8 and
@@ -275,18 +280,21 @@ __global__ void __launch_bounds__(BLEND_THREADS, (SURF || GUT) ? 6 : 10) k_blend
       }
       const float e1 = 3.5f * (fabsf(r0.z) + fabsf(r0.w)), e2 = 3.5f * (fabsf(r1.x) + fabsf(r1.y));
 #pragma unroll
-      for(uint32_t b = 0; b < 4; b++)
+      for(uint32_t b = 0; b < BLEND_WARPS; b++)
       {
-        const float ddx = tileCx + static_cast<float>(8u * (b & 1u)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b >> 1)) - r0.y;
+        const float ddx = tileCx + static_cast<float>(8u * (b % BLOCKS_X)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b / BLOCKS_X)) - r0.y;
         const float f1 = fabsf(ddx * r0.z + ddy * r0.w) - e1, f2 = fabsf(ddx * r1.x + ddy * r1.y) - e2;
         if(!(fmaxf(f1, f2) <= lim))
           bits &= ~(1u << b);
       }
     }
-    const unsigned m0 = __ballot_sync(FULL_MASK, bits & 1u), m1 = __ballot_sync(FULL_MASK, bits & 2u),
-                   m2 = __ballot_sync(FULL_MASK, bits & 4u), m3 = __ballot_sync(FULL_MASK, bits & 8u);
-    if(lane < 4)  // hit[buf][blend warp = lane][word = slot / 32]
-      stsU32(sbase + SMEM_HIT + ((buf * BLEND_WARPS + lane) * (BATCH / 32) + (slot >> 5)) * 4u, lane == 0 ? m0 : (lane == 1 ? m1 : (lane == 2 ? m2 : m3)));
+#pragma unroll
+    for(uint32_t b = 0; b < BLEND_WARPS; b++)
+    {
+      const unsigned mb = __ballot_sync(FULL_MASK, (bits >> b) & 1u);
+      if(lane == b)  // hit[buf][blend warp b][word = slot / 32]
+        stsU32(sbase + SMEM_HIT + ((buf * BLEND_WARPS + b) * (BATCH / 32) + (slot >> 5)) * 4u, mb);
+    }
   };
 
   // One list entry against this thread's two pixels, up to (not including) the ordered blend.

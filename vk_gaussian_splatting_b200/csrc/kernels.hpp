@@ -17,7 +17,7 @@ constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 8192 pairs p
 constexpr int      BIN_THREADS     = 256;
 constexpr int      TILE_W          = 16;
 constexpr int      TILE_H          = 16;
-constexpr int      BLEND_THREADS   = 128;    // 4 warps per 16x16 tile, two pixels per thread
+constexpr int      BLEND_THREADS   = TILE_W * TILE_H / 2;  // one warp per 8x8 pixel block of the tile, two pixels per thread
 
 // Small per-frame control block in HBM, cleared with one memset at the start of every frame.
 struct FrameCounters
