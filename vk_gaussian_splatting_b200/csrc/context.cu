@@ -21,6 +21,7 @@
 namespace vkgs {
 void initSortKernels();
 void initPreprocessKernels();
+void initBlendKernels();
 }  // namespace vkgs
 
 using namespace vkgs;
@@ -526,6 +527,7 @@ int vkgs_create(int device, vkgs_ctx** out)
   }
   initSortKernels();
   initPreprocessKernels();
+  initBlendKernels();
   if(!ok || cudaGetLastError() != cudaSuccess)
   {
     vkgs_destroy(c);

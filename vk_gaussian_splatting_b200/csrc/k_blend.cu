@@ -130,6 +130,12 @@ constexpr int      BLOCKS_X    = TILE_W / 8;  // the tile is split into BLOCKS_X
 constexpr int      BLOCKS_Y    = TILE_H / 8;
 static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && TILE_H % 8 == 0, "one warp per 8x8 pixel block");
 
+// dynamic shared memory of a blend CTA: records ring, hit masks, (surface info) normal + id rings
+__host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
+{
+  return 2u * BATCH * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u);
+}
+
 // One CTA (4 warps) per 16x16 tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
 // it (same column, rows ly and ly+4), evaluated together with packed fp32 instructions: the loads,
 // the loop control and the x-dependent products are shared by the pair and every FFMA2 retires two
@@ -156,7 +162,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   constexpr uint32_t SMEM_HIT  = 2 * SMEM_REC;       // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
   constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
   constexpr uint32_t SMEM_SID  = SMEM_SURF + 2 * BATCH * 16;
-  __shared__ __align__(16) unsigned char s_raw[SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF];
+  static_assert((SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF) == blendSmemBytes(SURF, GUT), "launch-side size");
+  extern __shared__ __align__(16) unsigned char s_raw[];
   const uint32_t sbase = smemBaseOpaque(s_raw);
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -669,6 +676,16 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
 
 }  // namespace
 
+void initBlendKernels()
+{
+  // the 3DGUT variant stages 96-byte records: above the 48 KB static limit for wide tiles
+  const int smem = static_cast<int>(blendSmemBytes(false, true));
+  cudaFuncSetAttribute(k_blend<true, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_blend<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_blend<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k_blend<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 void launchBlend(const BlendArgs& args, cudaStream_t stream)
 {
   const uint32_t tiles = args.tilesX * args.tilesY;
@@ -676,38 +693,41 @@ void launchBlend(const BlendArgs& args, cudaStream_t stream)
   if(args.outNormals)
   {
     // surface-info variant: front to back only (the context rejects other combinations)
+    constexpr uint32_t SMEM = blendSmemBytes(true, false);
     if(args.disableOpacityGaussian)
-      k_blend<true, true, false, true, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      k_blend<true, true, false, true, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
     else
-      k_blend<true, false, false, true, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+      k_blend<true, false, false, true, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
     return;
   }
   if(args.gut.enabled)
   {
     // VK3DGUT fragment stage (no fragment counters / surface info in this variant)
+    constexpr uint32_t SMEM = blendSmemBytes(false, true);
     if(args.frontToBack)
     {
       if(args.disableOpacityGaussian)
-        k_blend<true, true, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+        k_blend<true, true, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
       else
-        k_blend<true, false, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+        k_blend<true, false, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
     }
     else
     {
       if(args.disableOpacityGaussian)
-        k_blend<false, true, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+        k_blend<false, true, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
       else
-        k_blend<false, false, false, false, true><<<tiles, BLEND_THREADS, 0, stream>>>(args);
+        k_blend<false, false, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
     }
     return;
   }
+  constexpr uint32_t SMEM = blendSmemBytes(false, false);
 #define VKGS_BLEND_LAUNCH(F, G)                                                                                                  \
   do                                                                                                                             \
   {                                                                                                                              \
     if(count)                                                                                                                    \
-      k_blend<F, G, true, false, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                            \
+      k_blend<F, G, true, false, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                                            \
     else                                                                                                                         \
-      k_blend<F, G, false, false, false><<<tiles, BLEND_THREADS, 0, stream>>>(args);                                                           \
+      k_blend<F, G, false, false, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                                           \
   } while(0)
   if(args.frontToBack)
   {

@@ -15,7 +15,7 @@ constexpr int      SORT_THREADS    = 512;
 constexpr int      SORT_ITEMS      = 16;    // keys per thread
 constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 8192 pairs per partition (16 per thread: half the CTAs and look-back words of 8 per thread; measured +3.5 % fps)
 constexpr int      BIN_THREADS     = 256;
-constexpr int      TILE_W          = 16;
+constexpr int      TILE_W          = 32;
 constexpr int      TILE_H          = 16;
 constexpr int      BLEND_THREADS   = TILE_W * TILE_H / 2;  // one warp per 8x8 pixel block of the tile, two pixels per thread
 
