@@ -676,14 +676,23 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
 
 }  // namespace
 
+template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT>
+static void allowSmem()
+{
+  cudaFuncSetAttribute(k_blend<FTB, NOGAUSS, COUNT, SURF, GUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(blendSmemBytes(SURF, GUT)));
+}
+
 void initBlendKernels()
 {
-  // the 3DGUT variant stages 96-byte records: above the 48 KB static limit for wide tiles
-  const int smem = static_cast<int>(blendSmemBytes(false, true));
-  cudaFuncSetAttribute(k_blend<true, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_blend<true, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_blend<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  cudaFuncSetAttribute(k_blend<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  // dynamic shared memory above the 48 KB default (wide tiles, 96-byte 3DGUT records)
+  allowSmem<true, true, false, false, false>(), allowSmem<true, false, false, false, false>();
+  allowSmem<false, true, false, false, false>(), allowSmem<false, false, false, false, false>();
+  allowSmem<true, true, true, false, false>(), allowSmem<true, false, true, false, false>();
+  allowSmem<false, true, true, false, false>(), allowSmem<false, false, true, false, false>();
+  allowSmem<true, true, false, true, false>(), allowSmem<true, false, false, true, false>();
+  allowSmem<true, true, false, false, true>(), allowSmem<true, false, false, false, true>();
+  allowSmem<false, true, false, false, true>(), allowSmem<false, false, false, false, true>();
 }
 
 void launchBlend(const BlendArgs& args, cudaStream_t stream)
