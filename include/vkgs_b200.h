@@ -246,8 +246,8 @@ VKGS_API int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t widt
 VKGS_API void vkgs_default_camera(vkgs_camera* cam);
 /* Synchronous: returns after the frame (and the requested copies to host) completed. */
 VKGS_API int vkgs_render(vkgs_ctx* ctx, const vkgs_frame_params* fp, vkgs_outputs* out);
-/* Stream-ordered: enqueue one frame, result stays in the device framebuffer. Up to two frames are
- * in flight on two internal streams (the frames-in-flight of the reference's swapchain loop,
+/* Stream-ordered: enqueue one frame, result stays in the device framebuffer. Up to four frames are
+ * in flight, each on its own pair of internal streams (the frames-in-flight of the reference's swapchain loop,
  * nvpro_core2/nvapp/application.cpp:517-548); completion order == submission order. */
 VKGS_API int vkgs_render_async(vkgs_ctx* ctx, const vkgs_frame_params* fp);
 /* Same, plus an asynchronous copy of the finished RGBA frame (W*H*4 elements of the target
@@ -255,7 +255,7 @@ VKGS_API int vkgs_render_async(vkgs_ctx* ctx, const vkgs_frame_params* fp);
 VKGS_API int vkgs_render_to_host_async(vkgs_ctx* ctx, const vkgs_frame_params* fp, void* host_rgba);
 /* Change the colour target format (VKGS_FORMAT_*) for subsequent frames without re-uploading. */
 VKGS_API int vkgs_set_target_format(vkgs_ctx* ctx, uint32_t target_format);
-/* 1 = strictly one frame at a time, 2 (default) = overlap consecutive frames. */
+/* 1 = strictly one frame at a time (full-occupancy kernels, lowest latency), 2..4 (default 4) = overlap consecutive frames. */
 VKGS_API int vkgs_set_frames_in_flight(vkgs_ctx* ctx, int frames);
 VKGS_API int vkgs_sync(vkgs_ctx* ctx);
 /* Enable per-kernel cudaEvent timing for subsequent frames (off by default). */
