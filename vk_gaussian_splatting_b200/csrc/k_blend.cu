@@ -124,8 +124,10 @@ __device__ __forceinline__ void cpAsyncWaitAll()
 
 // record, 48 B: cx cy w1x w1y | w2x w2y r g | b a bbox bbox   (3DGUT: 96 B, see k_preprocess.cu)
 constexpr int      BLEND_WARPS = BLEND_THREADS / 32;
-constexpr int      EPT         = 1;                  // list entries gathered + classified per thread per round
-constexpr int      BATCH       = EPT * BLEND_THREADS;  // list entries staged per round
+constexpr int      BATCH       = 128;  // list entries staged per round, one per thread of the first BATCH/32 warps. Smaller than
+                                       // the CTA on purpose: with early termination most tiles finish inside their first
+                                       // batches, and whatever is classified beyond that point is wasted
+static_assert(BATCH % 32 == 0 && BATCH <= BLEND_THREADS, "whole staging warps");
 constexpr int      BLOCKS_X    = TILE_W / 8;  // the tile is split into BLOCKS_X x BLOCKS_Y warp blocks of 8x8 pixels
 constexpr int      BLOCKS_Y    = TILE_H / 8;
 static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && TILE_H % 8 == 0, "one warp per 8x8 pixel block");
@@ -524,20 +526,16 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   if(range.x < range.y)
   {
     // prologue: batch 0 lands and is classified; the list index of batch 1 is already on its way
-    uint32_t idNext[EPT];
+    const bool stager = tid < BATCH;  // (warp-uniform)
+    uint32_t   idNext = 0;
+    if(stager)
     {
-#pragma unroll
-      for(int e = 0; e < EPT; e++)
-        if(range.x + e * BLEND_THREADS + tid < range.y)
-          gather(a.tileVals[range.x + e * BLEND_THREADS + tid], 0, e * BLEND_THREADS + tid);
+      if(range.x + tid < range.y)
+        gather(a.tileVals[range.x + tid], 0, tid);
       cpAsyncCommit();
-#pragma unroll
-      for(int e = 0; e < EPT; e++)
-        idNext[e] = (range.x + BATCH + e * BLEND_THREADS + tid < range.y) ? a.tileVals[range.x + BATCH + e * BLEND_THREADS + tid] : 0u;
+      idNext = (range.x + BATCH + tid < range.y) ? a.tileVals[range.x + BATCH + tid] : 0u;
       cpAsyncWaitAll();
-#pragma unroll
-      for(int e = 0; e < EPT; e++)
-        classify(range.x + e * BLEND_THREADS + tid < range.y, 0, e * BLEND_THREADS + tid);
+      classify(range.x + tid < range.y, 0, tid);
     }
     __syncthreads();
     for(uint32_t base = range.x, buf = 0;; base += BATCH, buf ^= 1u)
@@ -546,15 +544,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       if(more)
       {
         // records of the next batch fly into the other buffer while this one is blended
-#pragma unroll
-        for(int e = 0; e < EPT; e++)
-          if(base + BATCH + e * BLEND_THREADS + tid < range.y)
-            gather(idNext[e], buf ^ 1u, e * BLEND_THREADS + tid);
-        cpAsyncCommit();
-#pragma unroll
-        for(int e = 0; e < EPT; e++)
-          if(base + 2 * BATCH + e * BLEND_THREADS + tid < range.y)
-            idNext[e] = a.tileVals[base + 2 * BATCH + e * BLEND_THREADS + tid];
+        if(stager)
+        {
+          if(base + BATCH + tid < range.y)
+            gather(idNext, buf ^ 1u, tid);
+          cpAsyncCommit();
+          if(base + 2 * BATCH + tid < range.y)
+            idNext = a.tileVals[base + 2 * BATCH + tid];
+        }
       }
 
       if(!warpDone)
@@ -605,12 +602,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
           }
         }
       }
-      if(more)
+      if(more && stager)
       {
         cpAsyncWaitAll();
-#pragma unroll
-        for(int e = 0; e < EPT; e++)
-          classify(base + BATCH + e * BLEND_THREADS + tid < range.y, buf ^ 1u, e * BLEND_THREADS + tid);
+        classify(base + BATCH + tid < range.y, buf ^ 1u, tid);
       }
       // one barrier per batch: publishes the next batch, retires this one, and votes on whether any
       // warp block of the tile still needs the rest of the list
