@@ -23,6 +23,7 @@ constexpr int BIN_WARPS    = BIN_THREADS / 32;
 constexpr int BIN_ITEMS = 4;                        // depth ranks per thread (one 16-byte id load)
 constexpr int BIN_PART  = BIN_THREADS * BIN_ITEMS;  // ranks per partition
 constexpr int BIN_CHUNK = 2048;                     // pairs staged in shared memory per round
+constexpr uint32_t BIN_BIG = 32;                    // splats covering more tiles than this are expanded warp-cooperatively
 
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant__ BinArgs a)
 {
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
     for(int i = 0; i < BIN_ITEMS; i++)
     {
       const uint32_t lo = max(off, w), hi = min(off + n[i], lim);
-      if(lo < hi)
+      const bool     big = n[i] > BIN_BIG;
+      if(lo < hi && !big)
       {
         const uint32_t j  = lo - off;
         uint32_t       ty = j / nx[i];
@@ -112,6 +114,23 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
           s_vals[p - w] = id[i];
           if(++tx == nx[i])
             tx = 0, ty++;
+        }
+      }
+      // a splat covering many tiles (close to the camera: up to the whole screen) is expanded by its
+      // whole warp, 32 pairs per step, instead of one thread walking thousands of tiles
+      unsigned bigMask = __ballot_sync(FULL_MASK, big && lo < hi);
+      while(bigMask)
+      {
+        const int src = __ffs(bigMask) - 1;
+        bigMask &= bigMask - 1;
+        const uint32_t bOff = __shfl_sync(FULL_MASK, off, src), bLo = __shfl_sync(FULL_MASK, lo, src), bHi = __shfl_sync(FULL_MASK, hi, src);
+        const uint32_t bNx = __shfl_sync(FULL_MASK, nx[i], src), bX0 = __shfl_sync(FULL_MASK, x0[i], src), bY0 = __shfl_sync(FULL_MASK, y0[i], src);
+        const uint32_t bId = __shfl_sync(FULL_MASK, id[i], src);
+        for(uint32_t p = bLo + lane; p < bHi; p += 32)
+        {
+          const uint32_t j = p - bOff, ty = j / bNx, tx = j - ty * bNx;
+          s_keys[p - w]    = (bY0 + ty) * a.tilesX + bX0 + tx;
+          s_vals[p - w]    = bId;
         }
       }
       off += n[i];
