@@ -28,6 +28,8 @@ using namespace vkgs;
 
 namespace {
 
+constexpr uint32_t BIG_LIST_CAPACITY = 1u << 16;  // huge splats per frame handed to k_bin_big (beyond: expanded in place)
+
 int fail(vkgs_ctx* ctx, int code, const char* msg)
 {
   if(ctx)
@@ -39,7 +41,7 @@ void freeSlotScene(FrameSlot& s)
 {
   for(int i = 0; i < 2; i++)
     freeDev(s.dKeys[i]), freeDev(s.dIds[i]), freeDev(s.dTileKeys[i]), freeDev(s.dTileVals[i]);
-  freeDev(s.dRecords), freeDev(s.dBboxes), freeDev(s.dSurface), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
+  freeDev(s.dRecords), freeDev(s.dBboxes), freeDev(s.dBigList), freeDev(s.dSurface), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
   s.tileCapacity = 0;
   s.haveFrame    = false;
 }
@@ -85,6 +87,7 @@ int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n, uint64_t preTiles)
   const uint64_t recordWords = c->opt.pipeline == VKGS_PIPELINE_3DGUT ? GUT_RECORD_WORDS : RECORD_WORDS;
   CU_TRY(c, cudaMalloc(&s.dRecords, n * recordWords * sizeof(uint32_t)));
   CU_TRY(c, cudaMalloc(&s.dBboxes, n * sizeof(uint2)));
+  CU_TRY(c, cudaMalloc(&s.dBigList, BIG_LIST_CAPACITY * sizeof(uint4)));
   if(c->opt.surface_info)
     CU_TRY(c, cudaMalloc(&s.dSurface, n * sizeof(float4)));
   const uint64_t binParts = (n + 255) / 256, sortParts = (n + SORT_PART - 1) / SORT_PART;
@@ -268,8 +271,11 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   ba.epoch      = nextEpoch(c);
   ba.ticketSlot = 5;
   ba.debugFlags = c->opt._reserved[0];
+  ba.bigList     = s.dBigList;
+  ba.bigCapacity = BIG_LIST_CAPACITY;
   launchBinEmit(ba, st);
-  c->launches++;
+  launchBinBig(ba, st);
+  c->launches += 2;
   mark(VKGS_K_BIN_EMIT + 1);
   mark(VKGS_K_TILE_HIST + 1);  // (tile-id digit histograms are fused into the emit kernel)
 

@@ -22,6 +22,7 @@ struct FrameSlot
   uint32_t *     dKeys[2] = {nullptr, nullptr}, *dIds[2] = {nullptr, nullptr};
   uint32_t*      dRecords    = nullptr;
   uint2*         dBboxes     = nullptr;
+  uint4*         dBigList    = nullptr;  // huge splats of the frame (k_bin_emit -> k_bin_big)
   float4*        dSurface    = nullptr;  // surface-info only: per-splat world normal + NDC depth
   float4*        dOutNormals = nullptr;  // surface-info only: side outputs of the frame
   float2*        dOutDepthT  = nullptr;

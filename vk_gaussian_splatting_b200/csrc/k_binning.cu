@@ -24,6 +24,7 @@ constexpr int BIN_ITEMS = 4;                        // depth ranks per thread (o
 constexpr int BIN_PART  = BIN_THREADS * BIN_ITEMS;  // ranks per partition
 constexpr int BIN_CHUNK = 2048;                     // pairs staged in shared memory per round
 constexpr uint32_t BIN_BIG = 32;                    // splats covering more tiles than this are expanded warp-cooperatively
+constexpr uint32_t BIN_HUGE = 256;                  // ... and more than this by a whole CTA of k_bin_big (see below)
 
 __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant__ BinArgs a)
 {
@@ -88,7 +89,98 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
   if(tid == 0)
     lb_store(a.status + part, lb_pack(a.epoch, part == 0 ? LB_INCLUSIVE : LB_AGGREGATE, total));
 
-  // ... then emit through shared memory so global writes are fully coalesced: every round stages up
+  // resolve the exclusive prefix of the pair counts (warp 0 only; result in s_base after the next barrier)
+  auto resolvePrefix = [&]() {
+    uint32_t excl = 0;
+    if(part != 0)
+    {
+      if(a.debugFlags & 32u)
+      {
+        if(tid == 0)
+          excl = atomicAdd(&a.counters->tilePairs, total);
+        excl = __shfl_sync(FULL_MASK, excl, 0);
+      }
+      else
+        excl = lb_lookback_warp<4>(a.status, part, a.epoch);
+      if(tid == 0)
+        lb_store(a.status + part, lb_pack(a.epoch, LB_INCLUSIVE, excl + total));
+    }
+    if(tid == 0)
+    {
+      s_base = excl;
+      if(part == parts - 1)
+      {
+        const uint32_t d             = excl + total;
+        a.counters->tilePairs        = d;
+        a.counters->tilePairsClamped = d < a.capacity ? d : a.capacity;
+        if(d > a.capacity)
+          a.counters->overflow = 1u;
+      }
+    }
+  };
+
+  // Partitions holding HUGE splats (camera close to / inside the scene: a splat can cover the whole screen,
+  // and depth order puts all of them into the same few partitions) take a different route: no staging rounds;
+  // huge splats are handed to k_bin_big with their absolute output offset (a whole CTA expands each), the rest
+  // is written straight to its final position. Rare, so the common path below stays as it is.
+  bool hasHuge = false;
+#pragma unroll
+  for(int i = 0; i < BIN_ITEMS; i++)
+    hasHuge = hasHuge || n[i] > BIN_HUGE;
+  if(__syncthreads_or(hasHuge))
+  {
+    if(tid < 32)
+      resolvePrefix();
+    __syncthreads();
+    const uint32_t base = s_base;
+    uint32_t       off  = local;
+#pragma unroll
+    for(int i = 0; i < BIN_ITEMS; i++)
+    {
+      const uint64_t g0 = static_cast<uint64_t>(base) + off;
+      if(n[i] > BIN_HUGE)
+      {
+        const uint32_t slot = atomicAdd(&a.counters->bigCount, 1u);
+        if(slot < a.bigCapacity && g0 + n[i] <= 0xffffffffull)
+          a.bigList[slot] = make_uint4(static_cast<uint32_t>(g0), id[i], x0[i] | (y0[i] << 16), nx[i] | ((n[i] / nx[i]) << 16));
+        else
+        {
+          // list full: expand it here after all (slow, still correct)
+          for(uint32_t j = 0; j < n[i]; j++)
+            if(g0 + j < a.capacity)
+            {
+              const uint32_t key = (y0[i] + j / nx[i]) * a.tilesX + x0[i] + j % nx[i];
+              a.tileKeys[g0 + j] = key, a.tileVals[g0 + j] = id[i];
+              atomicAdd(&s_whist[lane & (BIN_WARPS - 1)][0][key & 0xffu], 1u);
+              atomicAdd(&s_whist[lane & (BIN_WARPS - 1)][1][(key >> 8) & 0xffu], 1u);
+            }
+        }
+      }
+      // everything else: by the owning warp, 32 pairs per step
+      unsigned mask = __ballot_sync(FULL_MASK, n[i] != 0u && n[i] <= BIN_HUGE);
+      while(mask)
+      {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint64_t bG0 = __shfl_sync(FULL_MASK, g0, src);
+        const uint32_t bN = __shfl_sync(FULL_MASK, n[i], src), bNx = __shfl_sync(FULL_MASK, nx[i], src);
+        const uint32_t bX0 = __shfl_sync(FULL_MASK, x0[i], src), bY0 = __shfl_sync(FULL_MASK, y0[i], src), bId = __shfl_sync(FULL_MASK, id[i], src);
+        for(uint32_t j = lane; j < bN; j += 32)
+          if(bG0 + j < a.capacity)
+          {
+            const uint32_t ty = j / bNx, tx = j - ty * bNx, key = (bY0 + ty) * a.tilesX + bX0 + tx;
+            a.tileKeys[bG0 + j] = key, a.tileVals[bG0 + j] = bId;
+            atomicAdd(&s_whist[lane & (BIN_WARPS - 1)][0][key & 0xffu], 1u);
+            atomicAdd(&s_whist[lane & (BIN_WARPS - 1)][1][(key >> 8) & 0xffu], 1u);
+          }
+      }
+      off += n[i];
+    }
+    __syncthreads();
+  }
+  else
+  {
+  // ... emit through shared memory so global writes are fully coalesced: every round stages up
   // to BIN_CHUNK pairs of the block's contiguous output range and drains them row by row (the drain
   // also counts the two 8-bit digits of each tile id). The first round is staged BEFORE the
   // look-back is resolved: it only needs block-local offsets, and by the time it is done the
@@ -139,34 +231,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
     {
       // resolve the exclusive prefix of the pair counts (warp 0), everybody else is still staging
       if(tid < 32)
-      {
-        uint32_t excl = 0;
-        if(part != 0)
-        {
-          if(a.debugFlags & 32u)
-          {
-            if(tid == 0)
-              excl = atomicAdd(&a.counters->tilePairs, total);
-            excl = __shfl_sync(FULL_MASK, excl, 0);
-          }
-          else
-            excl = lb_lookback_warp<4>(a.status, part, a.epoch);
-          if(tid == 0)
-            lb_store(a.status + part, lb_pack(a.epoch, LB_INCLUSIVE, excl + total));
-        }
-        if(tid == 0)
-        {
-          s_base = excl;
-          if(part == parts - 1)
-          {
-            const uint32_t d             = excl + total;
-            a.counters->tilePairs        = d;
-            a.counters->tilePairsClamped = d < a.capacity ? d : a.capacity;
-            if(d > a.capacity)
-              a.counters->overflow = 1u;
-          }
-        }
-      }
+        resolvePrefix();
     }
     __syncthreads();
     if(w == 0)
@@ -195,6 +260,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
     }
     __syncthreads();
   }
+  }  // common path
   VKGS_TL(part, 4);
   for(int i = tid; i < 2 * 256; i += BIN_THREADS)
   {
@@ -207,7 +273,54 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
   }
 }
 
+// Huge splats handed over by k_bin_emit: entry = (absolute output offset, splat id, x0 | y0 << 16, nx | ny << 16) in
+// tiles. One CTA per entry (grid-strided) writes its nx * ny (tile id, splat id) pairs, coalesced, and counts
+// their digits for the tile sort.
+__global__ void __launch_bounds__(BIN_THREADS) k_bin_big(const __grid_constant__ BinArgs a)
+{
+  __shared__ uint32_t s_whist[BIN_WARPS][2][256];
+  const unsigned      tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t      count = min(a.counters->bigCount, a.bigCapacity);
+  if(blockIdx.x >= count)
+    return;
+  for(int i = tid; i < BIN_WARPS * 2 * 256; i += BIN_THREADS)
+    (&s_whist[0][0][0])[i] = 0u;
+  __syncthreads();
+  for(uint32_t e = blockIdx.x; e < count; e += gridDim.x)
+  {
+    const uint4    it = a.bigList[e];
+    const uint32_t x0 = it.z & 0xffffu, y0 = it.z >> 16, nx = it.w & 0xffffu, n = nx * (it.w >> 16);
+    for(uint32_t j = tid; j < n; j += BIN_THREADS)
+    {
+      const uint64_t g = static_cast<uint64_t>(it.x) + j;
+      if(g < a.capacity)
+      {
+        const uint32_t ty = j / nx, tx = j - ty * nx, key = (y0 + ty) * a.tilesX + x0 + tx;
+        a.tileKeys[g] = key, a.tileVals[g] = it.y;
+        atomicAdd(&s_whist[lane & (BIN_WARPS - 1)][0][key & 0xffu], 1u);
+        atomicAdd(&s_whist[lane & (BIN_WARPS - 1)][1][(key >> 8) & 0xffu], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for(int i = tid; i < 2 * 256; i += BIN_THREADS)
+  {
+    uint32_t v = 0;
+#pragma unroll
+    for(int wv = 0; wv < BIN_WARPS; wv++)
+      v += (&s_whist[wv][0][0])[i];
+    if(v)
+      atomicAdd(&a.counters->tileHist[0][0] + i, v);
+  }
+}
+
 }  // namespace
+
+void launchBinBig(const BinArgs& args, cudaStream_t stream)
+{
+  // (launched every frame: the list length is only known on the device; CTAs beyond it exit at once)
+  k_bin_big<<<148 * 2, BIN_THREADS, 0, stream>>>(args);
+}
 
 void launchBinEmit(const BinArgs& args, cudaStream_t stream)
 {

@@ -31,6 +31,7 @@ struct FrameCounters
   unsigned long long fragments[2];  // profiling only (vkgs_options._reserved[0] & 128): list entries evaluated by a
                                     // warp block (x64 pixels), and fragments that passed both discards and were blended
   uint32_t ticket[12];         // dynamic tile / partition tickets, one per kernel launch
+  uint32_t bigCount;           // huge splats handed from k_bin_emit to k_bin_big this frame
   uint32_t depthHist[4][256];  // digit histograms of the depth keys (filled by the preprocess kernel)
   uint32_t tileHist[2][256];   // digit histograms of the tile ids (filled by the binning kernel)
 };
@@ -131,9 +132,12 @@ struct BinArgs
   uint32_t        epoch;
   uint32_t        ticketSlot;
   uint32_t        debugFlags;  // profiling ablations (0 in production)
+  uint4*          bigList;     // [bigCapacity] huge splats: (output offset, splat id, x0 | y0 << 16, nx | ny << 16)
+  uint32_t        bigCapacity;
 };
 
 void launchBinEmit(const BinArgs& args, cudaStream_t stream);
+void launchBinBig(const BinArgs& args, cudaStream_t stream);  // expands the huge splats k_bin_emit set aside
 
 
 // per-frame constants of the VK3DGUT fragment stage (FrameInfo + SplatSetDesc fields it reads)
