@@ -284,6 +284,8 @@ def main():
     # headline e2e: the reference's default colour target (COLOR_MAIN = R16G16B16A16_SFLOAT); fp32 target alongside
     fps_e2e, ms_e2e_step, e2e_steps, d2h_bytes = e2e_run(A.FORMAT_FLOAT16, torch.float16)
     fps_e2e32, ms_e2e32_step, _, d2h_bytes32 = e2e_run(A.FORMAT_FLOAT32, torch.float32)
+    fps_e2e8, ms_e2e8_step, _, d2h_bytes8 = e2e_run(A.FORMAT_UINT8, torch.uint8)
+    r.set_target_format(A.FORMAT_FLOAT32)
 
     # ---- per-kernel profile (separate frames, cudaEvents around every launch on the launch stream) --
     r.set_frames_in_flight(1)  # per-kernel times need one frame at a time (no cross-frame overlap)
@@ -347,9 +349,11 @@ def main():
                                "note": "the blend stage is bounded by fp32 issue: its natural unit is fragments/s (BASELINE.md 3)"},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": C.sizeof(A.FrameParams),
-                    "d2h_bytes_per_step": d2h_bytes + 32, "steps": e2e_steps, "ms_per_step": ms_e2e_step,
+                    "d2h_bytes_per_step": d2h_bytes + 48, "steps": e2e_steps, "ms_per_step": ms_e2e_step,
                     "target": "RGBA16F (reference default COLOR_MAIN format), pinned host buffer, 2 frames in flight",
-                    "fp32_target": {"value": fps_e2e32, "ms_per_step": ms_e2e32_step, "d2h_bytes_per_step": d2h_bytes32 + 32}},
+                    "note": "PCIe-bound: d2h_bytes_per_step x value is the host link bandwidth; the other target formats show it",
+                    "fp32_target": {"value": fps_e2e32, "ms_per_step": ms_e2e32_step, "d2h_bytes_per_step": d2h_bytes32 + 48},
+                    "rgba8_target": {"value": fps_e2e8, "ms_per_step": ms_e2e8_step, "d2h_bytes_per_step": d2h_bytes8 + 48}},
         }
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_sorter_baseline(scene, cam)
