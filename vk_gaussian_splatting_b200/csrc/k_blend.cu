@@ -129,8 +129,9 @@ constexpr int      BATCH       = 128;  // list entries staged per round, one per
                                        // batches, and whatever is classified beyond that point is wasted
 static_assert(BATCH % 32 == 0 && BATCH <= BLEND_THREADS, "whole staging warps");
 constexpr int      BLOCKS_X    = TILE_W / 8;  // the tile is split into BLOCKS_X x BLOCKS_Y warp blocks of 8x8 pixels
-constexpr int      BLOCKS_Y    = TILE_H / 8;
-static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && TILE_H % 8 == 0, "one warp per 8x8 pixel block");
+constexpr int      BLOCKS_Y    = BLEND_H / 8;
+constexpr int      BANDS       = TILE_H / BLEND_H;  // CTAs per tile (consecutive block indices: they share the list in L2)
+static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && BLEND_H % 8 == 0 && TILE_H % BLEND_H == 0, "one warp per 8x8 pixel block");
 
 // dynamic shared memory of a blend CTA: records ring, hit masks, (surface info) normal + id rings
 __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
@@ -169,9 +170,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   const uint32_t sbase = smemBaseOpaque(s_raw);
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tile = blockIdx.x / BANDS, band = blockIdx.x % BANDS;
   const uint32_t tx = tile % a.tilesX, ty = tile / a.tilesX;
-  const uint32_t tileX0 = tx * TILE_W, tileY0 = ty * TILE_H;
+  const uint32_t tileX0 = tx * TILE_W, tileY0 = ty * TILE_H + band * BLEND_H;  // origin of this CTA's band
   const uint32_t px = tileX0 + (warp % BLOCKS_X) * 8u + (lane & 7u), pyA = tileY0 + (warp / BLOCKS_X) * 8u + (lane >> 3), pyB = pyA + 4u;
   const bool     insideA = px < a.width && pyA < a.height, insideB = px < a.width && pyB < a.height;
   const float    nfx = -(static_cast<float>(px) + 0.5f);
@@ -692,7 +693,7 @@ void initBlendKernels()
 
 void launchBlend(const BlendArgs& args, cudaStream_t stream)
 {
-  const uint32_t tiles = args.tilesX * args.tilesY;
+  const uint32_t tiles = args.tilesX * args.tilesY * BANDS;  // CTAs
   const bool count = args.fragmentCounters != nullptr;
   if(args.outNormals)
   {

@@ -16,8 +16,9 @@ constexpr int      SORT_ITEMS      = 16;    // keys per thread
 constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 8192 pairs per partition (16 per thread: half the CTAs and look-back words of 8 per thread; measured +3.5 % fps)
 constexpr int      BIN_THREADS     = 256;
 constexpr int      TILE_W          = 32;
-constexpr int      TILE_H          = 16;
-constexpr int      BLEND_THREADS   = TILE_W * TILE_H / 2;  // one warp per 8x8 pixel block of the tile, two pixels per thread
+constexpr int      TILE_H          = 32;    // binning / tile-sort granularity: 32x32 pixels (fewest (tile, splat) pairs) ...
+constexpr int      BLEND_H         = 16;    // ... blended by TILE_H / BLEND_H CTAs per tile, each a 32x16 band reading the same list
+constexpr int      BLEND_THREADS   = TILE_W * BLEND_H / 2;  // one warp per 8x8 pixel block of the band, two pixels per thread
 
 // Small per-frame control block in HBM, cleared with one memset at the start of every frame.
 struct FrameCounters
