@@ -9,7 +9,7 @@ python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ --launch-skip 18 --launch-count 9 -f -o gpurun_out/${tag}_full \
+ncu --set full --clock-control none --import-source on -k regex:k_ --launch-skip 20 --launch-count 10 -f -o gpurun_out/${tag}_full \
     python tools/prof_preprocess.py > gpurun_out/${tag}_ncu_full.log 2>&1
 python tools/bench_configs.py 2 3 5 sort > gpurun_out/${tag}_configs.jsonl 2>&1
 tail -3 gpurun_out/${tag}_tests.log; cat gpurun_out/${tag}_smoke.log; cat gpurun_out/${tag}_bench.json
