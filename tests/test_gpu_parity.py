@@ -539,7 +539,12 @@ def _compare_gut_frame(r, s, cam, w, h, **optkw):
     d = np.abs(img - oimg)
     if not optkw.get("front_to_back"):
         d[..., 3] /= np.maximum(1.0, np.abs(oimg[..., 3]))
-    assert d.max() <= RGBA_TOL, f"max abs diff {d.max()}"
+    # The particle response is ill-conditioned in the length of the canonical ray origin |ro| = |camera - centre| / scale
+    # (cross(rd, ro) cancels): two fp32 evaluation orders — the oracle's, the CUDA fast path's, or a Vulkan compiler's FMA
+    # contraction of the reference shader — differ by about 2^-24 |ro| in alpha. Accept / reject decisions stay exact.
+    ro_max = float((np.linalg.norm(s.positions - np.array(cam.eye, np.float32), axis=1) / np.exp(s.scale.min(axis=1))).max())
+    tol = RGBA_TOL + 4e-8 * ro_max
+    assert d.max() <= tol, f"max abs diff {d.max()} (tolerance {tol}, |ro| up to {ro_max:.0f})"
     return img, oimg, st, quads
 
 
@@ -560,6 +565,10 @@ def test_3dgut_pipeline_matches_oracle(gpu_renderer):
     _compare_gut_frame(r, s, g.orbit_camera(3, 8), 400, 300, front_to_back=1, disable_opacity_gaussian=1)
     # a larger frame: millions of fragments, so the guard bands around the two discard thresholds get exercised
     _compare_gut_frame(r, g.synth_scene(120_000, 3, 0x3D650103), g.orbit_camera(5, 8), 960, 540, front_to_back=1)
+    # tiny splats: canonical ray origins tens of thousands of units long (the fast path's guard band scales with |ro|)
+    tiny = g.synth_scene(30_000, 0, 0x3D650104)
+    tiny.scale -= np.float32(3.0)
+    _compare_gut_frame(r, tiny, cam, 320, 200, front_to_back=1)
     # not the same estimator as the 3DGS pipeline, but the same picture
     r.upload(s, g.default_options(front_to_back=1))
     img3, _, _, _ = r.render(g.frame_params(cam, 480, 270))

@@ -389,9 +389,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         // Fast path of the default (quadratic = Gaussian) kernel, both pixels with packed fp32:
         // dist = |rd x ro|^2 / |rd|^2 without normalising rd first, reciprocal and exp on the SFU. Within
         // The canonical origin is hundreds of units long (distance / scale), so the cross product cancels and the
-        // two evaluation orders differ by up to ~1e-4 relative in dist; a pixel whose alpha or response lands
-        // within 2e-3 (relative) of its discard threshold is re-evaluated exactly, so accept / reject decisions
-        // never differ from the oracle.
+        // two evaluation orders differ by about 2^-24 |ro| sqrt(dist) relative in the response; a pixel whose
+        // alpha or response lands within 2e-3 + 4e-7 |ro| (relative) of its discard threshold is re-evaluated
+        // exactly, so accept / reject decisions never differ from the oracle.
+        const float band = 2e-3f + 4e-7f * q2.w;
         const f32x2 m0 = pk(gutDirA[0], gutDirB[0]), m1 = pk(gutDirA[1], gutDirB[1]), m2 = pk(gutDirA[2], gutDirB[2]);
         const f32x2 r0 = mul2(fma2(m2, pk(q5.y, q5.y), fma2(m1, pk(q4.z, q4.z), mul2(m0, pk(q3.w, q3.w)))), pk(q3.x, q3.x));
         const f32x2 r1 = mul2(fma2(m2, pk(q5.z, q5.z), fma2(m1, pk(q4.w, q4.w), mul2(m0, pk(q4.x, q4.x)))), pk(q3.y, q3.y));
@@ -413,8 +414,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         const float THR = 1.0f / 255.0f, MINR = a.gut.kernelMinResponse;
         nOp[0] = (inA && alA > THR && respA > MINR) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
         nOp[1] = (inB && alB > THR && respB > MINR) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
-        const bool nearA = inA && (fabsf(alA - THR) <= 2e-3f * THR || fabsf(respA - MINR) <= 2e-3f * MINR);
-        const bool nearB = inB && (fabsf(alB - THR) <= 2e-3f * THR || fabsf(respB - MINR) <= 2e-3f * MINR);
+        const bool nearA = inA && (fabsf(alA - THR) <= band * THR || fabsf(respA - MINR) <= band * MINR);
+        const bool nearB = inB && (fabsf(alB - THR) <= band * THR || fabsf(respB - MINR) <= band * MINR);
         if(nearA || nearB)
         {
           if(nearA)

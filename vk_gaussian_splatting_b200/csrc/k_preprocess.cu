@@ -153,7 +153,7 @@ __device__ __forceinline__ int gutProjectPoint(const float world[3], const vkgs_
 }
 
 // Unscented-transform projection + conic extent of one splat. Writes the 24-word 3DGUT record
-//   cx cy ex ey | r g b a | ro.xyz - | 1/scale.xyz R00 | R01 R02 R10 R11 | R12 R20 R21 R22
+//   cx cy ex ey | r g b a | ro.xyz |ro| | 1/scale.xyz R00 | R01 R02 R10 R11 | R12 R20 R21 R22
 // (R = inverse rotation, ro = canonical ray origin: the ray origin is the camera for every pixel, so
 // particleCannonicalRay's origin half is evaluated once per splat) and returns the pixel bounding box.
 __device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const float c[4], const float4 rq, const float* scaleLog,
@@ -244,7 +244,8 @@ __device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const f
     ro[j] = giscl[j] * ((gposc[0] * rot[j][0] + gposc[1] * rot[j][1]) + gposc[2] * rot[j][2]);
   rec[0] = make_float4(pc[0], pc[1], ex, ey);
   rec[1] = col;
-  rec[2] = make_float4(ro[0], ro[1], ro[2], 0.0f);
+  // (w: length of the canonical origin — the blend's fast path scales its guard band with it, see k_blend.cu)
+  rec[2] = make_float4(ro[0], ro[1], ro[2], sqrtf((ro[0] * ro[0] + ro[1] * ro[1]) + ro[2] * ro[2]));
   rec[3] = make_float4(giscl[0], giscl[1], giscl[2], rot[0][0]);        // invRot row 0 = (rot[0][0], rot[1][0], rot[2][0])
   rec[4] = make_float4(rot[1][0], rot[2][0], rot[0][1], rot[1][1]);      // invRot[0][1..2], invRot[1][0..1]
   rec[5] = make_float4(rot[2][1], rot[0][2], rot[1][2], rot[2][2]);      // invRot[1][2], invRot[2][0..2]
