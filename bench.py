@@ -272,7 +272,7 @@ def main():
         e0.record(stream)
         for i in range(steps):
             # the call a user makes: host frame parameters in, finished RGBA frame copied to pinned host
-            # memory out, every step; two frames in flight so step i's copy overlaps step i+1's kernels
+            # memory out, every step; several frames in flight so step i's copy overlaps step i+1's kernels
             r.render_to_host_async(fp, host_np[i % 2])
         e1.record(stream)
         r.sync()
@@ -350,7 +350,7 @@ def main():
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": C.sizeof(A.FrameParams),
                     "d2h_bytes_per_step": d2h_bytes + 48, "steps": e2e_steps, "ms_per_step": ms_e2e_step,
-                    "target": "RGBA16F (reference default COLOR_MAIN format), pinned host buffer, 2 frames in flight",
+                    "target": "RGBA16F (reference default COLOR_MAIN format), pinned host buffer, 4 frames in flight",
                     "note": "PCIe-bound: d2h_bytes_per_step x value is the host link bandwidth; the other target formats show it",
                     "fp32_target": {"value": fps_e2e32, "ms_per_step": ms_e2e32_step, "d2h_bytes_per_step": d2h_bytes32 + 48},
                     "rgba8_target": {"value": fps_e2e8, "ms_per_step": ms_e2e8_step, "d2h_bytes_per_step": d2h_bytes8 + 48}},

@@ -4,10 +4,11 @@
 // (src/gaussian_splatting.cpp:1298-1367, 1369-1465) as a fixed sequence of stream-ordered launches
 // with every data-dependent size (V, tile-pair count) read on the device — no host round trip
 // inside a frame:
-//   memset(control block) -> preprocess -> <=4 x sort pass -> bin emit -> 2 x tile sort pass
-//   (the second also records the per-tile list ranges) -> blend
-// Up to two frames are in flight on two internal streams (FrameSlot), so one frame's latency-bound
-// front end overlaps the previous frame's blend.
+//   memset(control block) -> preprocess (one launch per splat-set instance) -> <=4 x sort pass ->
+//   bin emit -> bin big -> 2 x tile sort pass (the second also records the per-tile list ranges) -> blend
+// Up to four frames are in flight (FrameSlot), each with a high-priority stream for its front end and
+// a low-priority one for the blend + copy to host, so a frame's latency-bound front end runs beside
+// the previous frames' blends.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

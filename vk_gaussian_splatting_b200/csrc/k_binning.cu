@@ -5,7 +5,7 @@
 // primitive order. The CUDA rasterizer reproduces that order per pixel with per-tile lists:
 //   k_bin_emit   walks the depth-sorted ids in order, looks up each splat's pixel bounding box
 //                (written by the preprocess kernel), and appends one (tile id, splat id) pair per
-//                covered 16x16 tile at an offset given by a decoupled look-back prefix sum — so
+//                covered TILE_W x TILE_H tile at an offset given by a decoupled look-back prefix sum — so
 //                pairs are emitted in depth order;
 //   a stable 2-pass (16-bit) radix sort on the tile id (k_radix_sort.cu) groups them per tile and
 //                keeps the depth order inside every tile;

@@ -6,12 +6,13 @@
 //   src/gaussian_splatting.cpp:2066-2087 blend state: back-to-front "over" with additive alpha, or
 //                                       front-to-back "under" with premultiplied colour
 //   colour target cleared to 0 (src/gaussian_splatting.cpp:582), fp32 RGBA here.
-// One CTA per 16x16 tile, one thread per pixel, a warp covers an 8x4 pixel block. The tile's
-// depth-ordered splat list is consumed in batches of 256: each thread gathers one 48-byte record
-// (prefetched into registers one batch ahead), computes which of the 8 warp blocks the splat's
-// pixel bounding box touches, and parks both in shared memory; every warp then ballots the batch
-// 32 entries at a time and evaluates only the splats that touch its block, in list order — the
-// per-pixel blend order is exactly the sorted order, like the ROP.
+// Binning tiles are 32x32 pixels; each is blended by TILE_H / BLEND_H CTAs (32x16 bands) that read the
+// tile's depth-ordered splat list; a warp owns an 8x8 pixel block and every thread two pixels of it
+// (packed fp32). The list is consumed in batches of 128 through a shared ring filled with cp.async
+// gathers of the 48-byte records; the gathering thread classifies its entry against the CTA's warp
+// blocks and every warp then evaluates only the entries that can touch its block, in list order — the
+// per-pixel blend order is exactly the sorted order, like the ROP. Variants (template flags): fragment
+// counters (profiling), the surface-info side outputs, and the VK3DGUT fragment stage.
 //
 // Exactness: fragPos / A are evaluated with explicit fp32 mul/fma in the oracle's operation order,
 // so the `A > 8` discard is bit-exact. opacity uses the SFU ex2 for speed; whenever that value is
@@ -139,7 +140,7 @@ __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
   return 2u * BATCH * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u);
 }
 
-// One CTA (4 warps) per 16x16 tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
+// One CTA (BLEND_WARPS warps) per band of a tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
 // it (same column, rows ly and ly+4), evaluated together with packed fp32 instructions: the loads,
 // the loop control and the x-dependent products are shared by the pair and every FFMA2 retires two
 // IEEE-rounded results in one issue slot (the kernel is issue/latency bound, not FMA-pipe bound).
