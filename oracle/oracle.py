@@ -33,7 +33,7 @@ QUAD_DTYPE = np.dtype([("center", "<f4", 2), ("basis1", "<f4", 2), ("basis2", "<
 
 class OrcSet(C.Structure):
     _fields_ = [("centers", f32p), ("cov6", f32p), ("rgba", f32p), ("sh45", f32p), ("scale_log", f32p), ("n", C.c_uint64),
-                ("sh_degree", C.c_uint32), ("_pad", C.c_uint32)]
+                ("sh_degree", C.c_uint32), ("_pad", C.c_uint32), ("rotation_wxyz", f32p)]
 
 
 class OrcInstance(C.Structure):
@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
         l.orc_render_scene.argtypes = [C.POINTER(OrcSet), C.c_uint32, C.POINTER(OrcInstance), C.c_uint32,
                                        C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p, u32p, u32p]
         l.orc_render_scene.restype = C.c_uint32
+        l.orc_render_gut_scene.argtypes = l.orc_render_scene.argtypes
+        l.orc_render_gut_scene.restype = C.c_uint32
         l.orc_render_gut.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams),
                                      C.POINTER(A.Options), f32p, u32p, u32p, C.c_void_p]
         l.orc_render_gut.restype = C.c_uint32
@@ -170,11 +172,15 @@ def render(packed: Packed, fp, opt, want_quads=False):
     return img, keys[:v].copy(), ids[:v].copy(), quads
 
 
-def render_scene(packed_sets, instances, fp, opt):
+def render_scene(packed_sets, instances, fp, opt, rotations=None):
     """Multi-instance oracle frame. `instances`: list of (set_index, transform[4,4], transform_inverse[4,4]) in glm
-    column-major memory order. Returns (image, sorted_keys, sorted_global_ids)."""
+    column-major memory order. Returns (image, sorted_keys, sorted_global_ids). With `rotations` (one [N,4] wxyz array
+    per set) and opt.pipeline == 3DGUT the VK3DGUT pipeline renders the scene."""
     sets = (OrcSet * len(packed_sets))()
+    keep = [np.ascontiguousarray(r, np.float32) for r in rotations] if rotations is not None else None
     for i, p in enumerate(packed_sets):
+        if keep is not None:
+            sets[i].rotation_wxyz = _p(keep[i])
         sets[i].centers, sets[i].cov6, sets[i].rgba, sets[i].sh45, sets[i].scale_log = _p(p.centers), _p(p.cov6), _p(p.rgba), _p(p.sh), _p(p.scale)
         sets[i].n, sets[i].sh_degree = p.n, p.sh_degree
     inst = (OrcInstance * len(instances))()
@@ -187,7 +193,8 @@ def render_scene(packed_sets, instances, fp, opt):
     img = np.zeros((fp.height, fp.width, 4), np.float32)
     keys = np.empty(total, np.uint32)
     ids = np.empty(total, np.uint32)
-    v = lib().orc_render_scene(sets, len(packed_sets), inst, len(instances), C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids))
+    fn = lib().orc_render_gut_scene if (keep is not None and opt.pipeline == A.PIPELINE_3DGUT) else lib().orc_render_scene
+    v = fn(sets, len(packed_sets), inst, len(instances), C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids))
     return img, keys[:v].copy(), ids[:v].copy()
 
 

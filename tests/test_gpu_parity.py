@@ -578,3 +578,21 @@ def test_3dgut_pipeline_matches_oracle(gpu_renderer):
     for kw in (dict(extent_projection=A.EXTENT_EIGEN), dict(surface_info=1, front_to_back=1)):
         with pytest.raises(g.VkgsError):
             r.upload(s, g.default_options(pipeline=A.PIPELINE_3DGUT, **kw))
+
+
+def test_3dgut_multi_instance_scene_matches_oracle(gpu_renderer):
+    """VK3DGUT with several splat-set instances: the fragment stage takes its rays into the model space of the
+    entry's instance (threedgut_raster.frag.slang:112-121)."""
+    r = gpu_renderer
+    a, b = g.synth_scene(20_011, 3, 0x3D650111), g.synth_scene(6_007, 0, 0x3D650112)
+    xf = [_trs(0, 0, 0, 0, 1.0), _trs(0.9, 0.1, -0.4, 35, 0.6), _trs(-0.8, -0.2, 0.5, -70, 0.8)]
+    inst = [(0, *xf[0]), (1, *xf[1]), (0, *xf[2])]
+    cam, w, h = g.default_camera(), 480, 270
+    opt = g.default_options(pipeline=A.PIPELINE_3DGUT, front_to_back=1)
+    r.upload_scene([a, b], inst, opt)
+    img, st, ids, keys = r.render(g.frame_params(cam, w, h), want_sorted=True)
+    oimg, okeys, oids = O.render_scene([O.Packed(a), O.Packed(b)], inst, O.frame_params(cam, w, h), O.default_gut_options(front_to_back=1),
+                                       rotations=[a.rotation, b.rotation])
+    assert np.array_equal(ids, oids) and np.array_equal(keys, okeys) and st.visible_count > 20_000
+    ro_max = 6.0 / float(np.exp(min(a.scale.min(), b.scale.min())) * 0.6)
+    assert np.abs(img - oimg).max() <= RGBA_TOL + 4e-8 * ro_max

@@ -333,6 +333,15 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     std::memcpy(bl.gut.viewInverse, fp.view_inverse, sizeof(bl.gut.viewInverse));
     std::memcpy(bl.gut.projInverse, fp.proj_inverse, sizeof(bl.gut.projInverse));
     std::memcpy(bl.gut.modelInverse, inst.frameModel ? fp.model_inverse : inst.transformInverse, sizeof(bl.gut.modelInverse));
+    bl.gut.instanceCount = static_cast<uint32_t>(c->instances.size());
+    for(size_t k = 0; k < c->instances.size() && k < GUT_MAX_INSTANCES; k++)
+    {
+      const float* mi             = c->instances[k].frameModel ? fp.model_inverse : c->instances[k].transformInverse;
+      bl.gut.instanceOffset[k]    = c->instances[k].globalOffset;
+      for(int i = 0; i < 3; i++)
+        for(int j = 0; j < 3; j++)
+          bl.gut.instanceInverse[k][3 * i + j] = mi[4 * i + j];
+    }
     bl.gut.viewport[0] = fp.viewport[0], bl.gut.viewport[1] = fp.viewport[1];
     bl.gut.alphaClamp         = fp.alpha_clamp;
     bl.gut.kernelMinResponse  = fp.kernel_min_response;
@@ -648,8 +657,8 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
   if(opt.pipeline > VKGS_PIPELINE_3DGUT)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad pipeline");
   if(opt.pipeline == VKGS_PIPELINE_3DGUT
-     && (opt.extent_projection != VKGS_EXTENT_CONIC || opt.surface_info || (instances && instanceCount > 1)))
-    return fail(c, VKGS_ERR_UNSUPPORTED, "the 3DGUT pipeline is built for EXTENT_CONIC, one instance, no surface info");
+     && (opt.extent_projection != VKGS_EXTENT_CONIC || opt.surface_info || (instances && instanceCount > GUT_MAX_INSTANCES)))
+    return fail(c, VKGS_ERR_UNSUPPORTED, "the 3DGUT pipeline is built for EXTENT_CONIC, at most 8 instances, no surface info");
   if(opt.surface_info && !opt.front_to_back)
     return fail(c, VKGS_ERR_UNSUPPORTED, "surface_info needs front_to_back (the reference only produces it in its FTB pass)");
   uint64_t total = 0;

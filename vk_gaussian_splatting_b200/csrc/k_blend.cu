@@ -137,7 +137,8 @@ static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && BLEND_H %
 // dynamic shared memory of a blend CTA: records ring, hit masks, (surface info) normal + id rings
 __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
 {
-  return 2u * BATCH * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u);
+  return 2u * BATCH * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u)
+         + (gut ? 2u * BATCH * 4u : 0u);
 }
 
 // One CTA (BLEND_WARPS warps) per band of a tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   constexpr uint32_t SMEM_HIT  = 2 * SMEM_REC;       // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
   constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
   constexpr uint32_t SMEM_SID  = SMEM_SURF + 2 * BATCH * 16;
-  static_assert((SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF) == blendSmemBytes(SURF, GUT), "launch-side size");
+  constexpr uint32_t SMEM_INST = SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF;  // 3DGUT: instance index of every staged entry
+  static_assert(SMEM_INST + (GUT ? 2 * BATCH * 4 : 0) == blendSmemBytes(SURF, GUT), "launch-side size");
   extern __shared__ __align__(16) unsigned char s_raw[];
   const uint32_t sbase = smemBaseOpaque(s_raw);
 
@@ -182,7 +184,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   // 3DGUT: the model-space ray directions of this thread's two pixels (generatePinholeRay, cameras.h.slang:27-44,
   // called with SV_Position.xy AND a sub-pixel offset of 0.5, threedgut_raster.frag.slang:92 — restated as written;
   // then threedgut_raster.frag.slang:117-121), in the operation order of orc_gut_fragment
-  float gutDirA[3] = {0.f, 0.f, 0.f}, gutDirB[3] = {0.f, 0.f, 0.f};
+  float gutDirA[3] = {0.f, 0.f, 0.f}, gutDirB[3] = {0.f, 0.f, 0.f};      // model space of instance 0
+  float gutWorldA[3] = {0.f, 0.f, 0.f}, gutWorldB[3] = {0.f, 0.f, 0.f};  // world space (multi-instance scenes)
   const float gutPyA = static_cast<float>(pyA) + 0.5f, gutPyB = static_cast<float>(pyB) + 0.5f;
   if(GUT)
   {
@@ -207,6 +210,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       const float dn = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])), __fmul_rn(dir[2], dir[2])),
                                                            __fmul_rn(dir[3], dir[3]))));
       const float rd[3] = {__fmul_rn(dir[0], dn), __fmul_rn(dir[1], dn), __fmul_rn(dir[2], dn)};
+#pragma unroll
+      for(int j = 0; j < 3; j++)
+        (p ? gutWorldB : gutWorldA)[j] = rd[j];
       float       dm[3];
 #pragma unroll
       for(int j = 0; j < 3; j++)
@@ -246,6 +252,15 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
     {
       cpAsync16(sbase + SMEM_SURF + (buf * BATCH + slot) * 16u, a.surface + id);
       stsU32(sbase + SMEM_SID + (buf * BATCH + slot) * 4u, id);
+    }
+    if(GUT)
+    {
+      // which instance the global id belongs to (the global index table, implicit in the offsets)
+      uint32_t inst = 0;
+#pragma unroll
+      for(int k = 1; k < GUT_MAX_INSTANCES; k++)
+        inst += (static_cast<uint32_t>(k) < a.gut.instanceCount && id >= a.gut.instanceOffset[k]) ? 1u : 0u;
+      stsU32(sbase + SMEM_INST + (buf * BATCH + slot) * 4u, inst);
     }
   };
   // classify this thread's (landed) entry: per-warp-block hit bits -> per-warp hit masks
@@ -334,11 +349,31 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       f.r = q1.x, f.g = q1.y, f.b = q1.z, f.alpha = q1.w;
       f.gmin = 1.0f;
       f.A2   = pk(0.f, 0.f);
+      // ray directions in the model space of the entry's instance (threedgut_raster.frag.slang:117-121)
+      float dmA[3] = {gutDirA[0], gutDirA[1], gutDirA[2]}, dmB[3] = {gutDirB[0], gutDirB[1], gutDirB[2]};
+      if(a.gut.instanceCount > 1u)
+      {
+        const uint32_t slot = (addr - (sbase + surfBuf * SMEM_REC)) / REC_BYTES;
+        const float*   mi   = a.gut.instanceInverse[ldsU32(sbase + SMEM_INST + (surfBuf * BATCH + slot) * 4u)];
+#pragma unroll
+        for(int p = 0; p < 2; p++)
+        {
+          const float* rd = p ? gutWorldB : gutWorldA;
+          float        dm[3];
+#pragma unroll
+          for(int j = 0; j < 3; j++)
+            dm[j] = __fadd_rn(__fadd_rn(__fmul_rn(rd[0], mi[0 + j]), __fmul_rn(rd[1], mi[3 + j])), __fmul_rn(rd[2], mi[6 + j]));
+          const float dmn = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dm[0], dm[0]), __fmul_rn(dm[1], dm[1])), __fmul_rn(dm[2], dm[2]))));
+#pragma unroll
+          for(int j = 0; j < 3; j++)
+            (p ? dmB : dmA)[j] = __fmul_rn(dm[j], dmn);
+        }
+      }
       // exact evaluation of one pixel (the oracle's operation order and exp): the reference path for every kernel
       // degree, and the arbiter of the fast path below
       auto exactPixel = [&](int p) -> float {
         const float pxc = -nfx, pyc = p ? gutPyB : gutPyA;
-        const float* dm = p ? gutDirB : gutDirA;
+        const float* dm = p ? dmB : dmA;
         bool  ok = fabsf(__fsub_rn(pxc, q0.x)) <= q0.z && fabsf(__fsub_rn(pyc, q0.y)) <= q0.w && !(q1.w <= a.gut.alphaCullThreshold);
         const float rd0 = __fmul_rn(q3.x, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q3.w), __fmul_rn(dm[1], q4.z)), __fmul_rn(dm[2], q5.y)));
         const float rd1 = __fmul_rn(q3.y, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.x), __fmul_rn(dm[1], q4.w)), __fmul_rn(dm[2], q5.z)));
@@ -394,7 +429,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         // alpha or response lands within 2e-3 + 4e-7 |ro| (relative) of its discard threshold is re-evaluated
         // exactly, so accept / reject decisions never differ from the oracle.
         const float band = 2e-3f + 4e-7f * q2.w;
-        const f32x2 m0 = pk(gutDirA[0], gutDirB[0]), m1 = pk(gutDirA[1], gutDirB[1]), m2 = pk(gutDirA[2], gutDirB[2]);
+        const f32x2 m0 = pk(dmA[0], dmB[0]), m1 = pk(dmA[1], dmB[1]), m2 = pk(dmA[2], dmB[2]);
         const f32x2 r0 = mul2(fma2(m2, pk(q5.y, q5.y), fma2(m1, pk(q4.z, q4.z), mul2(m0, pk(q3.w, q3.w)))), pk(q3.x, q3.x));
         const f32x2 r1 = mul2(fma2(m2, pk(q5.z, q5.z), fma2(m1, pk(q4.w, q4.w), mul2(m0, pk(q4.x, q4.x)))), pk(q3.y, q3.y));
         const f32x2 r2 = mul2(fma2(m2, pk(q5.w, q5.w), fma2(m1, pk(q5.x, q5.x), mul2(m0, pk(q4.y, q4.y)))), pk(q3.z, q3.z));

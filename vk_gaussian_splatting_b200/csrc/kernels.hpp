@@ -142,11 +142,18 @@ void launchBinBig(const BinArgs& args, cudaStream_t stream);  // expands the hug
 
 
 // per-frame constants of the VK3DGUT fragment stage (FrameInfo + SplatSetDesc fields it reads)
+constexpr int GUT_MAX_INSTANCES = 8;  // splat-set instances of a 3DGUT scene (their inverse transforms travel as kernel arguments)
+
 struct GutFrameConstants
 {
   uint32_t enabled;
   uint32_t kernelDegree;
-  float    viewInverse[16], projInverse[16], modelInverse[16];
+  float    viewInverse[16], projInverse[16], modelInverse[16];  // modelInverse: instance 0
+  // multi-instance scenes: first global splat id of each instance and the upper-left 3x3 of its
+  // transformInverse (row-vector convention, [3*i + j] = transformInverse[4*i + j])
+  uint32_t instanceCount;
+  uint32_t instanceOffset[GUT_MAX_INSTANCES];
+  float    instanceInverse[GUT_MAX_INSTANCES][9];
   float    viewport[2];
   float    alphaClamp, kernelMinResponse, alphaCullThreshold;
 };
