@@ -102,7 +102,7 @@ typedef struct vkgs_options
                                         splat id per pixel, see vkgs_read_surface_info */
   uint32_t pipeline;                 /* VKGS_PIPELINE_3DGS (default: PIPELINE_MESH / PIPELINE_VERT, VK3DGSR) or
                                         VKGS_PIPELINE_3DGUT (PIPELINE_MESH_3DGUT, VK3DGUT: unscented-transform projection,
-                                        per-fragment ray / particle evaluation; pinhole camera, EXTENT_CONIC, <= 8 instances) */
+                                        per-fragment ray / particle evaluation; pinhole camera, <= 8 instances) */
   uint32_t extent_projection;        /* EXTENT_METHOD of the 3DGUT pipeline: VKGS_EXTENT_EIGEN or VKGS_EXTENT_CONIC (the
                                         reference's default, src/parameters.h:190); vkgs_default_options sets CONIC */
   uint32_t kernel_degree;            /* KERNEL_DEGREE of the 3DGUT particle response (shaders/shaderio.h:114-119);

@@ -574,8 +574,11 @@ def test_3dgut_pipeline_matches_oracle(gpu_renderer):
     img3, _, _, _ = r.render(g.frame_params(cam, 480, 270))
     mse = float(np.mean((img3[..., :3] - img_f[..., :3]) ** 2))
     assert 1e-7 < mse < 2e-3
+    # EXTENT_EIGEN quads (centre +- b1 +- b2 from the eigen-decomposition of the projected covariance)
+    _compare_gut_frame(r, s, cam, 480, 270, front_to_back=1, extent_projection=A.EXTENT_EIGEN)
+    _compare_gut_frame(r, s, g.orbit_camera(2, 8), 333, 217, extent_projection=A.EXTENT_EIGEN, ms_antialiasing=1)
     # unsupported combinations fail loudly
-    for kw in (dict(extent_projection=A.EXTENT_EIGEN), dict(surface_info=1, front_to_back=1)):
+    for kw in (dict(surface_info=1, front_to_back=1),):
         with pytest.raises(g.VkgsError):
             r.upload(s, g.default_options(pipeline=A.PIPELINE_3DGUT, **kw))
 

@@ -330,6 +330,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     const vkgs_ctx::Instance& inst = c->instances[0];
     bl.gut.enabled      = 1;
     bl.gut.kernelDegree = c->opt.kernel_degree;
+    bl.gut.extentEigen  = c->opt.extent_projection == VKGS_EXTENT_EIGEN;
     std::memcpy(bl.gut.viewInverse, fp.view_inverse, sizeof(bl.gut.viewInverse));
     std::memcpy(bl.gut.projInverse, fp.proj_inverse, sizeof(bl.gut.projInverse));
     std::memcpy(bl.gut.modelInverse, inst.frameModel ? fp.model_inverse : inst.transformInverse, sizeof(bl.gut.modelInverse));
@@ -657,8 +658,8 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
   if(opt.pipeline > VKGS_PIPELINE_3DGUT)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "bad pipeline");
   if(opt.pipeline == VKGS_PIPELINE_3DGUT
-     && (opt.extent_projection != VKGS_EXTENT_CONIC || opt.surface_info || (instances && instanceCount > GUT_MAX_INSTANCES)))
-    return fail(c, VKGS_ERR_UNSUPPORTED, "the 3DGUT pipeline is built for EXTENT_CONIC, at most 8 instances, no surface info");
+     && (opt.extent_projection > VKGS_EXTENT_CONIC || opt.surface_info || (instances && instanceCount > GUT_MAX_INSTANCES)))
+    return fail(c, VKGS_ERR_UNSUPPORTED, "the 3DGUT pipeline is built for at most 8 instances and without surface info");
   if(opt.surface_info && !opt.front_to_back)
     return fail(c, VKGS_ERR_UNSUPPORTED, "surface_info needs front_to_back (the reference only produces it in its FTB pass)");
   uint64_t total = 0;

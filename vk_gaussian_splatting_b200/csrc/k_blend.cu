@@ -270,7 +270,15 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
     {
       // 3DGUT quad: axis-aligned rectangle centre +- extent (EXTENT_CONIC); a block of pixel centres
       // [x0+0.5, x0+7.5] overlaps it iff |block centre - c| <= extent + 3.5 on both axes
-      const float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * REC_BYTES);  // cx cy ex ey
+      float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * REC_BYTES);  // cx cy ex ey
+      if(a.gut.extentEigen)
+      {
+        // words 2,3 hold w1 = b1 / |b1|^2, word 11 k = |w2| / |w1|, w2 = k (w1.y, -w1.x): bounding box of centre +- b1 +- b2
+        const float k   = __uint_as_float(ldsU32(sbase + buf * SMEM_REC + slot * REC_BYTES + 44));
+        const float i1  = 1.0f / (r0.z * r0.z + r0.w * r0.w), i2 = i1 / k;  // 1/|w1|^2, and b2 = w2 / |w2|^2 = (w1.y, -w1.x) / (k |w1|^2)
+        const float b1x = r0.z * i1, b1y = r0.w * i1, b2x = r0.w * i2, b2y = -r0.z * i2;
+        r0.z = (fabsf(b1x) + fabsf(b2x)) * 1.0001f, r0.w = (fabsf(b1y) + fabsf(b2y)) * 1.0001f;
+      }
 #pragma unroll
       for(uint32_t b = 0; b < BLEND_WARPS; b++)
       {
@@ -369,12 +377,20 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
             (p ? dmB : dmA)[j] = __fmul_rn(dm[j], dmn);
         }
       }
+      // pixel centre inside the quad: |p - c| <= extent (EXTENT_CONIC), or |dot(p - c, w_i)| <= 1 (EXTENT_EIGEN)
+      auto insideQuad = [&](float pxc, float pyc) -> bool {
+        const float ddx = __fsub_rn(pxc, q0.x), ddy = __fsub_rn(pyc, q0.y);
+        if(!a.gut.extentEigen)
+          return fabsf(ddx) <= q0.z && fabsf(ddy) <= q0.w;
+        const float w2x = q0.w * q2.w, w2y = -q0.z * q2.w;
+        return fabsf(ddx * q0.z + ddy * q0.w) <= 1.0f && fabsf(ddx * w2x + ddy * w2y) <= 1.0f;
+      };
       // exact evaluation of one pixel (the oracle's operation order and exp): the reference path for every kernel
       // degree, and the arbiter of the fast path below
       auto exactPixel = [&](int p) -> float {
         const float pxc = -nfx, pyc = p ? gutPyB : gutPyA;
         const float* dm = p ? dmB : dmA;
-        bool  ok = fabsf(__fsub_rn(pxc, q0.x)) <= q0.z && fabsf(__fsub_rn(pyc, q0.y)) <= q0.w && !(q1.w <= a.gut.alphaCullThreshold);
+        bool  ok = insideQuad(pxc, pyc) && !(q1.w <= a.gut.alphaCullThreshold);
         const float rd0 = __fmul_rn(q3.x, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q3.w), __fmul_rn(dm[1], q4.z)), __fmul_rn(dm[2], q5.y)));
         const float rd1 = __fmul_rn(q3.y, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.x), __fmul_rn(dm[1], q4.w)), __fmul_rn(dm[2], q5.z)));
         const float rd2 = __fmul_rn(q3.z, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.y), __fmul_rn(dm[1], q5.x)), __fmul_rn(dm[2], q5.w)));
@@ -428,7 +444,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         // two evaluation orders differ by about 2^-24 |ro| sqrt(dist) relative in the response; a pixel whose
         // alpha or response lands within 2e-3 + 4e-7 |ro| (relative) of its discard threshold is re-evaluated
         // exactly, so accept / reject decisions never differ from the oracle.
-        const float band = 2e-3f + 4e-7f * q2.w;
+        const float roLen = a.gut.extentEigen ? sqrtf(q2.x * q2.x + q2.y * q2.y + q2.z * q2.z) : q2.w;
+        const float band  = 2e-3f + 4e-7f * roLen;
         const f32x2 m0 = pk(dmA[0], dmB[0]), m1 = pk(dmA[1], dmB[1]), m2 = pk(dmA[2], dmB[2]);
         const f32x2 r0 = mul2(fma2(m2, pk(q5.y, q5.y), fma2(m1, pk(q4.z, q4.z), mul2(m0, pk(q3.w, q3.w)))), pk(q3.x, q3.x));
         const f32x2 r1 = mul2(fma2(m2, pk(q5.z, q5.z), fma2(m1, pk(q4.w, q4.w), mul2(m0, pk(q4.x, q4.x)))), pk(q3.y, q3.y));
@@ -445,8 +462,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         const float distA = __fdividef(nlo, dlo), distB = __fdividef(nhi, dhi);
         const float respA = ex2Approx(distA * -0.72134752044448170368f), respB = ex2Approx(distB * -0.72134752044448170368f);
         const float alA = fminf(a.gut.alphaClamp, respA * q1.w), alB = fminf(a.gut.alphaClamp, respB * q1.w);
-        const bool  inX = fabsf(__fsub_rn(-nfx, q0.x)) <= q0.z && !(q1.w <= a.gut.alphaCullThreshold);
-        const bool  inA = inX && fabsf(__fsub_rn(gutPyA, q0.y)) <= q0.w, inB = inX && fabsf(__fsub_rn(gutPyB, q0.y)) <= q0.w;
+        const bool  dense = !(q1.w <= a.gut.alphaCullThreshold);
+        const bool  inA = dense && insideQuad(-nfx, gutPyA), inB = dense && insideQuad(-nfx, gutPyB);
         const float THR = 1.0f / 255.0f, MINR = a.gut.kernelMinResponse;
         nOp[0] = (inA && alA > THR && respA > MINR) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
         nOp[1] = (inB && alB > THR && respB > MINR) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;

@@ -154,6 +154,7 @@ __device__ __forceinline__ int gutProjectPoint(const float world[3], const vkgs_
 
 // Unscented-transform projection + conic extent of one splat. Writes the 24-word 3DGUT record
 //   cx cy ex ey | r g b a | ro.xyz |ro| | 1/scale.xyz R00 | R01 R02 R10 R11 | R12 R20 R21 R22
+//   (EXTENT_EIGEN: words 2,3 = w1 of the quad, word 11 = |w2| / |w1|)
 // (R = inverse rotation, ro = canonical ray origin: the ray origin is the camera for every pixel, so
 // particleCannonicalRay's origin half is evaluated once per splat) and returns the pixel bounding box.
 __device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const float c[4], const float4 rq, const float* scaleLog,
@@ -205,29 +206,64 @@ __device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const f
     const float cx = sp[i + 1][0] - pc[0], cy = sp[i + 1][1] - pc[1];
     cov[0] += wi * (cx * cx), cov[1] += wi * (cx * cy), cov[2] += wi * (cy * cy);
   }
-  // threedgutProjectedExtentConicOpacity (threedgut.h.slang:118-163)
-  const float dc[3] = {cov[0] + 0.3f, cov[1], cov[2] + 0.3f};
-  const float ddet  = dc[0] * dc[2] - dc[1] * dc[1];
-  if(ddet == 0.0f)
-    return false;
-  float conicW = col.w;
-  if(a.opt.ms_antialiasing)
+  float ex, ey, q0z, q0w, q2w = 0.0f;  // record words 2,3 (extent, or w1 of the EIGEN quad) and 11 (|ro|, or |w2|/|w1|)
+  if(a.opt.extent_projection == VKGS_EXTENT_CONIC)
   {
-    const float det = cov[0] * cov[2] - cov[1] * cov[1];
-    conicW          = col.w * sqrtf(fmaxf(0.000025f, det / ddet));
+    // threedgutProjectedExtentConicOpacity (threedgut.h.slang:118-163)
+    const float dc[3] = {cov[0] + 0.3f, cov[1], cov[2] + 0.3f};
+    const float ddet  = dc[0] * dc[2] - dc[1] * dc[1];
+    if(ddet == 0.0f)
+      return false;
+    float conicW = col.w;
+    if(a.opt.ms_antialiasing)
+    {
+      const float det = cov[0] * cov[2] - cov[1] * cov[1];
+      conicW          = col.w * sqrtf(fmaxf(0.000025f, det / ddet));
+    }
+    if(conicW < 0.01f)
+      return false;
+    const float maxPower = logf(conicW / 0.01f);
+    const float ef       = fminf(3.33f, sqrtf(2.0f * maxPower));
+    const float mid      = 0.5f * (dc[0] + dc[2]);
+    const float lambda   = mid + sqrtf(fmaxf(0.01f, mid * mid - ddet));
+    const float radius   = ef * sqrtf(lambda);
+    ex = fminf(ef * sqrtf(dc[0]), radius), ey = fminf(ef * sqrtf(dc[2]), radius);
+    if(!(radius > 0.0f))
+      return false;
+    if(a.opt.ms_antialiasing)
+      col.w = conicW;
+    q0z = ex, q0w = ey;
   }
-  if(conicW < 0.01f)
-    return false;
-  const float maxPower = logf(conicW / 0.01f);
-  const float ef       = fminf(3.33f, sqrtf(2.0f * maxPower));
-  const float mid      = 0.5f * (dc[0] + dc[2]);
-  const float lambda   = mid + sqrtf(fmaxf(0.01f, mid * mid - ddet));
-  const float radius   = ef * sqrtf(lambda);
-  const float ex = fminf(ef * sqrtf(dc[0]), radius), ey = fminf(ef * sqrtf(dc[2]), radius);
-  if(!(radius > 0.0f))
-    return false;
-  if(a.opt.ms_antialiasing)
-    col.w = conicW;
+  else
+  {
+    // threedgsProjectedExtentBasis(cov, 3.33, splatScale, opacity, b1, b2) (threedgs.h.slang:60-121): the quad is
+    // centre +- b1 +- b2; the record keeps w1 = b1 / |b1|^2 and |w2| / |w1| (w2 is w1 turned by -90 degrees)
+    float cv0 = cov[0], cv1 = cov[1], cv2 = cov[2], detOrig = 0.0f;
+    if(a.opt.ms_antialiasing)
+      detOrig = cv0 * cv2 - cv1 * cv1;
+    cv0 += 0.3f, cv2 += 0.3f;
+    if(a.opt.ms_antialiasing)
+      col.w *= sqrtf(fmaxf(detOrig / (cv0 * cv2 - cv1 * cv1), 0.0f));
+    const float D = cv0 * cv2 - cv1 * cv1, trace = cv0 + cv2, t2 = 0.5f * trace;
+    const float term2 = sqrtf(fmaxf(0.1f, t2 * t2 - D));
+    float       ev1 = t2 + term2, ev2 = t2 - term2;
+    if(ev2 <= 0.0f)
+      return false;
+    if(a.opt.point_cloud_mode)
+      ev1 = ev2 = 0.2f;
+    float       e1x = (fabsf(cv1) < 0.001f) ? 1.0f : cv1, e1y = ev1 - cv0;
+    const float einv = 1.0f / sqrtf(e1x * e1x + e1y * e1y);
+    e1x *= einv, e1y *= einv;
+    const float m1 = fminf(3.33f * sqrtf(ev1), 2048.0f), m2 = fminf(3.33f * sqrtf(ev2), 2048.0f);
+    const float b1x = e1x * fp.splat_scale * m1, b1y = e1y * fp.splat_scale * m1;
+    const float b2x = e1y * fp.splat_scale * m2, b2y = -e1x * fp.splat_scale * m2;
+    const float n1 = b1x * b1x + b1y * b1y, n2 = b2x * b2x + b2y * b2y;
+    if(!(n1 > 0.0f) || !(n2 > 0.0f))
+      return false;
+    ex = fabsf(b1x) + fabsf(b2x), ey = fabsf(b1y) + fabsf(b2y);
+    q0z = b1x / n1, q0w = b1y / n1;
+    q2w = sqrtf(n1 / n2);
+  }
   float wc[4], vc[4], cc[4];
   mulVecMat(c, fp.model, wc);
   mulVecMat(wc, fp.view, vc);
@@ -242,10 +278,12 @@ __device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const f
 #pragma unroll
   for(int j = 0; j < 3; j++)  // invRotation[i][j] = rot[j][i]
     ro[j] = giscl[j] * ((gposc[0] * rot[j][0] + gposc[1] * rot[j][1]) + gposc[2] * rot[j][2]);
-  rec[0] = make_float4(pc[0], pc[1], ex, ey);
+  rec[0] = make_float4(pc[0], pc[1], q0z, q0w);
   rec[1] = col;
   // (w: length of the canonical origin — the blend's fast path scales its guard band with it, see k_blend.cu)
-  rec[2] = make_float4(ro[0], ro[1], ro[2], sqrtf((ro[0] * ro[0] + ro[1] * ro[1]) + ro[2] * ro[2]));
+  if(a.opt.extent_projection == VKGS_EXTENT_CONIC)
+    q2w = sqrtf((ro[0] * ro[0] + ro[1] * ro[1]) + ro[2] * ro[2]);
+  rec[2] = make_float4(ro[0], ro[1], ro[2], q2w);
   rec[3] = make_float4(giscl[0], giscl[1], giscl[2], rot[0][0]);        // invRot row 0 = (rot[0][0], rot[1][0], rot[2][0])
   rec[4] = make_float4(rot[1][0], rot[2][0], rot[0][1], rot[1][1]);      // invRot[0][1..2], invRot[1][0..1]
   rec[5] = make_float4(rot[2][1], rot[0][2], rot[1][2], rot[2][2]);      // invRot[1][2], invRot[2][0..2]
