@@ -52,6 +52,8 @@ extern "C" {
 #define VKGS_SIZE_CULLING_ENABLED 1
 #define VKGS_PIPELINE_3DGS 0
 #define VKGS_PIPELINE_3DGUT 1
+#define VKGS_CAMERA_PINHOLE 0
+#define VKGS_CAMERA_FISHEYE 1
 #define VKGS_EXTENT_EIGEN 0
 #define VKGS_EXTENT_CONIC 1
 
@@ -107,6 +109,10 @@ typedef struct vkgs_options
                                         reference's default, src/parameters.h:190); vkgs_default_options sets CONIC */
   uint32_t kernel_degree;            /* KERNEL_DEGREE of the 3DGUT particle response (shaders/shaderio.h:114-119);
                                         vkgs_default_options sets 2 (quadratic = Gaussian) */
+  uint32_t camera_model;             /* CAMERA_TYPE (shaders/shaderio.h:100-101): VKGS_CAMERA_PINHOLE (default) or VKGS_CAMERA_FISHEYE
+                                        (3DGUT pipeline only: equidistant fisheye projection of the sigma points, fisheye dist-stage
+                                        cull, generateFisheyeRay per pixel; frame fields fov_rad and the fisheye focal, see
+                                        vkgs_frame_params_set_fisheye) */
   uint32_t _reserved[1];             /* [0]: profiling flags (0 in production); bit 7 (128) = count blended fragments */
 } vkgs_options;
 
@@ -142,6 +148,7 @@ typedef struct vkgs_frame_params
   float    near_far[2];              /* FrameInfo.nearFar = camera clip planes */
   float    alpha_clamp;              /* FrameInfo.alphaClamp, default 0.99 */
   float    kernel_min_response;      /* KERNEL_MIN_RESPONSE, default 0.0113 (src/parameters.h:216) */
+  float    fov_rad;                  /* FrameInfo.fovRad = radians(vertical fov) (src/gaussian_splatting.cpp:1168); fisheye camera only */
 } vkgs_frame_params;
 
 /* The fields of struct Camera (src/camera_set.h:44-63) the pinhole path uses. */
@@ -244,6 +251,9 @@ VKGS_API int vkgs_global_index_table(const vkgs_ctx* ctx, uint32_t* instance_ind
  *      src/gaussian_splatting.cpp:1150,1298,1369). */
 VKGS_API int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t width, uint32_t height, vkgs_frame_params* out);
 VKGS_API void vkgs_default_camera(vkgs_camera* cam);
+/* Fisheye camera on the 3DGUT pipeline: FrameInfo.focal = (1,-1) * viewport / fovRad
+ * (src/gaussian_splatting.cpp:1239-1243). Call after vkgs_frame_params_from_camera. */
+VKGS_API void vkgs_frame_params_set_fisheye(vkgs_frame_params* fp);
 /* Synchronous: returns after the frame (and the requested copies to host) completed. */
 VKGS_API int vkgs_render(vkgs_ctx* ctx, const vkgs_frame_params* fp, vkgs_outputs* out);
 /* Stream-ordered: enqueue one frame, result stays in the device framebuffer. Up to four frames are

@@ -75,6 +75,11 @@ def lib() -> C.CDLL:
                                         C.POINTER(A.Options), C.POINTER(Quad)]
         l.orc_expf.argtypes = [C.c_float]
         l.orc_expf.restype = C.c_float
+        l.orc_atan2f_ypos.argtypes = [C.c_float, C.c_float]
+        l.orc_atan2f_ypos.restype = C.c_float
+        l.orc_acosf.argtypes = [C.c_float]
+        l.orc_acosf.restype = C.c_float
+        l.orc_sincosf.argtypes = [C.c_float, f32p, f32p]
         l.orc_raster_quad.argtypes = [C.POINTER(Quad), C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p]
         l.orc_render.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams),
                                  C.POINTER(A.Options), f32p, u32p, u32p, C.c_void_p]
@@ -114,9 +119,12 @@ def _u(a):
     return a.ctypes.data_as(u32p) if a is not None else None
 
 
-def frame_params(cam: A.Camera, w: int, h: int) -> A.FrameParams:
+def frame_params(cam: A.Camera, w: int, h: int, fisheye: bool = False) -> A.FrameParams:
     fp = A.FrameParams()
     lib().orc_frame_params_from_camera(C.byref(cam), w, h, C.byref(fp))
+    if fisheye:  # FISHEYE focal, src/gaussian_splatting.cpp:1239-1243
+        fp.focal[0] = np.float32(1.0) * np.float32(fp.viewport[0]) / np.float32(fp.fov_rad)
+        fp.focal[1] = np.float32(-1.0) * np.float32(fp.viewport[1]) / np.float32(fp.fov_rad)
     return fp
 
 

@@ -531,10 +531,12 @@ def test_surface_info_side_outputs_match_oracle(gpu_renderer):
 def _compare_gut_frame(r, s, cam, w, h, **optkw):
     opt = g.default_options(pipeline=A.PIPELINE_3DGUT, **optkw)
     r.upload(s, opt)
-    fp = g.frame_params(cam, w, h)
+    fisheye = optkw.get("camera_model") == A.CAMERA_FISHEYE
+    fp = g.frame_params(cam, w, h, fisheye=fisheye)
     img, st, ids, keys = r.render(fp, want_sorted=True)
     pk = O.Packed(s)
-    oimg, okeys, oids, quads = O.render_gut(pk, s.rotation, O.frame_params(cam, w, h), O.default_gut_options(**optkw), want_quads=True)
+    oimg, okeys, oids, quads = O.render_gut(pk, s.rotation, O.frame_params(cam, w, h, fisheye=fisheye), O.default_gut_options(**optkw),
+                                            want_quads=True)
     assert st.visible_count == len(oids) and np.array_equal(ids, oids) and np.array_equal(keys, okeys)
     d = np.abs(img - oimg)
     if not optkw.get("front_to_back"):
@@ -581,6 +583,31 @@ def test_3dgut_pipeline_matches_oracle(gpu_renderer):
     for kw in (dict(surface_info=1, front_to_back=1),):
         with pytest.raises(g.VkgsError):
             r.upload(s, g.default_options(pipeline=A.PIPELINE_3DGUT, **kw))
+
+
+def test_3dgut_fisheye_camera_matches_oracle(gpu_renderer):
+    """CAMERA_FISHEYE on the VK3DGUT path: fisheye dist-stage cull (ids / keys bit-exact), equidistant projection of the
+    sigma points, generateFisheyeRay per pixel with the field-of-view discard; fixed-sequence atan2 / acos / sin / cos on
+    both sides, so decisions are exact. Wide (170 degree) and narrow fields of view, both extents, both orders."""
+    r = gpu_renderer
+    s = g.synth_scene(40_000, 3, 0x3D650131)
+    cam = g.default_camera()
+    fe = dict(camera_model=A.CAMERA_FISHEYE)
+    img, oimg, st, quads = _compare_gut_frame(r, s, cam, 480, 270, front_to_back=1, **fe)
+    assert st.visible_count > 20_000 and quads["valid"].sum() > 15_000
+    # outside the unit circle of normalised pixel coordinates every fragment is discarded
+    yy, xx = np.mgrid[0:270, 0:480]
+    u, v = (xx + 0.5) / 479.0 * 2 - 1, (yy + 0.5) / 269.0 * 2 - 1
+    assert np.all(img[np.sqrt(u * u + v * v) > 1.001] == 0) and img[..., 3].max() > 0.5
+    _compare_gut_frame(r, s, cam, 333, 217, **fe)
+    wide = g.default_camera()
+    wide.fov_deg = 170.0
+    wide.eye[:] = (0.3, 0.2, 0.4)  # inside the cloud: splats all around, many beyond the maximum angle
+    _compare_gut_frame(r, s, wide, 400, 300, front_to_back=1, **fe)
+    _compare_gut_frame(r, s, g.orbit_camera(2, 8), 320, 320, front_to_back=1, extent_projection=A.EXTENT_EIGEN, ms_antialiasing=1, **fe)
+    # fisheye on the 3DGS raster pipelines is rejected (they are pinhole only)
+    with pytest.raises(g.VkgsError):
+        r.upload(s, g.default_options(camera_model=A.CAMERA_FISHEYE))
 
 
 def test_3dgut_multi_instance_scene_matches_oracle(gpu_renderer):

@@ -383,3 +383,72 @@ def test_3dgut_known_answers():
         assert ok and o == pytest.approx(min(0.99, a * want), rel=3e-3), deg
     # the frame: alpha at the centre pixel = clamped opacity
     assert img[199, 199, 3] == pytest.approx(min(0.99, a), rel=1e-6)
+
+
+def test_fixed_sequence_trigonometry_known_answers():
+    """orc_atan2f_ypos / orc_acosf / orc_sincosf (the fisheye camera's elementary functions, fixed operation sequences the
+    CUDA path reproduces bit for bit) against double-precision numpy: exact anchor values and <= 4e-7 absolute elsewhere."""
+    l = O.lib()
+    f32p = C.POINTER(C.c_float)
+    s, c = np.zeros(1, np.float32), np.zeros(1, np.float32)
+
+    def sincos(x):
+        l.orc_sincosf(float(x), s.ctypes.data_as(f32p), c.ctypes.data_as(f32p))
+        return float(s[0]), float(c[0])
+
+    assert sincos(0.0) == (0.0, 1.0)
+    assert l.orc_acosf(1.0) == 0.0 and l.orc_acosf(0.0) == float(np.float32(np.pi / 2))
+    assert l.orc_atan2f_ypos(1.0, 0.0) == float(np.float32(np.pi / 2))
+    assert abs(l.orc_atan2f_ypos(1.0, 1.0) - np.pi / 4) < 1e-7 and abs(l.orc_atan2f_ypos(1e-7, -1.0) - np.pi) < 3e-7
+    xs = np.linspace(-1, 1, 4001, dtype=np.float32)
+    assert max(abs(l.orc_acosf(float(x)) - np.arccos(np.float64(x))) for x in xs) < 4e-7
+    for x in np.concatenate([np.linspace(-6.5, 6.5, 4001), np.linspace(-100, 100, 1001)]).astype(np.float32):
+        sv, cv = sincos(x)
+        assert abs(sv - np.sin(np.float64(x))) < 2e-7 and abs(cv - np.cos(np.float64(x))) < 2e-7
+    rng = np.random.default_rng(5)
+    for _ in range(4000):
+        y, x = np.float32(10 ** rng.uniform(-7, 3)), np.float32(rng.choice([-1, 1]) * 10 ** rng.uniform(-7, 3))
+        assert abs(l.orc_atan2f_ypos(float(y), float(x)) - np.arctan2(np.float64(y), np.float64(x))) < 4e-7
+
+
+def test_3dgut_fisheye_known_answers():
+    """CAMERA_FISHEYE of the VK3DGUT oracle: the fisheye focal (gaussian_splatting.cpp:1239-1243), a splat on the optical
+    axis projects to the principal point, its response peaks at the pixel the projection names, pixels outside the unit
+    circle of normalised coordinates are discarded, the dist stage culls beyond the maximum angle."""
+    cam = g.default_camera()
+    w, h = 160, 90
+    fp = O.frame_params(cam, w, h, fisheye=True)
+    assert fp.fov_rad == np.float32(math.radians(60.0))
+    assert fp.focal[0] == np.float32(w) / np.float32(fp.fov_rad) and fp.focal[1] == -np.float32(h) / np.float32(fp.fov_rad)
+    assert bytes(fp) == bytes(g.frame_params(cam, w, h, fisheye=True))  # host helper of the product == oracle restatement
+    opt = O.default_gut_options(camera_model=A.CAMERA_FISHEYE, front_to_back=1)
+    s = g.synth_scene(3000, 0, 11)
+    s.positions[0] = (0.0, 0.0, 0.0)  # the camera looks at the origin: on the optical axis
+    s.scale[0] = np.log(0.05)
+    s.opacity[0] = 4.0
+    img, keys, ids, quads = O.render_gut(O.Packed(s), s.rotation, fp, opt, want_quads=True)
+    q0 = quads[0]
+    assert q0["valid"] == 1 and abs(q0["center"][0] - w / 2) < 1e-3 and abs(q0["center"][1] - h / 2) < 1e-3
+    ok, op = O.gut_fragment(q0, w / 2 + 0.5, h / 2 + 0.5, fp, opt)
+    assert ok and op > 0.6  # (the ray convention pixel / (res - 1) puts the axis 0.7 sigma away from this pixel centre)
+    # response peak of an off-axis splat lands next to its projected centre (half a pixel of quantisation + the up to
+    # half a pixel by which the ray convention pixel / (res - 1) and the projection's focal = res / fov disagree)
+    q = quads[quads["valid"] == 1]
+    big = q[np.argmax(q["extent"][:, 0])]
+    cx, cy = big["center"]
+    best = max((O.gut_fragment(big, i + 0.5, j + 0.5, fp, opt)[1], i + 0.5, j + 0.5)
+               for j in range(max(0, int(cy) - 5), min(h, int(cy) + 6)) for i in range(max(0, int(cx) - 5), min(w, int(cx) + 6))
+               if O.gut_fragment(big, i + 0.5, j + 0.5, fp, opt)[0])
+    assert abs(best[1] - cx) <= 1.5 and abs(best[2] - cy) <= 1.5
+    # field-of-view discard: corners of the frame are outside the unit circle
+    assert not O.gut_fragment(q0, 0.5, 0.5, fp, opt)[0]
+    yy, xx = np.mgrid[0:h, 0:w]
+    u, v = (xx + 0.5) / (w - 1) * 2 - 1, (yy + 0.5) / (h - 1) * 2 - 1
+    assert np.all(img[np.sqrt(u * u + v * v) > 1.001] == 0) and img[..., 3].max() > 0.9
+    # dist-stage cull: a camera inside the cloud keeps fewer splats than there are, and never one behind it
+    inside = g.default_camera()
+    inside.eye[:] = (0.3, 0.2, 0.4)
+    fpi = O.frame_params(inside, w, h, fisheye=True)
+    pk = O.Packed(s)
+    keys_i, ids_i = O.dist_cull(pk, fpi, opt)
+    assert 0 < len(ids_i) < len(s.positions)

@@ -26,6 +26,7 @@ FRUSTUM_CULLING_NONE, FRUSTUM_CULLING_AT_DIST, FRUSTUM_CULLING_AT_RASTER = 0, 1,
 SIZE_CULLING_DISABLED, SIZE_CULLING_ENABLED = 0, 1
 PIPELINE_3DGS, PIPELINE_3DGUT = 0, 1
 EXTENT_EIGEN, EXTENT_CONIC = 0, 1
+CAMERA_PINHOLE, CAMERA_FISHEYE = 0, 1
 
 K_NAMES = ["preprocess", "sort_hist", "sort_pass0", "sort_pass1", "sort_pass2", "sort_pass3", "bin_emit",
            "tile_hist", "tile_sort0", "tile_sort1", "tile_ranges", "blend"]
@@ -46,7 +47,7 @@ class Options(C.Structure):
                 ("point_cloud_mode", C.c_uint32), ("show_sh_only", C.c_uint32), ("disable_opacity_gaussian", C.c_uint32),
                 ("transmittance_epsilon", C.c_float), ("target_format", C.c_uint32), ("surface_info", C.c_uint32),
                 ("pipeline", C.c_uint32), ("extent_projection", C.c_uint32), ("kernel_degree", C.c_uint32),
-                ("_reserved", C.c_uint32 * 1)]
+                ("camera_model", C.c_uint32), ("_reserved", C.c_uint32 * 1)]
 
 
 class FrameParams(C.Structure):
@@ -58,7 +59,7 @@ class FrameParams(C.Structure):
                 ("height", C.c_uint32), ("depth_iso_threshold", C.c_float), ("thin_particle_threshold", C.c_float),
                 ("view_inverse", C.c_float * 16), ("proj_inverse", C.c_float * 16), ("view_quat", C.c_float * 4),
                 ("view_trans", C.c_float * 3), ("near_far", C.c_float * 2), ("alpha_clamp", C.c_float),
-                ("kernel_min_response", C.c_float)]
+                ("kernel_min_response", C.c_float), ("fov_rad", C.c_float)]
 
 
 class Camera(C.Structure):
@@ -102,6 +103,7 @@ SYMBOLS = {
     "vkgs_global_index_table": (C.c_int, [C.c_void_p, u32p, u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "vkgs_frame_params_from_camera": (C.c_int, [C.POINTER(Camera), C.c_uint32, C.c_uint32, C.POINTER(FrameParams)]),
     "vkgs_default_camera": (None, [C.POINTER(Camera)]),
+    "vkgs_frame_params_set_fisheye": (None, [C.POINTER(FrameParams)]),
     "vkgs_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.POINTER(Outputs)]),
     "vkgs_render_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams)]),
     "vkgs_render_to_host_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_void_p]),

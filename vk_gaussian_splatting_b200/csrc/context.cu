@@ -331,6 +331,8 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     bl.gut.enabled      = 1;
     bl.gut.kernelDegree = c->opt.kernel_degree;
     bl.gut.extentEigen  = c->opt.extent_projection == VKGS_EXTENT_EIGEN;
+    bl.gut.fisheye      = c->opt.camera_model == VKGS_CAMERA_FISHEYE;
+    bl.gut.fovRad       = fp.fov_rad;
     std::memcpy(bl.gut.viewInverse, fp.view_inverse, sizeof(bl.gut.viewInverse));
     std::memcpy(bl.gut.projInverse, fp.proj_inverse, sizeof(bl.gut.projInverse));
     std::memcpy(bl.gut.modelInverse, inst.frameModel ? fp.model_inverse : inst.transformInverse, sizeof(bl.gut.modelInverse));
@@ -660,6 +662,8 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
   if(opt.pipeline == VKGS_PIPELINE_3DGUT
      && (opt.extent_projection > VKGS_EXTENT_CONIC || opt.surface_info || (instances && instanceCount > GUT_MAX_INSTANCES)))
     return fail(c, VKGS_ERR_UNSUPPORTED, "the 3DGUT pipeline is built for at most 8 instances and without surface info");
+  if(opt.camera_model > VKGS_CAMERA_FISHEYE || (opt.camera_model == VKGS_CAMERA_FISHEYE && opt.pipeline != VKGS_PIPELINE_3DGUT))
+    return fail(c, VKGS_ERR_UNSUPPORTED, "the fisheye camera model needs the 3DGUT pipeline (the 3DGS raster pipelines are pinhole only)");
   if(opt.surface_info && !opt.front_to_back)
     return fail(c, VKGS_ERR_UNSUPPORTED, "surface_info needs front_to_back (the reference only produces it in its FTB pass)");
   uint64_t total = 0;

@@ -213,6 +213,87 @@ __device__ __forceinline__ float expfExact(float x)
   return __fmul_rn(e, __uint_as_float(static_cast<uint32_t>(k + 127) << 23));
 }
 
+// Fixed-sequence fp32 trigonometry of the fisheye camera (same operation sequences as orc_atan2f_ypos / orc_acosf /
+// orc_sincosf in oracle/vkgs_oracle.c: Cephes single-precision range reductions and polynomials).
+__device__ __forceinline__ float atanNonnegExact(float x)
+{
+  float y0 = 0.0f;
+  if(x > 2.414213562373095f)
+  {
+    y0 = 1.57079632679489661923f;
+    x  = -__fdiv_rn(1.0f, x);
+  }
+  else if(x > 0.4142135623730950f)
+  {
+    y0 = 0.78539816339744830962f;
+    x  = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f));
+  }
+  const float z = __fmul_rn(x, x);
+  float       p = 8.05374449538e-2f;
+  p             = __fmaf_rn(p, z, -1.38776856032e-1f);
+  p             = __fmaf_rn(p, z, 1.99777106478e-1f);
+  p             = __fmaf_rn(p, z, -3.33329491539e-1f);
+  return __fadd_rn(y0, __fmaf_rn(__fmul_rn(p, z), x, x));
+}
+
+__device__ __forceinline__ float atan2fYposExact(float y, float x)  // y > 0
+{
+  if(x == 0.0f)
+    return 1.57079632679489661923f;
+  const float t = __fdiv_rn(y, x);
+  return x > 0.0f ? atanNonnegExact(t) : __fsub_rn(3.14159265358979323846f, atanNonnegExact(-t));
+}
+
+__device__ __forceinline__ float asinSmallExact(float x)  // |x| <= 0.5
+{
+  const float z = __fmul_rn(x, x);
+  float       p = 4.2163199048e-2f;
+  p             = __fmaf_rn(p, z, 2.4181311049e-2f);
+  p             = __fmaf_rn(p, z, 4.5470025998e-2f);
+  p             = __fmaf_rn(p, z, 7.4953002686e-2f);
+  p             = __fmaf_rn(p, z, 1.6666752422e-1f);
+  return __fmaf_rn(__fmul_rn(p, z), x, x);
+}
+
+__device__ __forceinline__ float acosfExact(float x)  // x in [-1, 1]
+{
+  if(x > 0.5f)
+    return __fmul_rn(2.0f, asinSmallExact(__fsqrt_rn(__fmul_rn(0.5f, __fsub_rn(1.0f, x)))));
+  if(x < -0.5f)
+    return __fsub_rn(3.14159265358979323846f, __fmul_rn(2.0f, asinSmallExact(__fsqrt_rn(__fmul_rn(0.5f, __fadd_rn(1.0f, x))))));
+  return __fsub_rn(1.57079632679489661923f, asinSmallExact(x));
+}
+
+__device__ __forceinline__ void sincosfExact(float xx, float& sOut, float& cOut)  // |xx| < 8192
+{
+  float    x = fabsf(xx);
+  uint32_t j = static_cast<uint32_t>(__fmul_rn(x, 1.27323954473516f));
+  j          = (j + 1u) & ~1u;
+  const float y = static_cast<float>(j);
+  x             = __fmaf_rn(-y, 0.78515625f, x);
+  x             = __fmaf_rn(-y, 2.4187564849853515625e-4f, x);
+  x             = __fmaf_rn(-y, 3.77489497744594108e-8f, x);
+  const float z = __fmul_rn(x, x);
+  float       ps = -1.9515295891e-4f;
+  ps             = __fmaf_rn(ps, z, 8.3321608736e-3f);
+  ps             = __fmaf_rn(ps, z, -1.6666654611e-1f);
+  const float sp = __fmaf_rn(__fmul_rn(ps, z), x, x);
+  float       pc = 2.443315711809948e-5f;
+  pc             = __fmaf_rn(pc, z, -1.388731625493765e-3f);
+  pc             = __fmaf_rn(pc, z, 4.166664568298827e-2f);
+  const float cp = __fmaf_rn(pc, __fmul_rn(z, z), __fmaf_rn(-0.5f, z, 1.0f));
+  float       s, c;
+  switch((j >> 1) & 3u)
+  {
+    case 0: s = sp, c = cp; break;
+    case 1: s = cp, c = -sp; break;
+    case 2: s = -sp, c = -cp; break;
+    default: s = -cp, c = sp; break;
+  }
+  sOut = xx < 0.0f ? -s : s;
+  cOut = c;
+}
+
 // ---------------------------------------------------------------------------------------------
 // scans
 

@@ -193,7 +193,17 @@ extern "C" int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t wi
   out->near_far[0] = cam->znear, out->near_far[1] = cam->zfar;
   out->alpha_clamp         = 0.99f;    // shaders/shaderio.h:271
   out->kernel_min_response = 0.0113f;  // src/parameters.h:216
+  out->fov_rad             = fovy;     // cameraManip->getRadFov(), src/gaussian_splatting.cpp:1168
   out->depth_iso_threshold     = 0.7f;   // shaders/shaderio.h:311
   out->thin_particle_threshold = 1e-6f;  // shaders/shaderio.h:316
   return VKGS_OK;
+}
+
+// FISHEYE focal, src/gaussian_splatting.cpp:1239-1243
+extern "C" VKGS_API void vkgs_frame_params_set_fisheye(vkgs_frame_params* fp)
+{
+  if(!fp)
+    return;
+  fp->focal[0] = 1.0f * fp->viewport[0] / fp->fov_rad;
+  fp->focal[1] = -1.0f * fp->viewport[1] / fp->fov_rad;
 }

@@ -187,21 +187,44 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   float gutDirA[3] = {0.f, 0.f, 0.f}, gutDirB[3] = {0.f, 0.f, 0.f};      // model space of instance 0
   float gutWorldA[3] = {0.f, 0.f, 0.f}, gutWorldB[3] = {0.f, 0.f, 0.f};  // world space (multi-instance scenes)
   const float gutPyA = static_cast<float>(pyA) + 0.5f, gutPyB = static_cast<float>(pyB) + 0.5f;
+  bool        gutFovA = true, gutFovB = true;  // fisheye: pixel inside the field of view (else every fragment is discarded)
   if(GUT)
   {
 #pragma unroll
     for(int p = 0; p < 2; p++)
     {
-      const float pcx = __fadd_rn(static_cast<float>(px) + 0.5f, 0.5f), pcy = __fadd_rn(p ? gutPyB : gutPyA, 0.5f);
-      const float dx = __fsub_rn(__fmul_rn(__fdiv_rn(pcx, a.gut.viewport[0]), 2.0f), 1.0f);
-      const float dy = __fsub_rn(__fmul_rn(__fdiv_rn(pcy, a.gut.viewport[1]), 2.0f), 1.0f);
-      const float t4[4] = {dx, dy, 1.0f, 1.0f};
-      float       tgt[4], dir[4];
+      float tgt[4], dir[4];
+      if(a.gut.fisheye)
+      {
+        // generateFisheyeRay(SV_Position.xy, viewport, fovRad, 0, viewInverse) (cameras.h.slang:47-82), in the
+        // operation order of orc_gut_fragment; direction goes through viewInverse below like the pinhole target
+        const float fpx = static_cast<float>(px) + 0.5f, fpy = p ? gutPyB : gutPyA;
+        const float u = __fsub_rn(__fmul_rn(__fdiv_rn(fpx, __fsub_rn(a.gut.viewport[0], 1.0f)), 2.0f), 1.0f);
+        const float v = __fsub_rn(__fmul_rn(__fdiv_rn(fpy, __fsub_rn(a.gut.viewport[1], 1.0f)), 2.0f), 1.0f);
+        const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
+        (p ? gutFovB : gutFovA) = !(r > 1.0f);
+        float phiCos = fabsf(r) > 1e-9f ? __fdiv_rn(u, r) : 0.0f;
+        phiCos       = fminf(fmaxf(phiCos, -1.0f), 1.0f);
+        float phi    = acosfExact(phiCos);
+        phi          = v < 0.0f ? -phi : phi;
+        const float theta = __fmul_rn(__fmul_rn(r, a.gut.fovRad), 0.5f);
+        float       sphi, cphi, sth, cth;
+        sincosfExact(phi, sphi, cphi);
+        sincosfExact(theta, sth, cth);
+        tgt[0] = __fmul_rn(cphi, sth), tgt[1] = __fmul_rn(-sphi, sth), tgt[2] = -cth, tgt[3] = 0.0f;
+      }
+      else
+      {
+        const float pcx = __fadd_rn(static_cast<float>(px) + 0.5f, 0.5f), pcy = __fadd_rn(p ? gutPyB : gutPyA, 0.5f);
+        const float dx = __fsub_rn(__fmul_rn(__fdiv_rn(pcx, a.gut.viewport[0]), 2.0f), 1.0f);
+        const float dy = __fsub_rn(__fmul_rn(__fdiv_rn(pcy, a.gut.viewport[1]), 2.0f), 1.0f);
+        const float t4[4] = {dx, dy, 1.0f, 1.0f};
 #pragma unroll
-      for(int j = 0; j < 4; j++)
-        tgt[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t4[0], a.gut.projInverse[0 + j]), __fmul_rn(t4[1], a.gut.projInverse[4 + j])),
-                                     __fmul_rn(t4[2], a.gut.projInverse[8 + j])),
-                           __fmul_rn(t4[3], a.gut.projInverse[12 + j]));
+        for(int j = 0; j < 4; j++)
+          tgt[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t4[0], a.gut.projInverse[0 + j]), __fmul_rn(t4[1], a.gut.projInverse[4 + j])),
+                                       __fmul_rn(t4[2], a.gut.projInverse[8 + j])),
+                             __fmul_rn(t4[3], a.gut.projInverse[12 + j]));
+      }
 #pragma unroll
       for(int j = 0; j < 4; j++)
         dir[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(tgt[0], a.gut.viewInverse[0 + j]), __fmul_rn(tgt[1], a.gut.viewInverse[4 + j])),
@@ -378,7 +401,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         }
       }
       // pixel centre inside the quad: |p - c| <= extent (EXTENT_CONIC), or |dot(p - c, w_i)| <= 1 (EXTENT_EIGEN)
-      auto insideQuad = [&](float pxc, float pyc) -> bool {
+      auto insideQuad = [&](float pxc, float pyc, bool inFov) -> bool {
+        if(!inFov)
+          return false;
         const float ddx = __fsub_rn(pxc, q0.x), ddy = __fsub_rn(pyc, q0.y);
         if(!a.gut.extentEigen)
           return fabsf(ddx) <= q0.z && fabsf(ddy) <= q0.w;
@@ -390,7 +415,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       auto exactPixel = [&](int p) -> float {
         const float pxc = -nfx, pyc = p ? gutPyB : gutPyA;
         const float* dm = p ? dmB : dmA;
-        bool  ok = insideQuad(pxc, pyc) && !(q1.w <= a.gut.alphaCullThreshold);
+        bool  ok = insideQuad(pxc, pyc, p ? gutFovB : gutFovA) && !(q1.w <= a.gut.alphaCullThreshold);
         const float rd0 = __fmul_rn(q3.x, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q3.w), __fmul_rn(dm[1], q4.z)), __fmul_rn(dm[2], q5.y)));
         const float rd1 = __fmul_rn(q3.y, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.x), __fmul_rn(dm[1], q4.w)), __fmul_rn(dm[2], q5.z)));
         const float rd2 = __fmul_rn(q3.z, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.y), __fmul_rn(dm[1], q5.x)), __fmul_rn(dm[2], q5.w)));
@@ -463,7 +488,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         const float respA = ex2Approx(distA * -0.72134752044448170368f), respB = ex2Approx(distB * -0.72134752044448170368f);
         const float alA = fminf(a.gut.alphaClamp, respA * q1.w), alB = fminf(a.gut.alphaClamp, respB * q1.w);
         const bool  dense = !(q1.w <= a.gut.alphaCullThreshold);
-        const bool  inA = dense && insideQuad(-nfx, gutPyA), inB = dense && insideQuad(-nfx, gutPyB);
+        const bool  inA = dense && insideQuad(-nfx, gutPyA, gutFovA), inB = dense && insideQuad(-nfx, gutPyB, gutFovB);
         const float THR = 1.0f / 255.0f, MINR = a.gut.kernelMinResponse;
         nOp[0] = (inA && alA > THR && respA > MINR) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
         nOp[1] = (inB && alB > THR && respB > MINR) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;

@@ -121,9 +121,53 @@ __device__ __forceinline__ void shRadiance(const void* row, int rowBase, uint32_
 // ---- VK3DGUT per-splat stage (threedgut_raster.mesh.slang:97-255; pinhole camera, EXTENT_CONIC) ----------
 // Same operation order as orc_gut_project_splat / gut_project_point in oracle/vkgs_oracle.c.
 
+// projectPointFisheye on initPerfectFisheyeCamera(viewport, focal) (threedgut_camera_projections.h.slang:149-171,
+// threedgut_camera_models.h.slang:85-139), in the operation order of gut_project_fisheye (oracle)
+// (by-value interface: a pointer argument of a non-inlined function would push the caller's sigma-point array to local memory)
+__device__ __noinline__ float3 gutProjectFisheyeV(float posX, float posY, float posZ, const vkgs_frame_params& fp)
+{
+  const float pos[3] = {posX, posY, posZ};
+  float       projected[2];
+  const float W = fp.viewport[0], H = fp.viewport[1];
+  const float ppx = W / 2.0f, ppy = H / 2.0f;
+  const float mdx = (ppx > 0.5f * W) ? ppx : W - ppx, mdy = (ppy > 0.5f * H) ? ppy : H - ppy;
+  const float maxRadius = sqrtf(mdx * mdx + mdy * mdy);
+  const float fovAngleX = 2.0f * maxRadius / fp.focal[0], fovAngleY = 2.0f * maxRadius / fp.focal[1];
+  const float maxAngle  = fmaxf(fovAngleX, fovAngleY) / 2.0f;
+  const float absX = fabsf(pos[0]), absY = fabsf(pos[1]);
+  const float minVal = fminf(absX, absY), maxVal = fmaxf(absX, absY);
+  float       norm = 0.0f;
+  if(!(maxVal <= 0.0f))
+  {
+    const float ratio = minVal / maxVal;
+    norm              = maxVal * sqrtf(1.0f + ratio * ratio);
+  }
+  const float rho       = fmaxf(norm, 1e-7f);
+  const float thetaFull = atan2fYposExact(rho, pos[2]);
+  const float theta     = fminf(thetaFull, maxAngle);
+  const float theta2    = theta * theta;
+  float       poly      = 0.0f;
+#pragma unroll
+  for(int i = 2; i >= 0; --i)
+    poly = theta2 * poly + 0.0f;
+  const float delta = (theta * (poly * theta2 + 1.0f)) / rho;
+  projected[0]      = (fp.focal[0] * pos[0]) * delta + ppx;
+  projected[1]      = (fp.focal[1] * pos[1]) * delta + ppy;
+  const float tolx = W * 0.1f, toly = H * 0.1f;
+  const bool  valid = (theta < maxAngle) && (projected[0] > -tolx) && (projected[1] > -toly) && (projected[0] < W + tolx) && (projected[1] < H + toly);
+  return make_float3(projected[0], projected[1], valid ? 1.0f : 0.0f);
+}
+
+__device__ __forceinline__ int gutProjectFisheye(const float pos[3], const vkgs_frame_params& fp, float projected[2])
+{
+  const float3 r = gutProjectFisheyeV(pos[0], pos[1], pos[2], fp);
+  projected[0] = r.x, projected[1] = r.y;
+  return r.z != 0.0f;
+}
+
 // projectPointWithShutter (global shutter) + projectPointPinhole with zero distortion coefficients
-// (threedgut_camera_projections.h.slang:87-139,186-203)
-__device__ __forceinline__ int gutProjectPoint(const float world[3], const vkgs_frame_params& fp, float projected[2])
+// (threedgut_camera_projections.h.slang:87-139,186-203), or projectPointFisheye
+__device__ __forceinline__ int gutProjectPoint(const float world[3], const vkgs_frame_params& fp, uint32_t cameraModel, float projected[2])
 {
   const float t[3]  = {fp.view_trans[0] * 1.0f, fp.view_trans[1] * 1.0f, fp.view_trans[2] * -1.0f};
   const float q[4]  = {fp.view_quat[0] * -1.0f, fp.view_quat[1] * -1.0f, fp.view_quat[2] * 1.0f, fp.view_quat[3] * 1.0f};
@@ -132,6 +176,8 @@ __device__ __forceinline__ int gutProjectPoint(const float world[3], const vkgs_
   const float r[3]  = {(pf[0] + q[3] * tt[0]) + (q[1] * tt[2] - q[2] * tt[1]), (pf[1] + q[3] * tt[1]) + (q[2] * tt[0] - q[0] * tt[2]),
                        (pf[2] + q[3] * tt[2]) + (q[0] * tt[1] - q[1] * tt[0])};
   const float pos[3] = {r[0] + t[0], r[1] + t[1], r[2] + t[2]};
+  if(cameraModel == VKGS_CAMERA_FISHEYE)
+    return gutProjectFisheye(pos, fp, projected);
   if(pos[2] <= 0.0f)
   {
     projected[0] = projected[1] = 0.0f;
@@ -175,7 +221,7 @@ __device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const f
   int         nvalid = 0;
   float       world[4], pt[4];
   mulVecMat(c, fp.model, world);
-  nvalid += gutProjectPoint(world, fp, sp[0]);
+  nvalid += gutProjectPoint(world, fp, a.opt.camera_model, sp[0]);
   const float w0c   = GUT_LAMBDA / (GUT_D + GUT_LAMBDA);
   float       pc[2] = {sp[0][0] * w0c, sp[0][1] * w0c};
   const float wi    = 1.0f / (2.0f * (GUT_D + GUT_LAMBDA));
@@ -185,11 +231,11 @@ __device__ __forceinline__ bool gutProjectSplat(const PreprocessArgs& a, const f
     const float dl[3] = {(GUT_DELTA * scale[i]) * rot[i][0], (GUT_DELTA * scale[i]) * rot[i][1], (GUT_DELTA * scale[i]) * rot[i][2]};
     pt[0] = c[0] + dl[0], pt[1] = c[1] + dl[1], pt[2] = c[2] + dl[2], pt[3] = 1.0f;
     mulVecMat(pt, fp.model, world);
-    nvalid += gutProjectPoint(world, fp, sp[i + 1]);
+    nvalid += gutProjectPoint(world, fp, a.opt.camera_model, sp[i + 1]);
     pc[0] += wi * sp[i + 1][0], pc[1] += wi * sp[i + 1][1];
     pt[0] = c[0] - dl[0], pt[1] = c[1] - dl[1], pt[2] = c[2] - dl[2];
     mulVecMat(pt, fp.model, world);
-    nvalid += gutProjectPoint(world, fp, sp[i + 4]);
+    nvalid += gutProjectPoint(world, fp, a.opt.camera_model, sp[i + 4]);
     pc[0] += wi * sp[i + 4][0], pc[1] += wi * sp[i + 4][1];
   }
   if(nvalid == 0)
@@ -384,7 +430,17 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     const float w = ndc[3];
     ndc[0] = ndc[0] / w, ndc[1] = ndc[1] / w, ndc[2] = ndc[2] / w;
     const float depth = ndc[2];
-    if(a.opt.frustum_culling_mode == VKGS_FRUSTUM_CULLING_AT_DIST)
+    if(GUT && a.opt.frustum_culling_mode == VKGS_FRUSTUM_CULLING_AT_DIST && a.opt.camera_model == VKGS_CAMERA_FISHEYE)
+    {
+      // dist.comp.slang:75-90: fisheye projection of the view-space centre (z flipped), then the depth range
+      const float pos[3] = {1.0f * view[0], 1.0f * view[1], -1.0f * view[2]};
+      float       projected[2];
+      if(!gutProjectFisheye(pos, a.fp, projected))
+        keep = false;
+      if(ndc[2] < 0.f - a.fp.frustum_dilation || ndc[2] > 1.0f)
+        keep = false;
+    }
+    else if(a.opt.frustum_culling_mode == VKGS_FRUSTUM_CULLING_AT_DIST)
     {
       const float clip = 1.0f + a.fp.frustum_dilation;
       if(fabsf(ndc[0]) > clip || fabsf(ndc[1]) > clip || ndc[2] < 0.f - a.fp.frustum_dilation || ndc[2] > 1.0f)

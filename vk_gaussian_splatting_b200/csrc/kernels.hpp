@@ -149,6 +149,8 @@ struct GutFrameConstants
   uint32_t enabled;
   uint32_t kernelDegree;
   uint32_t extentEigen;  // EXTENT_METHOD == EXTENT_EIGEN: quad = centre +- b1 +- b2 instead of an axis-aligned rectangle
+  uint32_t fisheye;      // CAMERA_TYPE == CAMERA_FISHEYE: generateFisheyeRay instead of generatePinholeRay
+  float    fovRad;
   float    viewInverse[16], projInverse[16], modelInverse[16];  // modelInverse: instance 0
   // multi-instance scenes: first global splat id of each instance and the upper-left 3x3 of its
   // transformInverse (row-vector convention, [3*i + j] = transformInverse[4*i + j])
