@@ -134,11 +134,74 @@ constexpr int      BLOCKS_Y    = BLEND_H / 8;
 constexpr int      BANDS       = TILE_H / BLEND_H;  // CTAs per tile (consecutive block indices: they share the list in L2)
 static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && BLEND_H % 8 == 0 && TILE_H % BLEND_H == 0, "one warp per 8x8 pixel block");
 
-// dynamic shared memory of a blend CTA: records ring, hit masks, (surface info) normal + id rings
+// dynamic shared memory of a blend CTA: records ring, hit masks, (surface info) normal + id rings, (3DGUT) instance index
+// ring + the world-space ray directions of every thread's two pixels (multi-instance scenes only)
 __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
 {
   return 2u * BATCH * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u)
-         + (gut ? 2u * BATCH * 4u : 0u);
+         + (gut ? 2u * BATCH * 4u + BLEND_THREADS * 32u : 0u);
+}
+
+// ---- 3DGUT fragment helpers -----------------------------------------------------------------------------------------
+// pixel centre inside the quad: |p - c| <= extent (EXTENT_CONIC), or |dot(p - c, w_i)| <= 1 (EXTENT_EIGEN; q0.zw = w1,
+// k = |w2| / |w1|, w2 = k (w1.y, -w1.x)). A pixel outside the fisheye field of view carries y = 1e30 and fails here.
+__device__ __forceinline__ bool gutInsideQuad(bool eigen, const float4& q0, float k, float pxc, float pyc)
+{
+  const float ddx = __fsub_rn(pxc, q0.x), ddy = __fsub_rn(pyc, q0.y);
+  if(!eigen)
+    return fabsf(ddx) <= q0.z && fabsf(ddy) <= q0.w;
+  const float w2x = q0.w * k, w2y = -q0.z * k;
+  return fabsf(ddx * q0.z + ddy * q0.w) <= 1.0f && fabsf(ddx * w2x + ddy * w2y) <= 1.0f;
+}
+
+// Exact evaluation of one pixel against the record at shared address `addr` (the oracle's operation order and exp;
+// dm = ray direction in the model space of the entry's instance): the reference path for every kernel degree, and the
+// arbiter of the quadratic kernel's fast path. Returns MINUS the opacity, 0 when the fragment is discarded.
+// Not inlined: it is rare on the default path, and eight inlined copies (two hits x two pixels x two call sites)
+// would push the blend loop out of the instruction cache.
+template <bool NOGAUSS>
+__device__ __noinline__ float gutExactPixel(const GutFrameConstants& g, uint32_t addr, float pxc, float pyc, float dm0, float dm1, float dm2)
+{
+  const float4 q0 = ldsV4(addr), q1 = ldsV4(addr + 16), q2 = ldsV4(addr + 32), q3 = ldsV4(addr + 48), q4 = ldsV4(addr + 64), q5 = ldsV4(addr + 80);
+  bool  ok = gutInsideQuad(g.extentEigen != 0u, q0, q2.w, pxc, pyc) && !(q1.w <= g.alphaCullThreshold);
+  const float rd0 = __fmul_rn(q3.x, __fadd_rn(__fadd_rn(__fmul_rn(dm0, q3.w), __fmul_rn(dm1, q4.z)), __fmul_rn(dm2, q5.y)));
+  const float rd1 = __fmul_rn(q3.y, __fadd_rn(__fadd_rn(__fmul_rn(dm0, q4.x), __fmul_rn(dm1, q4.w)), __fmul_rn(dm2, q5.z)));
+  const float rd2 = __fmul_rn(q3.z, __fadd_rn(__fadd_rn(__fmul_rn(dm0, q4.y), __fmul_rn(dm1, q5.x)), __fmul_rn(dm2, q5.w)));
+  const float rn  = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rd0, rd0), __fmul_rn(rd1, rd1)), __fmul_rn(rd2, rd2))));
+  const float d0 = __fmul_rn(rd0, rn), d1 = __fmul_rn(rd1, rn), d2 = __fmul_rn(rd2, rn);
+  const float c0x = __fsub_rn(__fmul_rn(d1, q2.z), __fmul_rn(d2, q2.y)), c1x = __fsub_rn(__fmul_rn(d2, q2.x), __fmul_rn(d0, q2.z)),
+              c2x = __fsub_rn(__fmul_rn(d0, q2.y), __fmul_rn(d1, q2.x));
+  const float dist = __fadd_rn(__fadd_rn(__fmul_rn(c0x, c0x), __fmul_rn(c1x, c1x)), __fmul_rn(c2x, c2x));
+  float       resp;
+  switch(g.kernelDegree)
+  {
+    case 8: {
+      const float d2s = __fmul_rn(dist, dist);
+      resp            = expfExact(__fmul_rn(__fmul_rn(-0.000685871056241f, d2s), d2s));
+      break;
+    }
+    case 5:
+      resp = expfExact(__fmul_rn(__fmul_rn(__fmul_rn(-0.0185185185185f, dist), dist), __fsqrt_rn(dist)));
+      break;
+    case 4:
+      resp = expfExact(__fmul_rn(__fmul_rn(-0.0555555555556f, dist), dist));
+      break;
+    case 3:
+      resp = expfExact(__fmul_rn(__fmul_rn(-0.166666666667f, dist), __fsqrt_rn(dist)));
+      break;
+    case 1:
+      resp = expfExact(__fmul_rn(-1.5f, __fsqrt_rn(dist)));
+      break;
+    case 0:
+      resp = fmaxf(__fadd_rn(1.0f, __fmul_rn(-0.329630334487f, __fsqrt_rn(dist))), 0.0f);
+      break;
+    default:
+      resp = expfExact(__fmul_rn(-0.5f, dist));
+      break;
+  }
+  const float alpha = fminf(g.alphaClamp, __fmul_rn(resp, q1.w));
+  ok                = ok && alpha > 1.0f / 255.0f && resp > g.kernelMinResponse;
+  return ok ? (NOGAUSS ? -1.0f : -alpha) : 0.0f;
 }
 
 // One CTA (BLEND_WARPS warps) per band of a tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
@@ -158,7 +221,7 @@ __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
 // transmittance update is ordered. Signs are arranged so that no negation is needed per hit:
 // the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
 // colour.
-template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT>
+template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT, bool GUTX = false>
 __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
 {
   // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
@@ -168,7 +231,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
   constexpr uint32_t SMEM_SID  = SMEM_SURF + 2 * BATCH * 16;
   constexpr uint32_t SMEM_INST = SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF;  // 3DGUT: instance index of every staged entry
-  static_assert(SMEM_INST + (GUT ? 2 * BATCH * 4 : 0) == blendSmemBytes(SURF, GUT), "launch-side size");
+  constexpr uint32_t SMEM_WORLD = SMEM_INST + 2 * BATCH * 4;  // 3DGUT: world-space ray directions, 32 bytes per thread
+  static_assert(SMEM_INST + (GUT ? 2 * BATCH * 4 + BLEND_THREADS * 32 : 0) == blendSmemBytes(SURF, GUT), "launch-side size");
   extern __shared__ __align__(16) unsigned char s_raw[];
   const uint32_t sbase = smemBaseOpaque(s_raw);
 
@@ -185,16 +249,15 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
   // called with SV_Position.xy AND a sub-pixel offset of 0.5, threedgut_raster.frag.slang:92 — restated as written;
   // then threedgut_raster.frag.slang:117-121), in the operation order of orc_gut_fragment
   float gutDirA[3] = {0.f, 0.f, 0.f}, gutDirB[3] = {0.f, 0.f, 0.f};      // model space of instance 0
-  float gutWorldA[3] = {0.f, 0.f, 0.f}, gutWorldB[3] = {0.f, 0.f, 0.f};  // world space (multi-instance scenes)
-  const float gutPyA = static_cast<float>(pyA) + 0.5f, gutPyB = static_cast<float>(pyB) + 0.5f;
-  bool        gutFovA = true, gutFovB = true;  // fisheye: pixel inside the field of view (else every fragment is discarded)
+  float gutPyA = static_cast<float>(pyA) + 0.5f, gutPyB = static_cast<float>(pyB) + 0.5f;
+  bool  gutFovA = true, gutFovB = true;  // fisheye: pixel inside the field of view (else every fragment is discarded)
   if(GUT)
   {
 #pragma unroll
     for(int p = 0; p < 2; p++)
     {
       float tgt[4], dir[4];
-      if(a.gut.fisheye)
+      if(GUTX && a.gut.fisheye)
       {
         // generateFisheyeRay(SV_Position.xy, viewport, fovRad, 0, viewInverse) (cameras.h.slang:47-82), in the
         // operation order of orc_gut_fragment; direction goes through viewInverse below like the pinhole target
@@ -233,9 +296,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       const float dn = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])), __fmul_rn(dir[2], dir[2])),
                                                            __fmul_rn(dir[3], dir[3]))));
       const float rd[3] = {__fmul_rn(dir[0], dn), __fmul_rn(dir[1], dn), __fmul_rn(dir[2], dn)};
+      // multi-instance scenes re-derive the model-space direction per entry from the world-space one: parked in shared
+      // memory (six more live registers would spill the blend loop of the common single-instance case)
+      if(GUTX && a.gut.instanceCount > 1u)
+      {
 #pragma unroll
-      for(int j = 0; j < 3; j++)
-        (p ? gutWorldB : gutWorldA)[j] = rd[j];
+        for(int j = 0; j < 3; j++)
+          stsU32(sbase + SMEM_WORLD + tid * 32u + (3u * p + j) * 4u, __float_as_uint(rd[j]));
+      }
       float       dm[3];
 #pragma unroll
       for(int j = 0; j < 3; j++)
@@ -246,6 +314,12 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       for(int j = 0; j < 3; j++)
         (p ? gutDirB : gutDirA)[j] = __fmul_rn(dm[j], dmn);
     }
+    // outside the field of view every fragment is discarded (threedgut_raster.frag.slang:96-100): such a pixel fails
+    // every quad test from here on
+    if(GUTX && !gutFovA)
+      gutPyA = 1e30f;
+    if(GUTX && !gutFovB)
+      gutPyB = 1e30f;
   }
 
   const uint2 range = make_uint2(a.rangeBegin[tile], a.rangeEnd[tile]);  // empty tile: begin > end
@@ -276,7 +350,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       cpAsync16(sbase + SMEM_SURF + (buf * BATCH + slot) * 16u, a.surface + id);
       stsU32(sbase + SMEM_SID + (buf * BATCH + slot) * 4u, id);
     }
-    if(GUT)
+    if(GUT && GUTX)
     {
       // which instance the global id belongs to (the global index table, implicit in the offsets)
       uint32_t inst = 0;
@@ -294,7 +368,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       // 3DGUT quad: axis-aligned rectangle centre +- extent (EXTENT_CONIC); a block of pixel centres
       // [x0+0.5, x0+7.5] overlaps it iff |block centre - c| <= extent + 3.5 on both axes
       float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * REC_BYTES);  // cx cy ex ey
-      if(a.gut.extentEigen)
+      if(GUTX && a.gut.extentEigen)
       {
         // words 2,3 hold w1 = b1 / |b1|^2, word 11 k = |w2| / |w1|, w2 = k (w1.y, -w1.x): bounding box of centre +- b1 +- b2
         const float k   = __uint_as_float(ldsU32(sbase + buf * SMEM_REC + slot * REC_BYTES + 44));
@@ -382,15 +456,16 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
       f.A2   = pk(0.f, 0.f);
       // ray directions in the model space of the entry's instance (threedgut_raster.frag.slang:117-121)
       float dmA[3] = {gutDirA[0], gutDirA[1], gutDirA[2]}, dmB[3] = {gutDirB[0], gutDirB[1], gutDirB[2]};
-      if(a.gut.instanceCount > 1u)
+      if(GUTX && a.gut.instanceCount > 1u)
       {
         const uint32_t slot = (addr - (sbase + surfBuf * SMEM_REC)) / REC_BYTES;
         const float*   mi   = a.gut.instanceInverse[ldsU32(sbase + SMEM_INST + (surfBuf * BATCH + slot) * 4u)];
 #pragma unroll
         for(int p = 0; p < 2; p++)
         {
-          const float* rd = p ? gutWorldB : gutWorldA;
-          float        dm[3];
+          const uint32_t wAddr = sbase + SMEM_WORLD + tid * 32u + 12u * p;
+          const float    rd[3] = {__uint_as_float(ldsU32(wAddr)), __uint_as_float(ldsU32(wAddr + 4u)), __uint_as_float(ldsU32(wAddr + 8u))};
+          float          dm[3];
 #pragma unroll
           for(int j = 0; j < 3; j++)
             dm[j] = __fadd_rn(__fadd_rn(__fmul_rn(rd[0], mi[0 + j]), __fmul_rn(rd[1], mi[3 + j])), __fmul_rn(rd[2], mi[6 + j]));
@@ -400,66 +475,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
             (p ? dmB : dmA)[j] = __fmul_rn(dm[j], dmn);
         }
       }
-      // pixel centre inside the quad: |p - c| <= extent (EXTENT_CONIC), or |dot(p - c, w_i)| <= 1 (EXTENT_EIGEN)
-      auto insideQuad = [&](float pxc, float pyc, bool inFov) -> bool {
-        if(!inFov)
-          return false;
-        const float ddx = __fsub_rn(pxc, q0.x), ddy = __fsub_rn(pyc, q0.y);
-        if(!a.gut.extentEigen)
-          return fabsf(ddx) <= q0.z && fabsf(ddy) <= q0.w;
-        const float w2x = q0.w * q2.w, w2y = -q0.z * q2.w;
-        return fabsf(ddx * q0.z + ddy * q0.w) <= 1.0f && fabsf(ddx * w2x + ddy * w2y) <= 1.0f;
-      };
-      // exact evaluation of one pixel (the oracle's operation order and exp): the reference path for every kernel
-      // degree, and the arbiter of the fast path below
-      auto exactPixel = [&](int p) -> float {
-        const float pxc = -nfx, pyc = p ? gutPyB : gutPyA;
-        const float* dm = p ? dmB : dmA;
-        bool  ok = insideQuad(pxc, pyc, p ? gutFovB : gutFovA) && !(q1.w <= a.gut.alphaCullThreshold);
-        const float rd0 = __fmul_rn(q3.x, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q3.w), __fmul_rn(dm[1], q4.z)), __fmul_rn(dm[2], q5.y)));
-        const float rd1 = __fmul_rn(q3.y, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.x), __fmul_rn(dm[1], q4.w)), __fmul_rn(dm[2], q5.z)));
-        const float rd2 = __fmul_rn(q3.z, __fadd_rn(__fadd_rn(__fmul_rn(dm[0], q4.y), __fmul_rn(dm[1], q5.x)), __fmul_rn(dm[2], q5.w)));
-        const float rn  = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rd0, rd0), __fmul_rn(rd1, rd1)), __fmul_rn(rd2, rd2))));
-        const float d0 = __fmul_rn(rd0, rn), d1 = __fmul_rn(rd1, rn), d2 = __fmul_rn(rd2, rn);
-        const float c0x = __fsub_rn(__fmul_rn(d1, q2.z), __fmul_rn(d2, q2.y)), c1x = __fsub_rn(__fmul_rn(d2, q2.x), __fmul_rn(d0, q2.z)),
-                    c2x = __fsub_rn(__fmul_rn(d0, q2.y), __fmul_rn(d1, q2.x));
-        const float dist = __fadd_rn(__fadd_rn(__fmul_rn(c0x, c0x), __fmul_rn(c1x, c1x)), __fmul_rn(c2x, c2x));
-        float       resp;
-        switch(a.gut.kernelDegree)
-        {
-          case 8: {
-            const float d2s = __fmul_rn(dist, dist);
-            resp            = expfExact(__fmul_rn(__fmul_rn(-0.000685871056241f, d2s), d2s));
-            break;
-          }
-          case 5:
-            resp = expfExact(__fmul_rn(__fmul_rn(__fmul_rn(-0.0185185185185f, dist), dist), __fsqrt_rn(dist)));
-            break;
-          case 4:
-            resp = expfExact(__fmul_rn(__fmul_rn(-0.0555555555556f, dist), dist));
-            break;
-          case 3:
-            resp = expfExact(__fmul_rn(__fmul_rn(-0.166666666667f, dist), __fsqrt_rn(dist)));
-            break;
-          case 1:
-            resp = expfExact(__fmul_rn(-1.5f, __fsqrt_rn(dist)));
-            break;
-          case 0:
-            resp = fmaxf(__fadd_rn(1.0f, __fmul_rn(-0.329630334487f, __fsqrt_rn(dist))), 0.0f);
-            break;
-          default:
-            resp = expfExact(__fmul_rn(-0.5f, dist));
-            break;
-        }
-        const float alpha = fminf(a.gut.alphaClamp, __fmul_rn(resp, q1.w));
-        ok                = ok && alpha > 1.0f / 255.0f && resp > a.gut.kernelMinResponse;
-        return ok ? (NOGAUSS ? -1.0f : -alpha) : 0.0f;
-      };
       float nOp[2];
       if(a.gut.kernelDegree != 2u)
       {
-        nOp[0] = exactPixel(0);
-        nOp[1] = exactPixel(1);
+        nOp[0] = gutExactPixel<NOGAUSS>(a.gut, addr, -nfx, gutPyA, dmA[0], dmA[1], dmA[2]);
+        nOp[1] = gutExactPixel<NOGAUSS>(a.gut, addr, -nfx, gutPyB, dmB[0], dmB[1], dmB[2]);
       }
       else
       {
@@ -469,7 +489,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         // two evaluation orders differ by about 2^-24 |ro| sqrt(dist) relative in the response; a pixel whose
         // alpha or response lands within 2e-3 + 4e-7 |ro| (relative) of its discard threshold is re-evaluated
         // exactly, so accept / reject decisions never differ from the oracle.
-        const float roLen = a.gut.extentEigen ? sqrtf(q2.x * q2.x + q2.y * q2.y + q2.z * q2.z) : q2.w;
+        const float roLen = (GUTX && a.gut.extentEigen) ? sqrtf(q2.x * q2.x + q2.y * q2.y + q2.z * q2.z) : q2.w;
         const float band  = 2e-3f + 4e-7f * roLen;
         const f32x2 m0 = pk(dmA[0], dmB[0]), m1 = pk(dmA[1], dmB[1]), m2 = pk(dmA[2], dmB[2]);
         const f32x2 r0 = mul2(fma2(m2, pk(q5.y, q5.y), fma2(m1, pk(q4.z, q4.z), mul2(m0, pk(q3.w, q3.w)))), pk(q3.x, q3.x));
@@ -488,7 +508,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         const float respA = ex2Approx(distA * -0.72134752044448170368f), respB = ex2Approx(distB * -0.72134752044448170368f);
         const float alA = fminf(a.gut.alphaClamp, respA * q1.w), alB = fminf(a.gut.alphaClamp, respB * q1.w);
         const bool  dense = !(q1.w <= a.gut.alphaCullThreshold);
-        const bool  inA = dense && insideQuad(-nfx, gutPyA, gutFovA), inB = dense && insideQuad(-nfx, gutPyB, gutFovB);
+        const bool  inA = dense && gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyA), inB = dense && gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyB);
         const float THR = 1.0f / 255.0f, MINR = a.gut.kernelMinResponse;
         nOp[0] = (inA && alA > THR && respA > MINR) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
         nOp[1] = (inB && alB > THR && respB > MINR) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
@@ -497,9 +517,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
         if(nearA || nearB)
         {
           if(nearA)
-            nOp[0] = exactPixel(0);
+            nOp[0] = gutExactPixel<NOGAUSS>(a.gut, addr, -nfx, gutPyA, dmA[0], dmA[1], dmA[2]);
           if(nearB)
-            nOp[1] = exactPixel(1);
+            nOp[1] = gutExactPixel<NOGAUSS>(a.gut, addr, -nfx, gutPyB, dmB[0], dmB[1], dmB[2]);
         }
       }
       f.n2 = pk(nOp[0], nOp[1]);
@@ -751,10 +771,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / 
 
 }  // namespace
 
-template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT>
+template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT, bool GUTX = false>
 static void allowSmem()
 {
-  cudaFuncSetAttribute(k_blend<FTB, NOGAUSS, COUNT, SURF, GUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(k_blend<FTB, NOGAUSS, COUNT, SURF, GUT, GUTX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(blendSmemBytes(SURF, GUT)));
 }
 
@@ -768,6 +788,8 @@ void initBlendKernels()
   allowSmem<true, true, false, true, false>(), allowSmem<true, false, false, true, false>();
   allowSmem<true, true, false, false, true>(), allowSmem<true, false, false, false, true>();
   allowSmem<false, true, false, false, true>(), allowSmem<false, false, false, false, true>();
+  allowSmem<true, true, false, false, true, true>(), allowSmem<true, false, false, false, true, true>();
+  allowSmem<false, true, false, false, true, true>(), allowSmem<false, false, false, false, true, true>();
 }
 
 void launchBlend(const BlendArgs& args, cudaStream_t stream)
@@ -788,20 +810,32 @@ void launchBlend(const BlendArgs& args, cudaStream_t stream)
   {
     // VK3DGUT fragment stage (no fragment counters / surface info in this variant)
     constexpr uint32_t SMEM = blendSmemBytes(false, true);
+    // GUTX: the general instantiation (multi-instance scenes, EXTENT_EIGEN quads, fisheye rays); the common case
+    // (one instance, EXTENT_CONIC, pinhole) runs an instantiation with those branches compiled out
+    const bool general = args.gut.instanceCount > 1u || args.gut.extentEigen || args.gut.fisheye;
+#define VKGS_GUT_LAUNCH(F, G)                                                                                                    \
+  do                                                                                                                             \
+  {                                                                                                                              \
+    if(general)                                                                                                                  \
+      k_blend<F, G, false, false, true, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                      \
+    else                                                                                                                         \
+      k_blend<F, G, false, false, true, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                     \
+  } while(0)
     if(args.frontToBack)
     {
       if(args.disableOpacityGaussian)
-        k_blend<true, true, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
+        VKGS_GUT_LAUNCH(true, true);
       else
-        k_blend<true, false, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
+        VKGS_GUT_LAUNCH(true, false);
     }
     else
     {
       if(args.disableOpacityGaussian)
-        k_blend<false, true, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
+        VKGS_GUT_LAUNCH(false, true);
       else
-        k_blend<false, false, false, false, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
+        VKGS_GUT_LAUNCH(false, false);
     }
+#undef VKGS_GUT_LAUNCH
     return;
   }
   constexpr uint32_t SMEM = blendSmemBytes(false, false);
