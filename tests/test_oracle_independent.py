@@ -82,7 +82,7 @@ def _composite(order, frags, h, w, front_to_back):
     return img
 
 
-def _render_3dgs_float64(s, fp, front_to_back):
+def _render_3dgs_float64(s, fp, front_to_back, ms_antialiasing=False):
     h, w = fp.height, fp.width
     view, ndc, keep = _front_end(s, fp)
     cam_model = (np.linalg.inv(_mat(fp.model)) @ np.array(list(fp.camera_position) + [1.0]))[:3]
@@ -102,6 +102,9 @@ def _render_3dgs_float64(s, fp, front_to_back):
         T = J @ Wm
         c2 = T @ cov3[i] @ T.T
         a, b, d = c2[0, 0] + 0.3, c2[0, 1], c2[1, 1] + 0.3
+        al_i = alpha[i]
+        if ms_antialiasing:  # mip-splatting compensation: opacity *= sqrt(det / det') (threedgs.h.slang:63-76)
+            al_i = al_i * np.sqrt(max((c2[0, 0] * c2[1, 1] - b * b) / (a * d - b * b), 0.0))
         m = 0.5 * (a + d)
         t = np.sqrt(max(0.1, m * m - (a * d - b * b)))
         l1, l2 = m + t, m - t
@@ -123,7 +126,7 @@ def _render_3dgs_float64(s, fp, front_to_back):
         u = (dx * b1[0] + dy * b1[1]) / (b1 @ b1)
         v = (dx * b2[0] + dy * b2[1]) / (b2 @ b2)
         Aq = 8.0 * (u * u + v * v)
-        al = np.exp(-0.5 * Aq) * alpha[i]
+        al = np.exp(-0.5 * Aq) * al_i
         ok = (np.abs(u) <= 1) & (np.abs(v) <= 1) & (Aq <= 8.0) & (al > 1.0 / 255.0)
         if ok.any():
             frags[i] = (yy[ok], xx[ok], al[ok], rgb[i])
@@ -318,3 +321,25 @@ def test_3dgut_fisheye_projection_and_ray_match_the_equidistant_model():
                 ro = np.linalg.norm(o) / S[i].min()
                 assert abs(op - a) < 5e-5 + 1e-7 * ro, (op, a, ro)
     assert accepted > 100
+
+
+def test_3dgs_oracle_options_match_float64_restatement():
+    """Mip-splatting antialiasing, a non-trivial model transform and a splat scale, through the same float64 restatement."""
+    s = g.synth_scene(2000, 3, 0x3D65F068)
+    s.scale += np.float32(0.8)
+    cam = g.orbit_camera(1, 8)
+    w, h = 180, 140
+    fp = O.frame_params(cam, w, h)
+    # model = translate * rotate(z, 0.4) * uniform scale 1.1, with its inverse (SplatSetDesc.transform / transformInverse)
+    c, sn, k = np.cos(0.4), np.sin(0.4), 1.1
+    Mm = np.array([[k * c, -k * sn, 0, 0.05], [k * sn, k * c, 0, -0.1], [0, 0, k, 0.02], [0, 0, 0, 1.0]])
+    fp.model[:] = Mm.T.astype(np.float32).reshape(-1).tolist()
+    fp.model_inverse[:] = np.linalg.inv(Mm).T.astype(np.float32).reshape(-1).tolist()
+    fp.splat_scale = 0.75
+    pk = O.Packed(s)
+    for aa in (0, 1):
+        img, keys, ids, _ = O.render(pk, fp, O.default_options(front_to_back=1, ms_antialiasing=aa))
+        ref = _render_3dgs_float64(s, fp, True, ms_antialiasing=bool(aa))
+        per_pixel = _agreement(img, ref, True)
+        assert (ref[..., 3] > 0).mean() > 0.2
+        assert np.quantile(per_pixel, 0.995) < 3e-5 and per_pixel.max() < 2.0 / 255.0, (np.quantile(per_pixel, 0.995), per_pixel.max())
