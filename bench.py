@@ -362,6 +362,17 @@ def main():
                                     "sample": f"best of {cb['reps']} full sorts of all {N_SPLATS} splats (CPU Dist {cb['ms_dist']:.2f} ms + "
                                               f"CPU Sort {cb['ms_sort']:.2f} ms, splat_sorter_async restatement, __gnu_parallel::sort); "
                                               "raster excluded: the reference has no CPU rasterizer"}
+            # the whole path (dist + sort + projection + raster + blend) once through the CPU oracle, same workload
+            try:
+                from oracle import oracle as O
+                t0 = time.perf_counter()
+                pk = O.Packed(scene)
+                O.render(pk, O.frame_params(cam, WIDTH, HEIGHT), O.default_options(front_to_back=1))
+                line["cpu_baseline"]["oracle_frame"] = {"ms": 1000.0 * (time.perf_counter() - t0), "cores": O.render_threads(),
+                                                        "sample": "one frame of the workload through oracle/vkgs_oracle.c (pack + dist + sort + "
+                                                                  "per-splat + raster in row bands), exact compositing (no early termination)"}
+            except Exception as e:  # the baseline must never take the bench line down
+                line["cpu_baseline"]["oracle_frame"] = {"error": repr(e)}
         else:
             line["cpu_baseline"] = None
     r.close()

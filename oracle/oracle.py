@@ -206,6 +206,12 @@ def render_scene(packed_sets, instances, fp, opt, rotations=None):
     return img, keys[:v].copy(), ids[:v].copy()
 
 
+def render_threads() -> int:
+    """Threads the whole-frame oracle renders use (row bands; ORC_THREADS overrides)."""
+    lib().orc_threads.restype = C.c_int
+    return int(lib().orc_threads())
+
+
 def default_gut_options(**kw) -> A.Options:
     """Reference defaults of the 3DGUT pipeline restated independently (src/parameters.h:190,215)."""
     o = default_options(pipeline=A.PIPELINE_3DGUT, extent_projection=A.EXTENT_CONIC, kernel_degree=2)
