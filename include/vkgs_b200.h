@@ -113,6 +113,9 @@ typedef struct vkgs_options
                                         (3DGUT pipeline only: equidistant fisheye projection of the sigma points, fisheye dist-stage
                                         cull, generateFisheyeRay per pixel; frame fields fov_rad and the fisheye focal, see
                                         vkgs_frame_params_set_fisheye) */
+  uint32_t quantize_normals;         /* QUANTIZE_NORMALS (surface_info only; prmRaster.quantizeNormals, src/parameters.h:195, default 1):
+                                        the per-splat normal travels from the mesh to the fragment stage as a 2x16-bit octahedral
+                                        code (shaders/octahedral_normal.h.slang, threedgs_raster.mesh.slang:224-229, frag.slang:198-203) */
   uint32_t _reserved[1];             /* [0]: profiling flags (0 in production); bit 7 (128) = count blended fragments */
 } vkgs_options;
 
@@ -315,6 +318,9 @@ VKGS_API int vkgs_image_metrics_host(vkgs_ctx* ctx, const float* reference, cons
  *        splat_id           W*H u32    global id of the last blended fragment, 0xffffffff where nothing was blended
  *      (with transmittance_epsilon > 0 the list is cut short: ids / T are exact only for epsilon = 0) */
 VKGS_API int vkgs_read_surface_info(vkgs_ctx* ctx, float* normals, float* depth_transmittance, uint32_t* splat_id);
+/* The QUANTIZE_NORMALS round trip (encodeNormalOctahedral -> decodeNormalOctahedral, shaders/octahedral_normal.h.slang) on
+ * `count` unit normals, host arrays [3*count]; host only, no GPU needed (the kernel runs the same function). */
+VKGS_API int vkgs_quantize_normals_host(const float* normals_in, float* normals_out, uint64_t count);
 
 /* ---- parity/debug read-backs of per-splat intermediates of the last frame ----------------
  * Per-splat record, indexed by splat id (only ids that passed the dist-stage cull are valid):

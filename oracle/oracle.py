@@ -132,6 +132,7 @@ def default_options(**kw) -> A.Options:
     """Reference defaults restated independently of the product (src/parameters.h, shaderio.h)."""
     o = A.Options()
     o.frustum_culling_mode = A.FRUSTUM_CULLING_AT_DIST
+    o.quantize_normals = 1  # prmRaster.quantizeNormals, src/parameters.h:195
     for k, v in kw.items():
         setattr(o, k, v)
     return o
@@ -204,6 +205,13 @@ def render_scene(packed_sets, instances, fp, opt, rotations=None):
     fn = lib().orc_render_gut_scene if (keep is not None and opt.pipeline == A.PIPELINE_3DGUT) else lib().orc_render_scene
     v = fn(sets, len(packed_sets), inst, len(instances), C.byref(fp), C.byref(opt), _p(img), _u(keys), _u(ids))
     return img, keys[:v].copy(), ids[:v].copy()
+
+
+def oct_quantize_normal(n) -> np.ndarray:
+    """QUANTIZE_NORMALS round trip of one unit normal (shaders/octahedral_normal.h.slang)."""
+    v = np.ascontiguousarray(n, np.float32).copy()
+    lib().orc_oct_quantize_normal(_p(v))
+    return v
 
 
 def render_threads() -> int:

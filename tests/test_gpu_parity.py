@@ -511,12 +511,14 @@ def test_surface_info_side_outputs_match_oracle(gpu_renderer):
     fp = g.frame_params(cam, w, h)
     r.upload(s, g.default_options(front_to_back=1))
     img0, _, _, _ = r.render(fp)
-    r.upload(s, g.default_options(front_to_back=1, surface_info=1))
+    # (full-precision normals here; the reference's default 2x16-bit octahedral transport is the last test of this file)
+    r.upload(s, g.default_options(front_to_back=1, surface_info=1, quantize_normals=0))
     img, st, ids, _ = r.render(fp, want_sorted=True)
     assert np.array_equal(img, img0)
     nrm, dt, sid = r.read_surface_info(w, h)
     pk = O.Packed(s)
-    oimg, onrm, odt, osid, oids = O.render_surface(pk, s.rotation, O.frame_params(cam, w, h), O.default_options(front_to_back=1))
+    oimg, onrm, odt, osid, oids = O.render_surface(pk, s.rotation, O.frame_params(cam, w, h),
+                                                   O.default_options(front_to_back=1, quantize_normals=0))
     assert np.array_equal(ids, oids)
     assert np.abs(img - oimg).max() <= RGBA_TOL and np.abs(nrm - onrm).max() <= RGBA_TOL
     assert np.abs(dt[..., 1] - odt[..., 1]).max() <= RGBA_TOL
@@ -626,3 +628,30 @@ def test_3dgut_multi_instance_scene_matches_oracle(gpu_renderer):
     assert np.array_equal(ids, oids) and np.array_equal(keys, okeys) and st.visible_count > 20_000
     ro_max = 6.0 / float(np.exp(min(a.scale.min(), b.scale.min())) * 0.6)
     assert np.abs(img - oimg).max() <= RGBA_TOL + 4e-8 * ro_max
+
+
+def test_surface_info_quantized_normals_match_oracle(gpu_renderer):
+    """QUANTIZE_NORMALS (the reference default, src/parameters.h:195): the per-splat normal reaches the fragment stage
+    through its 2x16-bit octahedral code (shaders/octahedral_normal.h.slang). The kernel runs the function whose host
+    instantiation tests/test_oracle_kat.py pins bit for bit against the oracle; a normal that differs in its last bit before
+    quantisation (device expf of the log-scale) can land in the neighbouring 16-bit bucket (one step = 3.05e-5 in octahedral
+    space, <= 5.3e-5 per component after decoding), hence the 1.5e-4 bar on the integrated normals."""
+    r = gpu_renderer
+    s = g.synth_scene(30_000, 3, 0x3D6500F2)
+    s.scale[::89, 2] = np.log(1e-7)
+    cam, w, h = g.orbit_camera(1, 8), 384, 256
+    fp = g.frame_params(cam, w, h)
+    opt = g.default_options(front_to_back=1, surface_info=1)
+    assert opt.quantize_normals == 1
+    r.upload(s, opt)
+    img, st, ids, _ = r.render(fp, want_sorted=True)
+    nrm, dt, sid = r.read_surface_info(w, h)
+    pk = O.Packed(s)
+    oimg, onrm, odt, osid, oids = O.render_surface(pk, s.rotation, O.frame_params(cam, w, h), O.default_options(front_to_back=1))
+    _, onrm_full, _, _, _ = O.render_surface(pk, s.rotation, O.frame_params(cam, w, h), O.default_options(front_to_back=1, quantize_normals=0))
+    assert np.array_equal(ids, oids) and np.abs(img - oimg).max() <= RGBA_TOL
+    assert np.abs(nrm - onrm).max() <= 1.5e-4
+    # most pixels are bit-close; and the quantisation itself is visible against the full-precision normals
+    assert np.quantile(np.abs(nrm - onrm).max(axis=-1), 0.99) <= 2e-6
+    assert 1e-6 < np.abs(onrm - onrm_full).max() < 3e-4
+    assert (sid == osid).mean() > 0.9999

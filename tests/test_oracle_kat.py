@@ -338,7 +338,7 @@ def test_surface_outputs_single_splat():
     q = O.project_splat(pk, 0, fp, O.default_options(front_to_back=1))
     picked = dt[..., 0] != 0
     assert picked.any() and np.all(dt[picked, 0] == np.float32(q.ndc_z)) and np.all(dt[picked, 1] < 0.7) and np.all(dt[hit & ~picked, 1] >= 0.7)
-    n = O.splat_normal(pk, s.rotation, 0, fp)
+    n = O.oct_quantize_normal(O.splat_normal(pk, s.rotation, 0, fp))  # default: the normal travels as an octahedral code
     assert np.allclose(nrm[hit, :3], n[None, :] * img[hit, 3:4], atol=1e-6)
 
 
@@ -452,3 +452,32 @@ def test_3dgut_fisheye_known_answers():
     pk = O.Packed(s)
     keys_i, ids_i = O.dist_cull(pk, fpi, opt)
     assert 0 < len(ids_i) < len(s.positions)
+
+
+def test_octahedral_normal_quantisation_known_answers_and_host_kernel_function():
+    """QUANTIZE_NORMALS round trip (shaders/octahedral_normal.h.slang): axis normals survive exactly up to one 16-bit step,
+    every result is a unit vector within the 2x16-bit resolution of its input, and the function the CUDA kernel runs
+    (its host instantiation behind vkgs_quantize_normals_host) equals the oracle bit for bit."""
+    for axis in np.eye(3, dtype=np.float32):
+        for sign in (1.0, -1.0):
+            q = O.oct_quantize_normal(sign * axis)
+            assert np.abs(q - sign * axis).max() < 4e-5 and abs(np.linalg.norm(q) - 1) < 2e-7
+    rng = np.random.default_rng(17)
+    n = rng.normal(size=(50_000, 3)).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True).astype(np.float32)
+    n = np.concatenate([n, np.array([[0.70710678, 0.70710678, 0], [0.70710678, 0, -0.70710678], [-0.0, 0.6, -0.8], [0.6, -0.0, 0.8]], np.float32)])
+    ref = np.stack([O.oct_quantize_normal(v) for v in n])
+    assert np.abs(ref - n).max() < 1.3e-4 and np.abs(np.linalg.norm(ref, axis=1) - 1).max() < 3e-7
+    # bottom hemisphere really goes through the wrap (sign of z preserved)
+    assert np.all(np.sign(ref[np.abs(n[:, 2]) > 1e-3, 2]) == np.sign(n[np.abs(n[:, 2]) > 1e-3, 2]))
+    out = np.empty_like(n)
+    f32p = C.POINTER(C.c_float)
+    assert A.lib().vkgs_quantize_normals_host(n.ctypes.data_as(f32p), out.ctypes.data_as(f32p), len(n)) == 0
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    # surface frame: quantisation changes the integrated normals by no more than the code's resolution
+    s = g.synth_scene(3000, 0, 23)
+    fp = O.frame_params(g.default_camera(), 160, 100)
+    pk = O.Packed(s)
+    _, nq, _, _, _ = O.render_surface(pk, s.rotation, fp, O.default_options(front_to_back=1))
+    _, nf, _, _, _ = O.render_surface(pk, s.rotation, fp, O.default_options(front_to_back=1, quantize_normals=0))
+    assert 0 < np.abs(nq - nf).max() < 3e-4

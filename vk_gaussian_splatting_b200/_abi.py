@@ -47,7 +47,7 @@ class Options(C.Structure):
                 ("point_cloud_mode", C.c_uint32), ("show_sh_only", C.c_uint32), ("disable_opacity_gaussian", C.c_uint32),
                 ("transmittance_epsilon", C.c_float), ("target_format", C.c_uint32), ("surface_info", C.c_uint32),
                 ("pipeline", C.c_uint32), ("extent_projection", C.c_uint32), ("kernel_degree", C.c_uint32),
-                ("camera_model", C.c_uint32), ("_reserved", C.c_uint32 * 1)]
+                ("camera_model", C.c_uint32), ("quantize_normals", C.c_uint32), ("_reserved", C.c_uint32 * 1)]
 
 
 class FrameParams(C.Structure):
@@ -104,6 +104,7 @@ SYMBOLS = {
     "vkgs_frame_params_from_camera": (C.c_int, [C.POINTER(Camera), C.c_uint32, C.c_uint32, C.POINTER(FrameParams)]),
     "vkgs_default_camera": (None, [C.POINTER(Camera)]),
     "vkgs_frame_params_set_fisheye": (None, [C.POINTER(FrameParams)]),
+    "vkgs_quantize_normals_host": (C.c_int, [f32p, f32p, C.c_uint64]),
     "vkgs_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.POINTER(Outputs)]),
     "vkgs_render_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams)]),
     "vkgs_render_to_host_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_void_p]),

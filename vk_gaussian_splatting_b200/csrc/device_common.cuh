@@ -213,6 +213,35 @@ __device__ __forceinline__ float expfExact(float x)
   return __fmul_rn(e, __uint_as_float(static_cast<uint32_t>(k + 127) << 23));
 }
 
+// QUANTIZE_NORMALS: encodeNormalOctahedral -> decodeNormalOctahedral (shaders/octahedral_normal.h.slang:28-85), the
+// operation order of orc_oct_quantize_normal (oracle). Host + device: tests/test_abi.py pins the host instantiation
+// against the oracle bit for bit (callers are compiled without FMA contraction).
+__host__ __device__ inline void octQuantizeNormal(float n[3])
+{
+  // octEncode: project to the octahedron, wrap the bottom hemisphere
+  const float inv = 1.0f / ((fabsf(n[0]) + fabsf(n[1])) + fabsf(n[2]));
+  float       px = n[0] * inv, py = n[1] * inv;
+  if(n[2] < 0.0f)
+  {
+    const float wx = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f), wy = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f);
+    px = wx, py = wy;
+  }
+  // octPack / octUnpack: 16 bits per component
+  const float    sx = (px * 0.5f + 0.5f) * 65535.0f, sy = (py * 0.5f + 0.5f) * 65535.0f;
+  const uint32_t ux = static_cast<uint32_t>(fminf(fmaxf(sx, 0.0f), 65535.0f)), uy = static_cast<uint32_t>(fminf(fmaxf(sy, 0.0f), 65535.0f));
+  const float    fx = static_cast<float>(ux) / 65535.0f * 2.0f - 1.0f, fy = static_cast<float>(uy) / 65535.0f * 2.0f - 1.0f;
+  // octDecode
+  float x = fx, y = fy;
+  const float z = (1.0f - fabsf(fx)) - fabsf(fy);
+  if(z < 0.0f)
+  {
+    x = (1.0f - fabsf(fy)) * (fx >= 0.0f ? 1.0f : -1.0f);
+    y = (1.0f - fabsf(fx)) * (fy >= 0.0f ? 1.0f : -1.0f);
+  }
+  const float rn = 1.0f / sqrtf((x * x + y * y) + z * z);
+  n[0] = x * rn, n[1] = y * rn, n[2] = z * rn;
+}
+
 // Fixed-sequence fp32 trigonometry of the fisheye camera (same operation sequences as orc_atan2f_ypos / orc_acosf /
 // orc_sincosf in oracle/vkgs_oracle.c: Cephes single-precision range reductions and polynomials).
 __device__ __forceinline__ float atanNonnegExact(float x)

@@ -128,6 +128,7 @@ extern "C" void vkgs_default_options(vkgs_options* opt)
   opt->pipeline              = VKGS_PIPELINE_3DGS;
   opt->extent_projection     = VKGS_EXTENT_CONIC;  // src/parameters.h:190 (only the 3DGUT pipeline reads it)
   opt->kernel_degree         = 2;                  // KERNEL_DEGREE_QUADRATIC, src/parameters.h:215
+  opt->quantize_normals      = 1;                  // prmRaster.quantizeNormals, src/parameters.h:195 (surface_info only)
 }
 
 extern "C" int vkgs_frame_params_from_camera(const vkgs_camera* cam, uint32_t width, uint32_t height, vkgs_frame_params* out)

@@ -734,7 +734,10 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
       float       nw[4];
       mulVecMat(n4, a.fp.model, nw);
       const float winv = 1.0f / sqrtf((nw[0] * nw[0] + nw[1] * nw[1]) + nw[2] * nw[2]);
-      a.surface[a.idBase + id] = make_float4(nw[0] * winv, nw[1] * winv, nw[2] * winv, ndcDepth);
+      float       nq[3] = {nw[0] * winv, nw[1] * winv, nw[2] * winv};
+      if(a.opt.quantize_normals)  // QUANTIZE_NORMALS: the fragment stage sees the normal through its 2x16-bit octahedral code
+        octQuantizeNormal(nq);
+      a.surface[a.idBase + id] = make_float4(nq[0], nq[1], nq[2], ndcDepth);
     }
   }
 
@@ -859,3 +862,17 @@ void launchPreprocess(const PreprocessArgs& args, cudaStream_t stream)
 }
 
 }  // namespace vkgs
+
+// Host instantiation of the normal quantiser the kernel runs (parity pin without a GPU).
+extern "C" VKGS_API int vkgs_quantize_normals_host(const float* normals_in, float* normals_out, uint64_t count)
+{
+  if(!normals_in || !normals_out)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  for(uint64_t i = 0; i < count; i++)
+  {
+    float n[3] = {normals_in[3 * i], normals_in[3 * i + 1], normals_in[3 * i + 2]};
+    vkgs::octQuantizeNormal(n);
+    normals_out[3 * i] = n[0], normals_out[3 * i + 1] = n[1], normals_out[3 * i + 2] = n[2];
+  }
+  return VKGS_OK;
+}
