@@ -25,7 +25,14 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+
+#include <functional>
+#include <thread>
 
 #include "vkgs_b200.h"
 
@@ -69,6 +76,83 @@ bool readFile(const std::string& path, std::vector<uint8_t>& out)
   return f ? true : failLoad("read error on " + path);
 }
 
+// Read-only view of a whole file: mapped when possible (no copy, no zero fill of a staging vector), read() otherwise.
+class FileBytes
+{
+public:
+  FileBytes() = default;
+  FileBytes(const FileBytes&)            = delete;
+  FileBytes& operator=(const FileBytes&) = delete;
+  ~FileBytes()
+  {
+    if(m_mapped)
+      munmap(const_cast<uint8_t*>(m_data), m_size);
+  }
+  bool open(const std::string& path)
+  {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if(fd < 0)
+      return failLoad("cannot open " + path);
+    struct stat st;
+    if(fstat(fd, &st) != 0 || !S_ISREG(st.st_mode))
+    {
+      ::close(fd);
+      return readFile(path, m_fallback) && adoptFallback();
+    }
+    m_size = static_cast<size_t>(st.st_size);
+    if(m_size == 0)
+    {
+      ::close(fd);
+      m_data = nullptr;
+      return true;
+    }
+    void* p = mmap(nullptr, m_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if(p == MAP_FAILED)
+      return readFile(path, m_fallback) && adoptFallback();
+    madvise(p, m_size, MADV_SEQUENTIAL);
+    m_data   = static_cast<const uint8_t*>(p);
+    m_mapped = true;
+    return true;
+  }
+  const uint8_t* data() const { return m_data; }
+  size_t         size() const { return m_size; }
+  uint8_t        operator[](size_t i) const { return m_data[i]; }
+
+private:
+  bool adoptFallback()
+  {
+    m_data = m_fallback.data(), m_size = m_fallback.size();
+    return true;
+  }
+  const uint8_t*       m_data   = nullptr;
+  size_t               m_size   = 0;
+  bool                 m_mapped = false;
+  std::vector<uint8_t> m_fallback;
+};
+
+// fn(begin, end) over [0, n) on the host's threads (rows of a scene are independent)
+void parallelFor(size_t n, const std::function<void(size_t, size_t)>& fn)
+{
+  const size_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const size_t T  = n < (1u << 16) ? 1 : hw;
+  if(T == 1)
+  {
+    fn(0, n);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t             chunk = (n + T - 1) / T;
+  for(size_t t = 0; t < T; t++)
+  {
+    const size_t b = t * chunk, e = std::min(n, b + chunk);
+    if(b < e)
+      pool.emplace_back([&fn, b, e] { fn(b, e); });
+  }
+  for(std::thread& th : pool)
+    th.join();
+}
+
 // SplatSet::convertCoordinates(RDF, RUB): flipP = (1,-1,-1), flipQ = (1,-1,-1) on (x,y,z), per-coefficient
 // SH signs (spz coordinateConverter with x match, y and z flipped).
 void rdfToRub(vkgs_scene& s)
@@ -78,33 +162,32 @@ void rdfToRub(vkgs_scene& s)
   const float  x = 1.0f, y = -1.0f, z = -1.0f;
   const float  flipSh[15] = {y, z, x, x * y, y * z, 1.0f, x * z, 1.0f, y, x * y * z, y, z, x, z, x};
   const size_t n          = s.positions.size() / 3;
-  for(size_t i = 0; i < s.positions.size(); i += 3)
-  {
-    s.positions[i + 0] *= flipP[0];
-    s.positions[i + 1] *= flipP[1];
-    s.positions[i + 2] *= flipP[2];
-  }
-  for(size_t i = 0; i < s.rotation.size(); i += 4)
-  {
-    s.rotation[i + 1] *= flipQ[0];
-    s.rotation[i + 2] *= flipQ[1];
-    s.rotation[i + 3] *= flipQ[2];
-  }
   if(n == 0)
     return;
   const size_t perPoint = s.f_rest.size() / 3 / n;
-  size_t       idx      = 0;
-  for(size_t i = 0; i < n; ++i)
-  {
-    for(size_t j = 0; j < perPoint && j < 15; ++j)
+  const size_t nRot     = s.rotation.size() / 4;
+  parallelFor(n, [&](size_t b, size_t e) {
+    for(size_t i = b; i < e; ++i)
     {
-      const float flip = flipSh[j];
-      s.f_rest[idx + j] *= flip;
-      s.f_rest[idx + perPoint + j] *= flip;
-      s.f_rest[idx + perPoint * 2 + j] *= flip;
+      s.positions[3 * i + 0] *= flipP[0];
+      s.positions[3 * i + 1] *= flipP[1];
+      s.positions[3 * i + 2] *= flipP[2];
+      if(i < nRot)
+      {
+        s.rotation[4 * i + 1] *= flipQ[0];
+        s.rotation[4 * i + 2] *= flipQ[1];
+        s.rotation[4 * i + 3] *= flipQ[2];
+      }
+      const size_t idx = i * 3 * perPoint;
+      for(size_t j = 0; j < perPoint && j < 15; ++j)
+      {
+        const float flip = flipSh[j];
+        s.f_rest[idx + j] *= flip;
+        s.f_rest[idx + perPoint + j] *= flip;
+        s.f_rest[idx + perPoint * 2 + j] *= flip;
+      }
     }
-    idx += 3 * perPoint;
-  }
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -245,8 +328,8 @@ uint64_t scalarToCount(const uint8_t* p, PlyType t, bool swap)
 
 bool loadPly(const std::string& path, vkgs_scene& out)
 {
-  std::vector<uint8_t> data;
-  if(!readFile(path, data))
+  FileBytes data;
+  if(!data.open(path))
     return false;
   // ---- header ----
   size_t pos = 0;
@@ -399,12 +482,32 @@ bool loadPly(const std::string& path, vkgs_scene& out)
           idx.push_back(k);
         }
         dst.resize(n * names.size());
+        const size_t m = idx.size();
+        bool         plainFloats = format != Ascii && !swap;  // the INRIA layout: native-endian float32 properties
+        for(size_t j = 0; j < m; j++)
+          plainFloats = plainFloats && el.props[idx[j]].type == PlyType::Float;
+        if(plainFloats)
+        {
+          std::vector<size_t> off(m);
+          for(size_t j = 0; j < m; j++)
+            off[j] = el.props[idx[j]].offset;
+          const size_t rowBytes = el.rowBytes;
+          float*       d        = dst.data();
+          parallelFor(n, [&](size_t b, size_t e) {
+            for(size_t i = b; i < e; i++)
+            {
+              const uint8_t* row = base + i * rowBytes;
+              for(size_t j = 0; j < m; j++)
+                std::memcpy(d + i * m + j, row + off[j], 4);
+            }
+          });
+          return true;
+        }
         for(size_t i = 0; i < n; i++)
-          for(size_t j = 0; j < idx.size(); j++)
+          for(size_t j = 0; j < m; j++)
           {
             const PlyProp& pr = el.props[idx[j]];
-            dst[i * idx.size() + j] =
-                format == Ascii ? rows[i * np + idx[j]] : scalarToFloat(base + i * el.rowBytes + pr.offset, pr.type, swap);
+            dst[i * m + j] = format == Ascii ? rows[i * np + idx[j]] : scalarToFloat(base + i * el.rowBytes + pr.offset, pr.type, swap);
           }
         return true;
       };
