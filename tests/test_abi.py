@@ -121,3 +121,9 @@ def test_c_abi_header_is_strict_c99_and_cpp_host_layer_fails_loudly_without_gpu(
     assert r.returncode == 2 and "no CPU fallback" in r.stdout, (r.returncode, r.stdout, r.stderr)
     r = subprocess.run([str(cpp_bin), "--synth", "2000", "--size", "64x64"], capture_output=True, text=True)
     assert r.returncode == 2 and "no sm_100 CUDA device" in r.stderr, (r.returncode, r.stdout, r.stderr)
+    assert "synthetic scene: 2000 splats, SH degree 3" in r.stdout
+    # a scene file goes through SplatSet::loadFromFile (the library's loader) before the device is touched
+    fixture = sorted((root / "tests" / "golden").glob("*.ply"))[0]
+    expect = g.load_scene(str(fixture))
+    r = subprocess.run([str(cpp_bin), str(fixture)], capture_output=True, text=True)
+    assert r.returncode == 2 and f"{expect.size()} splats, SH degree {expect.max_sh_degree()}" in r.stdout, (r.stdout, r.stderr)
