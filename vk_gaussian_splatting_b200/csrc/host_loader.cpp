@@ -689,29 +689,36 @@ bool loadSpz(const std::string& path, vkgs_scene& out)
 
   if(f16)
   {
-    for(size_t i = 0; i < n * 3; i++)
-    {
-      uint16_t h;
-      std::memcpy(&h, pPos + 2 * i, 2);
-      out.positions[i] = halfBitsToFloat(h);
-    }
+    parallelFor(n * 3, [&](size_t b, size_t e) {
+      for(size_t i = b; i < e; i++)
+      {
+        uint16_t h;
+        std::memcpy(&h, pPos + 2 * i, 2);
+        out.positions[i] = halfBitsToFloat(h);
+      }
+    });
   }
   else
   {
     const float scale = static_cast<float>(1.0 / (1 << fractionalBits));
-    for(size_t i = 0; i < n * 3; i++)
-    {
-      int32_t fixed32 = pPos[i * 3 + 0];
-      fixed32 |= pPos[i * 3 + 1] << 8;
-      fixed32 |= pPos[i * 3 + 2] << 16;
-      fixed32 |= (fixed32 & 0x800000) ? 0xff000000 : 0;
-      out.positions[i] = static_cast<float>(fixed32) * scale;
-    }
+    parallelFor(n * 3, [&](size_t b, size_t e) {
+      for(size_t i = b; i < e; i++)
+      {
+        int32_t fixed32 = pPos[i * 3 + 0];
+        fixed32 |= pPos[i * 3 + 1] << 8;
+        fixed32 |= pPos[i * 3 + 2] << 16;
+        fixed32 |= (fixed32 & 0x800000) ? 0xff000000 : 0;
+        out.positions[i] = static_cast<float>(fixed32) * scale;
+      }
+    });
   }
-  for(size_t i = 0; i < n * 3; i++)
-    out.scale[i] = pScl[i] / 16.0f - 10.0f;
+  parallelFor(n * 3, [&](size_t b, size_t e) {
+    for(size_t i = b; i < e; i++)
+      out.scale[i] = pScl[i] / 16.0f - 10.0f;
+  });
   constexpr float sqrt1_2 = static_cast<float>(0.707106781186547524401);
-  for(size_t i = 0; i < n; i++)
+  parallelFor(n, [&](size_t rb, size_t re) {
+  for(size_t i = rb; i < re; i++)
   {
     float q[4];  // x y z w as spz stores them
     if(smallest3)
@@ -750,19 +757,21 @@ bool loadSpz(const std::string& path, vkgs_scene& out)
     out.rotation[4 * i + 2] = q[1];
     out.rotation[4 * i + 3] = q[2];
   }
-  for(size_t i = 0; i < n; i++)
-  {
-    const float a  = pAlp[i] / 255.0f;
-    out.opacity[i] = std::log(a / (1.0f - a));  // invSigmoid
-  }
+  });
   constexpr float colorScale = 0.15f;
-  for(size_t i = 0; i < n * 3; i++)
-    out.f_dc[i] = ((pCol[i] / 255.0f) - 0.5f) / colorScale;
-  // SH: spz keeps RGB inner per coefficient; SplatSet wants channel-major per splat (:326-346)
-  for(size_t i = 0; i < n; i++)
-    for(size_t j = 0; j < shDim; j++)
+  parallelFor(n, [&](size_t b, size_t e) {
+    for(size_t i = b; i < e; i++)
+    {
+      const float a  = pAlp[i] / 255.0f;
+      out.opacity[i] = std::log(a / (1.0f - a));  // invSigmoid
       for(size_t c = 0; c < 3; c++)
-        out.f_rest[i * shDim * 3 + c * shDim + j] = (static_cast<float>(pSh[(i * shDim + j) * 3 + c]) - 128.0f) / 128.0f;
+        out.f_dc[3 * i + c] = ((pCol[3 * i + c] / 255.0f) - 0.5f) / colorScale;
+      // SH: spz keeps RGB inner per coefficient; SplatSet wants channel-major per splat (:326-346)
+      for(size_t j = 0; j < shDim; j++)
+        for(size_t c = 0; c < 3; c++)
+          out.f_rest[i * shDim * 3 + c * shDim + j] = (static_cast<float>(pSh[(i * shDim + j) * 3 + c]) - 128.0f) / 128.0f;
+    }
+  });
   return true;
 }
 
