@@ -127,3 +127,31 @@ def test_c_abi_header_is_strict_c99_and_cpp_host_layer_fails_loudly_without_gpu(
     expect = g.load_scene(str(fixture))
     r = subprocess.run([str(cpp_bin), str(fixture)], capture_output=True, text=True)
     assert r.returncode == 2 and f"{expect.size()} splats, SH degree {expect.max_sh_degree()}" in r.stdout, (r.stdout, r.stderr)
+
+
+def test_product_never_reaches_into_the_oracle():
+    """oracle/ is test infrastructure: no Python module of the package imports it, no product source includes a file from it
+    (comments may name it), and the shared library neither links nor dlopens it. Only tests/, __graft_entry__.smoke() and
+    bench.py's CPU-baseline legs may use it."""
+    import subprocess
+    root = Path(__file__).resolve().parents[1]
+    pkg = root / "vk_gaussian_splatting_b200"
+    for py in pkg.glob("*.py"):
+        for line in py.read_text().splitlines():
+            code = line.split("#", 1)[0]
+            if py.name == "build.py" and ("oracle" in code):
+                continue  # build_oracle() compiles the checker; compiling is not using
+            assert not re.search(r"\b(import|from)\s+oracle\b", code) and "libvkgs_oracle" not in code, (py.name, line)
+    for src in list((pkg / "csrc").iterdir()) + list((root / "include").iterdir()) + list((root / "examples").glob("*.c*")):
+        for line in src.read_text().splitlines():
+            if line.lstrip().startswith("#include"):
+                assert "oracle" not in line, (src.name, line)
+    lib = pkg / "lib" / "libvkgs_b200.so"
+    needed = subprocess.run(["readelf", "-d", str(lib)], capture_output=True, text=True).stdout
+    assert "NEEDED" in needed and "oracle" not in needed
+    blob = lib.read_bytes()
+    assert b"libvkgs_oracle" not in blob and b"orc_render" not in blob
+    # bench.py touches it only inside the cpu-baseline / reference-arm functions
+    bench = (root / "bench.py").read_text()
+    for m in re.finditer(r"^(\s*)from oracle import", bench, re.M):
+        assert len(m.group(1)) >= 4, "oracle imports in bench.py must be local to the baseline functions"
