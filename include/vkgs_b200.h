@@ -321,6 +321,10 @@ VKGS_API int vkgs_read_surface_info(vkgs_ctx* ctx, float* normals, float* depth_
 /* The QUANTIZE_NORMALS round trip (encodeNormalOctahedral -> decodeNormalOctahedral, shaders/octahedral_normal.h.slang) on
  * `count` unit normals, host arrays [3*count]; host only, no GPU needed (the kernel runs the same function). */
 VKGS_API int vkgs_quantize_normals_host(const float* normals_in, float* normals_out, uint64_t count);
+/* Host instantiations of the fixed-sequence fp32 elementary functions the kernels run at their discard / cull decisions
+ * (the reference's are driver intrinsics): which = 0 exp(a); 1 atan2(a = y > 0, b = x); 2 acos(a); 3 sin(a) -> out,
+ * cos(a) -> out2. Host only, no GPU needed; pinned bit for bit against the oracle in tests/test_oracle_kat.py. */
+VKGS_API int vkgs_exact_math_host(uint32_t which, const float* a, const float* b, float* out, float* out2, uint64_t count);
 
 /* ---- parity/debug read-backs of per-splat intermediates of the last frame ----------------
  * Per-splat record, indexed by splat id (only ids that passed the dist-stage cull are valid):

@@ -481,3 +481,51 @@ def test_octahedral_normal_quantisation_known_answers_and_host_kernel_function()
     _, nq, _, _, _ = O.render_surface(pk, s.rotation, fp, O.default_options(front_to_back=1))
     _, nf, _, _, _ = O.render_surface(pk, s.rotation, fp, O.default_options(front_to_back=1, quantize_normals=0))
     assert 0 < np.abs(nq - nf).max() < 3e-4
+
+
+def test_kernel_exact_math_host_instantiations_equal_the_oracle_bitwise():
+    """The fixed-sequence exp / atan2 / acos / sin / cos the kernels run at their discard and cull decisions are
+    host+device functions (csrc/device_common.cuh: round-to-nearest intrinsics on the device, the same IEEE operators on
+    the host); their host instantiations must equal the oracle's restatements bit for bit over the whole domain the
+    path uses. (Together with the GPU parity tests this pins both halves: same source on host and device, same bits
+    as the oracle on the host.)"""
+    l, ol = A.lib(), O.lib()
+    f32p = C.POINTER(C.c_float)
+    rng = np.random.default_rng(29)
+
+    def run(which, a, b=None):
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32) if b is not None else None
+        out, out2 = np.empty_like(a), np.empty_like(a)
+        rc = l.vkgs_exact_math_host(which, a.ctypes.data_as(f32p), b.ctypes.data_as(f32p) if b is not None else None,
+                                    out.ctypes.data_as(f32p), out2.ctypes.data_as(f32p), len(a))
+        assert rc == 0
+        return out, out2
+
+    # exp: the fragment domain [-4, 0], the kernel-degree domains, and the clamped tails
+    x = np.concatenate([rng.uniform(-4.5, 0.0, 100_000), rng.uniform(-90, 90, 50_000), [0.0, -0.0, -87.0, 88.0, -1e9, 1e9]]).astype(np.float32)
+    got, _ = run(0, x)
+    ref = np.array([ol.orc_expf(float(v)) for v in x], np.float32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # atan2(y > 0, x)
+    y = (10.0 ** rng.uniform(-7, 4, 100_000)).astype(np.float32)
+    xx = (rng.choice([-1.0, 1.0], 100_000) * 10.0 ** rng.uniform(-7, 4, 100_000)).astype(np.float32)
+    xx[:100] = 0.0
+    got, _ = run(1, y, xx)
+    ref = np.array([ol.orc_atan2f_ypos(float(a), float(b)) for a, b in zip(y, xx)], np.float32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # acos on [-1, 1]
+    c = np.concatenate([rng.uniform(-1, 1, 100_000), [-1.0, 1.0, 0.0, 0.5, -0.5]]).astype(np.float32)
+    got, _ = run(2, c)
+    ref = np.array([ol.orc_acosf(float(v)) for v in c], np.float32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # sin / cos: angles of the fisheye ray (|phi| <= pi, theta <= pi) and beyond
+    t = np.concatenate([rng.uniform(-np.pi, np.pi, 100_000), rng.uniform(-100, 100, 20_000), [0.0, -0.0]]).astype(np.float32)
+    gs, gc = run(3, t)
+    s_, c_ = np.zeros(1, np.float32), np.zeros(1, np.float32)
+    rs, rc_ = np.empty_like(t), np.empty_like(t)
+    for i, v in enumerate(t):
+        ol.orc_sincosf(float(v), s_.ctypes.data_as(f32p), c_.ctypes.data_as(f32p))
+        rs[i], rc_[i] = s_[0], c_[0]
+    assert np.array_equal(gs.view(np.uint32), rs.view(np.uint32)) and np.array_equal(gc.view(np.uint32), rc_.view(np.uint32))
+    assert l.vkgs_exact_math_host(7, t.ctypes.data_as(f32p), None, gs.ctypes.data_as(f32p), None, 1) == A.VKGS_ERR_INVALID_ARGUMENT

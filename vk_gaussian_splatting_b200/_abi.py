@@ -105,6 +105,7 @@ SYMBOLS = {
     "vkgs_default_camera": (None, [C.POINTER(Camera)]),
     "vkgs_frame_params_set_fisheye": (None, [C.POINTER(FrameParams)]),
     "vkgs_quantize_normals_host": (C.c_int, [f32p, f32p, C.c_uint64]),
+    "vkgs_exact_math_host": (C.c_int, [C.c_uint32, f32p, f32p, f32p, f32p, C.c_uint64]),
     "vkgs_render": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.POINTER(Outputs)]),
     "vkgs_render_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams)]),
     "vkgs_render_to_host_async": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), C.c_void_p]),

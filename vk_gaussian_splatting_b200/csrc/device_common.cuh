@@ -3,7 +3,9 @@
 //   * epoch-stamped decoupled look-back status words (no per-frame zeroing)
 //   * warp / block scan helpers
 #pragma once
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 
 namespace vkgs {
@@ -193,24 +195,54 @@ __device__ __forceinline__ unsigned match_digit(unsigned active, uint32_t digit)
   return peers;
 }
 
+// ---- exact fp32 building blocks ---------------------------------------------------------------------------------
+// The decision-critical elementary functions below run on the device with explicit round-to-nearest intrinsics (immune
+// to FMA contraction, whatever the file's -fmad setting) and on the host with the plain operators (host code of this
+// library is compiled with -ffp-contract=off): the same IEEE operations in the same order. The host instantiations are
+// exported through vkgs_exact_math_host so that tests/test_oracle_kat.py can pin the functions the kernels run against
+// the oracle bit for bit on a machine without a GPU.
+#ifdef __CUDA_ARCH__
+#define VKGS_FMA(a, b, c) __fmaf_rn(a, b, c)
+#define VKGS_MUL(a, b) __fmul_rn(a, b)
+#define VKGS_ADD(a, b) __fadd_rn(a, b)
+#define VKGS_SUB(a, b) __fsub_rn(a, b)
+#define VKGS_DIV(a, b) __fdiv_rn(a, b)
+#define VKGS_SQRT(a) __fsqrt_rn(a)
+#define VKGS_U2F(u) __uint_as_float(u)
+#else
+__host__ inline float vkgsHostU2F(uint32_t u)
+{
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+#define VKGS_FMA(a, b, c) fmaf(a, b, c)
+#define VKGS_MUL(a, b) ((a) * (b))
+#define VKGS_ADD(a, b) ((a) + (b))
+#define VKGS_SUB(a, b) ((a) - (b))
+#define VKGS_DIV(a, b) ((a) / (b))
+#define VKGS_SQRT(a) sqrtf(a)
+#define VKGS_U2F(u) vkgsHostU2F(u)
+#endif
+
 // Same operation sequence as orc_expf (oracle/vkgs_oracle.c): Cody-Waite + Cephes polynomial.
-__device__ __forceinline__ float expfExact(float x)
+__host__ __device__ __forceinline__ float expfExact(float x)
 {
   x              = fminf(fmaxf(x, -87.0f), 88.0f);
-  const float kf = rintf(__fmul_rn(x, 1.44269504088896341f));
-  float       r  = __fmaf_rn(-kf, 0.693359375f, x);
-  r              = __fmaf_rn(-kf, -2.12194440e-4f, r);
+  const float kf = rintf(VKGS_MUL(x, 1.44269504088896341f));
+  float       r  = VKGS_FMA(-kf, 0.693359375f, x);
+  r              = VKGS_FMA(-kf, -2.12194440e-4f, r);
   float p        = 1.9875691500e-4f;
-  p              = __fmaf_rn(p, r, 1.3981999507e-3f);
-  p              = __fmaf_rn(p, r, 8.3334519073e-3f);
-  p              = __fmaf_rn(p, r, 4.1665795894e-2f);
-  p              = __fmaf_rn(p, r, 1.6666665459e-1f);
-  p              = __fmaf_rn(p, r, 5.0000001201e-1f);
-  const float r2 = __fmul_rn(r, r);
-  float       e  = __fmaf_rn(p, r2, r);
-  e              = __fadd_rn(e, 1.0f);
+  p              = VKGS_FMA(p, r, 1.3981999507e-3f);
+  p              = VKGS_FMA(p, r, 8.3334519073e-3f);
+  p              = VKGS_FMA(p, r, 4.1665795894e-2f);
+  p              = VKGS_FMA(p, r, 1.6666665459e-1f);
+  p              = VKGS_FMA(p, r, 5.0000001201e-1f);
+  const float r2 = VKGS_MUL(r, r);
+  float       e  = VKGS_FMA(p, r2, r);
+  e              = VKGS_ADD(e, 1.0f);
   const int   k  = static_cast<int>(kf);
-  return __fmul_rn(e, __uint_as_float(static_cast<uint32_t>(k + 127) << 23));
+  return VKGS_MUL(e, VKGS_U2F(static_cast<uint32_t>(k + 127) << 23));
 }
 
 // QUANTIZE_NORMALS: encodeNormalOctahedral -> decodeNormalOctahedral (shaders/octahedral_normal.h.slang:28-85), the
@@ -244,73 +276,73 @@ __host__ __device__ inline void octQuantizeNormal(float n[3])
 
 // Fixed-sequence fp32 trigonometry of the fisheye camera (same operation sequences as orc_atan2f_ypos / orc_acosf /
 // orc_sincosf in oracle/vkgs_oracle.c: Cephes single-precision range reductions and polynomials).
-__device__ __forceinline__ float atanNonnegExact(float x)
+__host__ __device__ __forceinline__ float atanNonnegExact(float x)
 {
   float y0 = 0.0f;
   if(x > 2.414213562373095f)
   {
     y0 = 1.57079632679489661923f;
-    x  = -__fdiv_rn(1.0f, x);
+    x  = -VKGS_DIV(1.0f, x);
   }
   else if(x > 0.4142135623730950f)
   {
     y0 = 0.78539816339744830962f;
-    x  = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f));
+    x  = VKGS_DIV(VKGS_SUB(x, 1.0f), VKGS_ADD(x, 1.0f));
   }
-  const float z = __fmul_rn(x, x);
+  const float z = VKGS_MUL(x, x);
   float       p = 8.05374449538e-2f;
-  p             = __fmaf_rn(p, z, -1.38776856032e-1f);
-  p             = __fmaf_rn(p, z, 1.99777106478e-1f);
-  p             = __fmaf_rn(p, z, -3.33329491539e-1f);
-  return __fadd_rn(y0, __fmaf_rn(__fmul_rn(p, z), x, x));
+  p             = VKGS_FMA(p, z, -1.38776856032e-1f);
+  p             = VKGS_FMA(p, z, 1.99777106478e-1f);
+  p             = VKGS_FMA(p, z, -3.33329491539e-1f);
+  return VKGS_ADD(y0, VKGS_FMA(VKGS_MUL(p, z), x, x));
 }
 
-__device__ __forceinline__ float atan2fYposExact(float y, float x)  // y > 0
+__host__ __device__ __forceinline__ float atan2fYposExact(float y, float x)  // y > 0
 {
   if(x == 0.0f)
     return 1.57079632679489661923f;
-  const float t = __fdiv_rn(y, x);
-  return x > 0.0f ? atanNonnegExact(t) : __fsub_rn(3.14159265358979323846f, atanNonnegExact(-t));
+  const float t = VKGS_DIV(y, x);
+  return x > 0.0f ? atanNonnegExact(t) : VKGS_SUB(3.14159265358979323846f, atanNonnegExact(-t));
 }
 
-__device__ __forceinline__ float asinSmallExact(float x)  // |x| <= 0.5
+__host__ __device__ __forceinline__ float asinSmallExact(float x)  // |x| <= 0.5
 {
-  const float z = __fmul_rn(x, x);
+  const float z = VKGS_MUL(x, x);
   float       p = 4.2163199048e-2f;
-  p             = __fmaf_rn(p, z, 2.4181311049e-2f);
-  p             = __fmaf_rn(p, z, 4.5470025998e-2f);
-  p             = __fmaf_rn(p, z, 7.4953002686e-2f);
-  p             = __fmaf_rn(p, z, 1.6666752422e-1f);
-  return __fmaf_rn(__fmul_rn(p, z), x, x);
+  p             = VKGS_FMA(p, z, 2.4181311049e-2f);
+  p             = VKGS_FMA(p, z, 4.5470025998e-2f);
+  p             = VKGS_FMA(p, z, 7.4953002686e-2f);
+  p             = VKGS_FMA(p, z, 1.6666752422e-1f);
+  return VKGS_FMA(VKGS_MUL(p, z), x, x);
 }
 
-__device__ __forceinline__ float acosfExact(float x)  // x in [-1, 1]
+__host__ __device__ __forceinline__ float acosfExact(float x)  // x in [-1, 1]
 {
   if(x > 0.5f)
-    return __fmul_rn(2.0f, asinSmallExact(__fsqrt_rn(__fmul_rn(0.5f, __fsub_rn(1.0f, x)))));
+    return VKGS_MUL(2.0f, asinSmallExact(VKGS_SQRT(VKGS_MUL(0.5f, VKGS_SUB(1.0f, x)))));
   if(x < -0.5f)
-    return __fsub_rn(3.14159265358979323846f, __fmul_rn(2.0f, asinSmallExact(__fsqrt_rn(__fmul_rn(0.5f, __fadd_rn(1.0f, x))))));
-  return __fsub_rn(1.57079632679489661923f, asinSmallExact(x));
+    return VKGS_SUB(3.14159265358979323846f, VKGS_MUL(2.0f, asinSmallExact(VKGS_SQRT(VKGS_MUL(0.5f, VKGS_ADD(1.0f, x))))));
+  return VKGS_SUB(1.57079632679489661923f, asinSmallExact(x));
 }
 
-__device__ __forceinline__ void sincosfExact(float xx, float& sOut, float& cOut)  // |xx| < 8192
+__host__ __device__ __forceinline__ void sincosfExact(float xx, float& sOut, float& cOut)  // |xx| < 8192
 {
   float    x = fabsf(xx);
-  uint32_t j = static_cast<uint32_t>(__fmul_rn(x, 1.27323954473516f));
+  uint32_t j = static_cast<uint32_t>(VKGS_MUL(x, 1.27323954473516f));
   j          = (j + 1u) & ~1u;
   const float y = static_cast<float>(j);
-  x             = __fmaf_rn(-y, 0.78515625f, x);
-  x             = __fmaf_rn(-y, 2.4187564849853515625e-4f, x);
-  x             = __fmaf_rn(-y, 3.77489497744594108e-8f, x);
-  const float z = __fmul_rn(x, x);
+  x             = VKGS_FMA(-y, 0.78515625f, x);
+  x             = VKGS_FMA(-y, 2.4187564849853515625e-4f, x);
+  x             = VKGS_FMA(-y, 3.77489497744594108e-8f, x);
+  const float z = VKGS_MUL(x, x);
   float       ps = -1.9515295891e-4f;
-  ps             = __fmaf_rn(ps, z, 8.3321608736e-3f);
-  ps             = __fmaf_rn(ps, z, -1.6666654611e-1f);
-  const float sp = __fmaf_rn(__fmul_rn(ps, z), x, x);
+  ps             = VKGS_FMA(ps, z, 8.3321608736e-3f);
+  ps             = VKGS_FMA(ps, z, -1.6666654611e-1f);
+  const float sp = VKGS_FMA(VKGS_MUL(ps, z), x, x);
   float       pc = 2.443315711809948e-5f;
-  pc             = __fmaf_rn(pc, z, -1.388731625493765e-3f);
-  pc             = __fmaf_rn(pc, z, 4.166664568298827e-2f);
-  const float cp = __fmaf_rn(pc, __fmul_rn(z, z), __fmaf_rn(-0.5f, z, 1.0f));
+  pc             = VKGS_FMA(pc, z, -1.388731625493765e-3f);
+  pc             = VKGS_FMA(pc, z, 4.166664568298827e-2f);
+  const float cp = VKGS_FMA(pc, VKGS_MUL(z, z), VKGS_FMA(-0.5f, z, 1.0f));
   float       s, c;
   switch((j >> 1) & 3u)
   {

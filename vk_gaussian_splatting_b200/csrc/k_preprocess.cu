@@ -876,3 +876,22 @@ extern "C" VKGS_API int vkgs_quantize_normals_host(const float* normals_in, floa
   }
   return VKGS_OK;
 }
+
+// Host instantiations of the fixed-sequence elementary functions the kernels run (parity pin without a GPU):
+// which = 0 expfExact(a), 1 atan2fYposExact(a = y > 0, b = x), 2 acosfExact(a), 3 sincosfExact(a) -> out = sin, out2 = cos.
+extern "C" VKGS_API int vkgs_exact_math_host(uint32_t which, const float* a, const float* b, float* out, float* out2, uint64_t count)
+{
+  if(!a || !out || which > 3u || (which == 1u && !b) || (which == 3u && !out2))
+    return VKGS_ERR_INVALID_ARGUMENT;
+  for(uint64_t i = 0; i < count; i++)
+  {
+    switch(which)
+    {
+      case 0: out[i] = vkgs::expfExact(a[i]); break;
+      case 1: out[i] = vkgs::atan2fYposExact(a[i], b[i]); break;
+      case 2: out[i] = vkgs::acosfExact(a[i]); break;
+      default: vkgs::sincosfExact(a[i], out[i], out2[i]); break;
+    }
+  }
+  return VKGS_OK;
+}
