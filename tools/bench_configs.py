@@ -9,14 +9,14 @@ PEAK = 6538.6
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 r = g.GaussianSplatting(0, stream=stream.cuda_stream)
 
-def run(name, n, w, h, seed, steps=100, **optkw):
+def run(name, n, w, h, seed, steps=100, fisheye=False, **optkw):
     t0 = time.time()
     s = g.synth_scene(n, 3, seed)
     t_gen = time.time() - t0
     t0 = time.time()
-    r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0 ** -15, **optkw))
+    r.upload(s, g.default_options(**{"front_to_back": 1, "transmittance_epsilon": 2.0 ** -15, **optkw}))
     t_up = time.time() - t0
-    fp = g.frame_params(g.default_camera(), w, h)
+    fp = g.frame_params(g.default_camera(), w, h, fisheye=fisheye)
     r.set_frames_in_flight(2)
     for _ in range(5): r.render_async(fp)
     r.sync()
@@ -43,6 +43,11 @@ if "2" in which: run("cfg2 1M SH3 1080p", 1_000_000, 1920, 1080, 0x3D650001, 200
 if "3" in which: run("cfg3 6M SH3 4K", 6_000_000, 3840, 2160, 0x3D650002, 50)
 if "5" in which: run("cfg5 30M SH3 1080p", 30_000_000, 1920, 1080, 0x3D650004, 20)
 if "gut" in which: run("cfg2 1M SH3 1080p VK3DGUT pipeline", 1_000_000, 1920, 1080, 0x3D650001, 100, pipeline=1)
+# the general 3DGUT blend instantiation (EXTENT_EIGEN quads / fisheye camera), same frame
+if "gutx" in which:
+    run("cfg2 1M SH3 1080p VK3DGUT, EXTENT_EIGEN", 1_000_000, 1920, 1080, 0x3D650001, 100, pipeline=1, extent_projection=0)
+    run("cfg2 1M SH3 1080p VK3DGUT, fisheye camera", 1_000_000, 1920, 1080, 0x3D650001, 100, pipeline=1, camera_model=1, fisheye=True)
+    run("cfg2 1M SH3 1080p back-to-front (reference default order)", 1_000_000, 1920, 1080, 0x3D650001, 100, front_to_back=0)
 if "surf" in which: run("cfg2 1M SH3 1080p + surface info", 1_000_000, 1920, 1080, 0x3D650001, 100, surface_info=1)
 if "sort" in which:
     rng = np.random.default_rng(5)

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ --launch-skip 20 --launch-count 10 -f -o gpurun_out/${tag}_full \
     python tools/prof_preprocess.py > gpurun_out/${tag}_ncu_full.log 2>&1
-python tools/bench_configs.py 2 3 5 sort gut surf > gpurun_out/${tag}_configs.jsonl 2>&1
+python tools/bench_configs.py 2 3 5 sort gut gutx surf > gpurun_out/${tag}_configs.jsonl 2>&1
 # the C++ host driver over the C ABI (include/vkgs_b200.hpp)
 L=$PWD/vk_gaussian_splatting_b200/lib
 g++ -std=c++17 -Iinclude examples/render_host.cpp -L$L -lvkgs_b200 -Wl,-rpath,$L -o gpurun_out/render_host \
