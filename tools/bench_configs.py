@@ -2,7 +2,7 @@
 bench contract — that is bench.py; this feeds the tables in DESIGN.md / profiles/)."""
 import json, sys, time
 import numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))  # this checkout
 import vk_gaussian_splatting_b200 as g
 
 PEAK = 6538.6
