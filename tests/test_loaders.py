@@ -130,3 +130,15 @@ def test_truncated_and_corrupted_files_fail_cleanly():
                     assert e.code == A.VKGS_ERR_IO
                     outcomes["err"] += 1
     assert outcomes["err"] >= len(files) * 5  # every truncation is rejected
+
+
+def test_header_promising_more_vertices_than_memory_is_an_error_not_an_abort(tmp_path):
+    """No exception crosses the C ABI: an ascii header with 2^40 vertices ends in VKGS_ERR_IO (bad_alloc caught at the boundary)."""
+    from vk_gaussian_splatting_b200 import _abi as A
+    props = ["x", "y", "z", "opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3", "f_dc_0", "f_dc_1", "f_dc_2"]
+    hdr = "ply\nformat ascii 1.0\nelement vertex 1099511627776\n" + "".join(f"property float {p}\n" for p in props) + "end_header\n1 2 3\n"
+    path = tmp_path / "huge.ply"
+    path.write_bytes(hdr.encode())
+    with pytest.raises(g.VkgsError) as e:
+        g.load_scene(path)
+    assert e.value.code == A.VKGS_ERR_IO

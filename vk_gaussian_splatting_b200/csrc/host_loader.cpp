@@ -789,12 +789,19 @@ int vkgs_scene_load(const char* path, vkgs_scene** out)
   const std::string p   = path;
   const std::string ext = lowerExt(p);
   bool              ok  = false;
-  if(ext == ".splat")
-    ok = loadSplat(p, *s);
-  else if(ext == ".spz")
-    ok = loadSpz(p, *s);
-  else
-    ok = loadPly(p, *s);
+  try  // no exception crosses the C ABI (a header that promises 2^40 vertices ends in bad_alloc, not in terminate)
+  {
+    if(ext == ".splat")
+      ok = loadSplat(p, *s);
+    else if(ext == ".spz")
+      ok = loadSpz(p, *s);
+    else
+      ok = loadPly(p, *s);
+  }
+  catch(const std::exception& e)
+  {
+    ok = failLoad(std::string("loading ") + p + " failed: " + e.what());
+  }
   if(!ok)
   {
     delete s;
