@@ -40,6 +40,7 @@ extern "C" {
 #define VKGS_ERR_OVERFLOW (-5)      /* tile-list capacity exceeded even after regrow */
 #define VKGS_ERR_UNSUPPORTED (-6)   /* option outside the hot-path scope */
 #define VKGS_ERR_IO (-7)            /* loader: file missing / malformed */
+#define VKGS_ERR_OUT_OF_MEMORY (-8) /* a host allocation failed while packing / staging (no exception crosses the ABI) */
 
 /* value sets = the reference's shader macros (shaders/shaderio.h:23-103) */
 #define VKGS_FORMAT_FLOAT32 0

@@ -20,6 +20,7 @@ VKGS_ERR_NOT_UPLOADED = -4
 VKGS_ERR_OVERFLOW = -5
 VKGS_ERR_UNSUPPORTED = -6
 VKGS_ERR_IO = -7
+VKGS_ERR_OUT_OF_MEMORY = -8
 
 FORMAT_FLOAT32, FORMAT_FLOAT16, FORMAT_UINT8 = 0, 1, 2
 FRUSTUM_CULLING_NONE, FRUSTUM_CULLING_AT_DIST, FRUSTUM_CULLING_AT_RASTER = 0, 1, 2

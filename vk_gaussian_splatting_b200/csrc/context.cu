@@ -497,18 +497,25 @@ int vkgs_pack_host(const vkgs_splat_set_view* set, const vkgs_options* optIn, fl
     opt = *optIn;
   else
     vkgs_default_options(&opt);
-  PackedSplatSet packed;
-  if(int rc = packSplatSet(*set, opt, 1, packed))
-    return rc;
-  const uint64_t n = packed.count;
-  if(centers)
-    std::memcpy(centers, packed.centers.data(), n * 12);
-  if(cov6)
-    std::memcpy(cov6, packed.cov6.data(), n * 24);
-  if(rgba)
-    std::memcpy(rgba, packed.rgba.data(), n * 4 * formatSize(opt.rgba_format));
-  if(sh && packed.shDegree)
-    std::memcpy(sh, packed.sh.data(), n * 45 * formatSize(opt.sh_format));
+  try
+  {
+    PackedSplatSet packed;
+    if(int rc = packSplatSet(*set, opt, 1, packed))
+      return rc;
+    const uint64_t n = packed.count;
+    if(centers)
+      std::memcpy(centers, packed.centers.data(), n * 12);
+    if(cov6)
+      std::memcpy(cov6, packed.cov6.data(), n * 24);
+    if(rgba)
+      std::memcpy(rgba, packed.rgba.data(), n * 4 * formatSize(opt.rgba_format));
+    if(sh && packed.shDegree)
+      std::memcpy(sh, packed.sh.data(), n * 45 * formatSize(opt.sh_format));
+  }
+  catch(const std::exception&)
+  {
+    return VKGS_ERR_OUT_OF_MEMORY;
+  }
   return VKGS_OK;
 }
 
@@ -761,7 +768,14 @@ int vkgs_upload(vkgs_ctx* c, const vkgs_splat_set_view* set, const vkgs_options*
 {
   if(!c || !set)
     return VKGS_ERR_INVALID_ARGUMENT;
-  return uploadScene(c, set, 1, nullptr, 0, optIn);
+  try
+  {
+    return uploadScene(c, set, 1, nullptr, 0, optIn);
+  }
+  catch(const std::exception& e)
+  {
+    return fail(c, VKGS_ERR_OUT_OF_MEMORY, (std::string("host allocation failed while packing the scene: ") + e.what()).c_str());
+  }
 }
 
 int vkgs_upload_scene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t set_count, const vkgs_instance* instances,
@@ -769,7 +783,14 @@ int vkgs_upload_scene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t set
 {
   if(!c || !sets || !instances)
     return VKGS_ERR_INVALID_ARGUMENT;
-  return uploadScene(c, sets, set_count, instances, instance_count, optIn);
+  try
+  {
+    return uploadScene(c, sets, set_count, instances, instance_count, optIn);
+  }
+  catch(const std::exception& e)
+  {
+    return fail(c, VKGS_ERR_OUT_OF_MEMORY, (std::string("host allocation failed while packing the scene: ") + e.what()).c_str());
+  }
 }
 
 int vkgs_set_instance_transform(vkgs_ctx* c, uint32_t instance, const float* transform, const float* transform_inverse)
