@@ -112,6 +112,24 @@ def test_c_abi_header_is_strict_c99_and_cpp_host_layer_fails_loudly_without_gpu(
     c_bin, cpp_bin = tmp_path / "abi_from_c", tmp_path / "render_host"
     _compile(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", str(root / "examples" / "abi_from_c.c"), "-o", str(c_bin)] + link)
     _compile(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", str(root / "examples" / "render_host.cpp"), "-o", str(cpp_bin)] + link)
+    # every member of the header-only layer instantiates (the example does not use the multi-instance overload)
+    allm = tmp_path / "all_members.cpp"
+    allm.write_text("""#include "vkgs_b200.hpp"
+int main() {
+  vkgs_b200::SplatSet a, b; a.synthesize(8, 3, 1); b.synthesize(4, 0, 2);
+  vkgs_b200::GaussianSplatting gs; gs.onResize(64, 48);
+  vkgs_instance inst[2] = {}; inst[0].splat_set_index = 0; inst[1].splat_set_index = 1;
+  for(auto& i : inst) for(int k = 0; k < 4; k++) i.transform[5 * k] = i.transform_inverse[5 * k] = 1.0f;
+  bool ok = gs.initDataStorage({&a, &b}, {inst[0], inst[1]});   // no context attached: must fail cleanly
+  vkgs_camera cam; vkgs_default_camera(&cam);
+  ok = gs.updateAndUploadFrameInfoUBO(cam) && ok;
+  ok = gs.onRenderAsync() || gs.sync() || gs.lastFrameStats(nullptr) || ok;
+  return (a.size() == 8 && a.maxShDegree() == 3 && b.maxShDegree() == 0 && !ok && !gs.lastError().empty()) ? 0 : 1;
+}
+""")
+    all_bin = tmp_path / "all_members"
+    _compile(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", str(allm), "-o", str(all_bin)] + link)
+    assert subprocess.run([str(all_bin)]).returncode == 0
     # bad arguments / unreadable scene: exit 3 before any device work
     r = subprocess.run([str(cpp_bin), str(tmp_path / "missing.ply")], capture_output=True, text=True)
     assert r.returncode == 3 and "cannot load" in r.stderr
