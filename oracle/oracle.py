@@ -267,6 +267,22 @@ def render_surface(packed: Packed, rotation, fp, opt):
     return img, nrm, dt, sid, ids[:v].copy()
 
 
+def render_gut_surface(packed: Packed, rotation, fp, opt):
+    """VK3DGUT front-to-back frame with the surface-info side outputs (groundwork: the CUDA path does not build this
+    combination yet). Returns (image, normals [H,W,4], depth_transmittance [H,W,2], splat_id [H,W], sorted_ids)."""
+    h, w = fp.height, fp.width
+    img, nrm = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    dt, sid = np.zeros((h, w, 2), np.float32), np.zeros((h, w), np.uint32)
+    ids = np.empty(packed.n, np.uint32)
+    rot = np.ascontiguousarray(rotation, np.float32)
+    fn = lib().orc_render_gut_surface
+    fn.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p, f32p, f32p, u32p, u32p]
+    fn.restype = C.c_uint32
+    v = fn(_p(packed.centers), _p(packed.rgba), _p(packed.sh), _p(packed.scale), _p(rot), packed.n, packed.sh_degree, C.byref(fp),
+           C.byref(opt), _p(img), _p(nrm), _p(dt), _u(sid), _u(ids))
+    return img, nrm, dt, sid, ids[:v].copy()
+
+
 def image_metrics(reference, current, flip_mode=0):
     """(mse_fixed, flip_fixed, mse, psnr, flip): the shader's accumulators + the read-back arithmetic of
     src/image_compare.cpp:874-905."""

@@ -529,3 +529,41 @@ def test_kernel_exact_math_host_instantiations_equal_the_oracle_bitwise():
         rs[i], rc_[i] = s_[0], c_[0]
     assert np.array_equal(gs.view(np.uint32), rs.view(np.uint32)) and np.array_equal(gc.view(np.uint32), rc_.view(np.uint32))
     assert l.vkgs_exact_math_host(7, t.ctypes.data_as(f32p), None, gs.ctypes.data_as(f32p), None, 1) == A.VKGS_ERR_INVALID_ARGUMENT
+
+
+def test_3dgut_surface_outputs_known_answers():
+    """Oracle groundwork for NEED_SURFACE_INFO on the VK3DGUT pipeline (threedgut_raster.frag.slang:129-133,194-222,
+    particleProcessHitGutWithNormal): the colour frame equals the plain 3DGUT frame; normal.a == colour.a and T == 1 - alpha;
+    the fragment normal of a regular or flat particle is the per-splat max-density-plane normal of the 3DGS surface pass
+    (it depends on the ray origin only), a needle takes minus its own ray direction; depth is picked where T < 0.7."""
+    cam = g.default_camera()
+    w, h = 96, 96
+    fp = O.frame_params(cam, w, h)
+    opt = O.default_gut_options(front_to_back=1)
+
+    def one(scale):
+        s = g.SplatSet(np.zeros((1, 3)), np.ones((1, 3)), np.zeros((1, 0)), np.array([6.0]), np.log(np.array([scale], np.float32)),
+                       np.array([[0.9, 0.1, -0.3, 0.2]], np.float32))
+        pk = O.Packed(s)
+        img0, _, _, _ = O.render_gut(pk, s.rotation, fp, opt)
+        img, nrm, dt, sid, ids = O.render_gut_surface(pk, s.rotation, fp, opt)
+        assert np.array_equal(img, img0)
+        hit = sid != 0xffffffff
+        assert hit.any() and not hit.all() and np.array_equal(nrm[..., 3], img[..., 3])
+        assert np.allclose(dt[..., 1], 1.0 - img[..., 3], atol=1e-6) and np.all(dt[~hit] == [0.0, 1.0]) and np.all(nrm[~hit] == 0)
+        picked = dt[..., 0] != 0
+        assert np.all(dt[picked, 1] < 0.7) and np.all(dt[hit & ~picked, 1] >= 0.7)
+        return s, pk, img, nrm, hit
+
+    s, pk, img, nrm, hit = one((0.05, 0.02, 0.08))
+    n = O.splat_normal(pk, s.rotation, 0, fp)  # (3DGS surface pass, libm exp of the scale: last-bit differences only)
+    assert np.allclose(nrm[hit, :3], n[None, :] * img[hit, 3:4], atol=2e-6)
+    s, pk, img, nrm, hit = one((0.05, 1e-7, 0.08))  # flat: its thin axis
+    n = O.splat_normal(pk, s.rotation, 0, fp)
+    assert np.allclose(nrm[hit, :3], n[None, :] * img[hit, 3:4], atol=2e-6)
+    s, pk, img, nrm, hit = one((1e-7, 1e-7, 0.08))  # needle: minus the ray direction of each pixel -> varies over the footprint
+    if hit.sum() > 1:
+        dirs = nrm[hit, :3] / img[hit, 3:4]
+        assert np.allclose(np.linalg.norm(dirs, axis=1), 1.0, atol=1e-5)
+        to_cam = np.array(cam.eye, np.float32) / np.linalg.norm(cam.eye)
+        assert np.all(dirs @ to_cam > 0.99)  # towards the camera, within the few degrees the footprint spans
