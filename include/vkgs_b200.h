@@ -134,8 +134,9 @@ typedef struct vkgs_frame_params
   float    camera_position[3]; /* FrameInfo.cameraPosition (world) */
   float    focal[2];           /* FrameInfo.focal = (P00*W/2, P11*H/2); focal[1] < 0 */
   float    viewport[2];        /* FrameInfo.viewport = (W,H) */
-  float    basis_viewport[2];  /* FrameInfo.basisViewport = (1/W,1/H) */
-  float    inverse_focal_adjustment; /* 1 */
+  float    basis_viewport[2];  /* FrameInfo.basisViewport: must be (1/W,1/H) ... */
+  float    inverse_focal_adjustment; /* ... and 1: other values (devicePixelRatio != 1, orthographic focal adjustment) are
+                                        rejected with VKGS_ERR_UNSUPPORTED rather than silently ignored */
   float    splat_scale;              /* FrameInfo.splatScale, default 1 */
   float    frustum_dilation;         /* default 0.2 */
   float    alpha_cull_threshold;     /* default 1/255 */
@@ -183,7 +184,7 @@ typedef struct vkgs_outputs
   float     ms_total;        /* first kernel to framebuffer complete (device time) */
   float     ms_kernel[16];   /* per-kernel device time, see VKGS_K_* */
   uint64_t  bytes_algorithmic; /* 12N + (132+SH(d))V + 16P, SURVEY.md §8(d) */
-  /* profiling only, 0 unless options._reserved[4] & 128: (list entry, 8x8 pixel block) pairs the blend evaluated, and
+  /* profiling only, 0 unless options._reserved[0] & 128: (list entry, 8x8 pixel block) pairs the blend evaluated, and
    * fragments that passed both discards and were blended (the reference's ROP invocations) */
   uint64_t  list_entries_evaluated;
   uint64_t  fragments_blended;
@@ -260,6 +261,14 @@ VKGS_API void vkgs_default_camera(vkgs_camera* cam);
 VKGS_API void vkgs_frame_params_set_fisheye(vkgs_frame_params* fp);
 /* Synchronous: returns after the frame (and the requested copies to host) completed. */
 VKGS_API int vkgs_render(vkgs_ctx* ctx, const vkgs_frame_params* fp, vkgs_outputs* out);
+/* The reference's CPU-sorting mode (SORTING_CPU_ASYNC_MULTI): the frame is drawn from an index buffer sorted elsewhere
+ * — SplatSorterAsync on the host in the reference (src/splat_sorter_async.cpp:92-141), consumed and uploaded by
+ * SplatSetManagerVk::tryConsumeAndUploadCpuSortingResult (src/splat_set_manager_vk.cpp:3334-3416). `ids` = `count` HOST
+ * global splat ids in draw order (count <= splats of the scene; borrowed for the call). No dist stage and no sort run:
+ * every id is drawn, frustum culling moves to the raster stage and size culling is off, exactly as the reference's UI
+ * forces them in this mode (src/gaussian_splatting_ui.cpp:1468-1490). The blend operator still follows
+ * options.front_to_back. Synchronous; out->sorted_ids (if set) receives the ids back, sorted_keys is not written. */
+VKGS_API int vkgs_render_presorted(vkgs_ctx* ctx, const vkgs_frame_params* fp, const uint32_t* ids, uint64_t count, vkgs_outputs* out);
 /* Stream-ordered: enqueue one frame, result stays in the device framebuffer. Up to four frames are
  * in flight, each on its own pair of internal streams (the frames-in-flight of the reference's swapchain loop,
  * nvpro_core2/nvapp/application.cpp:517-548); completion order == submission order. */
@@ -271,12 +280,17 @@ VKGS_API int vkgs_render_to_host_async(vkgs_ctx* ctx, const vkgs_frame_params* f
 VKGS_API int vkgs_set_target_format(vkgs_ctx* ctx, uint32_t target_format);
 /* 1 = strictly one frame at a time (full-occupancy kernels, lowest latency), 2..4 (default 4) = overlap consecutive frames. */
 VKGS_API int vkgs_set_frames_in_flight(vkgs_ctx* ctx, int frames);
+/* Wait for every frame in flight. A frame whose tile lists overflowed is handled here, out of the caller's sight: the lists
+ * are grown and the frame is rendered again on its own slot with the same parameters and host destination. Only when a slot
+ * was reused between two vkgs_sync calls (more frames enqueued than frames in flight) and one of its EARLIER frames
+ * overflowed does the call return VKGS_ERR_OVERFLOW (lists grown; render the frames since the previous sync again). */
 VKGS_API int vkgs_sync(vkgs_ctx* ctx);
 /* Enable per-kernel cudaEvent timing for subsequent frames (off by default). */
 VKGS_API int vkgs_set_profiling(vkgs_ctx* ctx, int enabled);
 /* Stats of the most recent frame (syncs). Fills everything in vkgs_outputs except the buffers. */
 VKGS_API int vkgs_last_frame_stats(vkgs_ctx* ctx, vkgs_outputs* out);
-/* Device pointer of the fp32 RGBA framebuffer of the last frame (W*H*4 floats). */
+/* Device pointer of the RGBA framebuffer of the last frame: W*H*4 elements of the colour target format in use
+ * (fp32 by default; half / unorm8 bit patterns after vkgs_set_target_format or options.target_format). */
 VKGS_API const void* vkgs_device_framebuffer(const vkgs_ctx* ctx);
 /* Number of kernels launched by this context since creation. */
 VKGS_API uint64_t vkgs_launch_count(const vkgs_ctx* ctx);
@@ -287,6 +301,15 @@ VKGS_API uint64_t vkgs_launch_count(const vkgs_ctx* ctx);
  *      averaged over `repeats` runs (>=1) on the same input. */
 VKGS_API int vkgs_sort_pairs(vkgs_ctx* ctx, const uint32_t* keys, const uint32_t* values, uint64_t n,
                     uint32_t* keys_out, uint32_t* values_out, int repeats, float* ms_device);
+
+/* The same sort on DEVICE buffers, the way the reference records it: keys and values are sorted IN PLACE, the pair count is
+ * read on the device from *d_count (<= max_count; vrdx's indirect buffer), `d_storage` is caller-provided scratch of at least
+ * vkgs_sort_pairs_storage_bytes(max_count) bytes (vrdxGetSorterKeyValueStorageRequirements,
+ * 3rdparty/vrdx/src/vk_radix_sort.cc:209-224). Stream-ordered on `cuda_stream` (cudaStream_t as void*; NULL = the context's
+ * own stream): nothing is synchronised, like a recorded vkCmd. */
+VKGS_API uint64_t vkgs_sort_pairs_storage_bytes(uint64_t max_count);
+VKGS_API int vkgs_sort_pairs_device(vkgs_ctx* ctx, uint32_t* d_keys, uint32_t* d_values, const uint32_t* d_count, uint64_t max_count,
+                                    void* d_storage, uint64_t storage_bytes, void* cuda_stream);
 
 /* ---- image comparison metrics (replaces ImageCompare's metrics pass: shaders/image_compare_metric.comp.slang:84-190,
  *      371-477, dispatch src/image_compare.cpp:770-830, read-back src/image_compare.cpp:874-905).

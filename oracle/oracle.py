@@ -181,6 +181,29 @@ def render(packed: Packed, fp, opt, want_quads=False):
     return img, keys[:v].copy(), ids[:v].copy(), quads
 
 
+def render_rop16(packed: Packed, fp, opt):
+    """Oracle frame with the colour target rounded to fp16 after every blend (ROP on R16G16B16A16_SFLOAT)."""
+    fn = lib().orc_render_rop16
+    fn.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams), C.POINTER(A.Options), f32p]
+    fn.restype = C.c_uint32
+    img = np.zeros((fp.height, fp.width, 4), np.float32)
+    fn(_p(packed.centers), _p(packed.cov6), _p(packed.rgba), _p(packed.sh), _p(packed.scale), packed.n, packed.sh_degree,
+       C.byref(fp), C.byref(opt), _p(img))
+    return img
+
+
+def render_presorted(packed: Packed, fp, opt, ids):
+    """The reference's CPU-sorting mode: draw `ids` (global splat ids) in the caller's order, cull at raster."""
+    fn = lib().orc_render_presorted
+    fn.argtypes = [f32p, f32p, f32p, f32p, C.c_uint64, C.c_uint32, C.POINTER(A.FrameParams), C.POINTER(A.Options), u32p, C.c_uint64, f32p]
+    fn.restype = None
+    order = np.ascontiguousarray(ids, np.uint32)
+    img = np.zeros((fp.height, fp.width, 4), np.float32)
+    fn(_p(packed.centers), _p(packed.cov6), _p(packed.rgba), _p(packed.sh), packed.n, packed.sh_degree, C.byref(fp), C.byref(opt),
+       _u(order), order.size, _p(img))
+    return img
+
+
 def render_scene(packed_sets, instances, fp, opt, rotations=None):
     """Multi-instance oracle frame. `instances`: list of (set_index, transform[4,4], transform_inverse[4,4]) in glm
     column-major memory order. Returns (image, sorted_keys, sorted_global_ids). With `rotations` (one [N,4] wxyz array

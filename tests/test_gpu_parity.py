@@ -16,17 +16,21 @@ pytestmark = pytest.mark.gpu
 RGBA_TOL = 1e-4  # per-channel absolute tolerance, fp32 colour target
 
 
-def _compare_frame(r, splats, cam, w, h, sh_degree=3, **optkw):
+def _compare_frame(r, splats, cam, w, h, sh_degree=3, fp_set=None, tol=None, **optkw):
     opt = g.default_options(**optkw)
     r.upload(splats, opt)
     fp = g.frame_params(cam, w, h)
     fp.sh_degree = sh_degree
+    for k, v in (fp_set or {}).items():
+        setattr(fp, k, v)
     img, st, ids, keys = r.render(fp, want_sorted=True)
     rec = r.read_records()
 
-    oopt = O.default_options(**optkw)
+    oopt = O.default_options(**{k: v for k, v in optkw.items() if k != "transmittance_epsilon"})  # the oracle never terminates early
     ofp = O.frame_params(cam, w, h)
     ofp.sh_degree = sh_degree
+    for k, v in (fp_set or {}).items():
+        setattr(ofp, k, v)
     pk = O.Packed(splats, sh_format=opt.sh_format, rgba_format=opt.rgba_format)
     oimg, okeys, oids, quads = O.render(pk, ofp, oopt, want_quads=True)
 
@@ -50,7 +54,7 @@ def _compare_frame(r, splats, cam, w, h, sh_degree=3, **optkw):
     if not optkw.get("front_to_back"):
         # BTF alpha is an unbounded sum of alphas: compare it relative to its magnitude
         diff[..., 3] /= np.maximum(1.0, np.abs(oimg[..., 3]))
-    assert diff.max() <= RGBA_TOL, f"max abs diff {diff.max()}"
+    assert diff.max() <= (tol or RGBA_TOL), f"max abs diff {diff.max()}"
     return img, oimg, st
 
 
@@ -103,11 +107,41 @@ def test_orbit_cameras_and_model_transform(gpu_renderer):
     dict(disable_opacity_gaussian=1, front_to_back=1),
     dict(sh_format=A.FORMAT_FLOAT16, rgba_format=A.FORMAT_FLOAT16),
     dict(sh_format=A.FORMAT_UINT8, rgba_format=A.FORMAT_UINT8),
+    dict(size_culling_mode=A.SIZE_CULLING_ENABLED),
 ])
 def test_shader_macro_variants(gpu_renderer, optkw):
     s = g.synth_scene(30_000, 3, 0x3D650005)
     cam = g.make_camera((0.4, 0.3, 1.6), (0, 0, 0)) if "frustum_culling_mode" in optkw else g.default_camera()
     _compare_frame(gpu_renderer, s, cam, 400, 300, **optkw)
+
+
+def test_size_culling_threshold_straddle(gpu_renderer):
+    """SIZE_CULLING_MODE (dist.comp.slang:93-134) with splats on both sides of sizeCullingMinPixels: the projected size
+    goes through exp(scale); kernel and oracle run the same fixed-sequence exp, so V, keys and ids stay bit-exact even for
+    splats within an ulp of the threshold. Thresholds are chosen so that a large share of the scene is culled."""
+    s = g.synth_scene(120_000, 3, 0x3D650015)
+    cam = g.default_camera()
+    seen = []
+    for min_px in (1.0, 6.0, 14.5, 40.0):
+        _, _, st = _compare_frame(gpu_renderer, s, cam, 640, 360, fp_set=dict(size_culling_min_pixels=min_px),
+                                  size_culling_mode=A.SIZE_CULLING_ENABLED)
+        seen.append(st.visible_count)
+    assert seen[0] > seen[1] > seen[2] > seen[3] > 0 and seen[3] < seen[0] // 2
+    # a splat set whose projected sizes sit exactly AT the threshold: every splat at the same view depth, scales
+    # spread over a few ulps around the value where projectedPixels == minPixels
+    n = 4096
+    t = g.synth_scene(n, 0, 0x3D650016)
+    t.positions[:, 2] = 0.0
+    t.positions[:, :2] *= 0.05
+    camz = g.make_camera((0, 0, 3), (0, 0, 0))
+    fpz = g.frame_params(camz, 256, 256)
+    focal = max(abs(fpz.focal[0]), abs(fpz.focal[1]))
+    crit = np.float32(np.log(2.0 * 3.0 / (2.8284271247 * 2.0 * focal)))  # extent * focal / dist == 2 px
+    steps = np.arange(n, dtype=np.int32) - n // 2
+    t.scale[:] = (np.full(n, crit, np.float32).view(np.int32) + steps // 8).view(np.float32)[:, None]
+    _, _, st = _compare_frame(gpu_renderer, t, camz, 256, 256, sh_degree=0, fp_set=dict(size_culling_min_pixels=2.0),
+                              size_culling_mode=A.SIZE_CULLING_ENABLED)
+    assert 0 < st.visible_count < n
 
 
 @pytest.mark.parametrize("sh_degree", [0, 1, 2, 3])
@@ -242,6 +276,45 @@ def test_config2_1m_deg3_1080p_image_vs_oracle(gpu_renderer):
     _compare_frame(gpu_renderer, s, g.default_camera(), 1920, 1080, front_to_back=1)
 
 
+def test_bench_configuration_image_vs_oracle(gpu_renderer):
+    """Exactly what bench.py times: 1 M splats, SH3, 1080p, front to back, transmittance_epsilon = 2^-15, four frames in
+    flight through the asynchronous entry point, frame copied to pinned host memory — against the oracle's exact frame.
+    Bound: eps * max|rgb| (SH colours reach ~1.6) stays under the 1e-4 colour tolerance."""
+    import torch
+    s = g.synth_scene(1_000_000, 3, 0x3D650001)
+    cam, w, h = g.default_camera(), 1920, 1080
+    r = gpu_renderer
+    r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0 ** -15))
+    r.set_frames_in_flight(4)
+    fp = g.frame_params(cam, w, h)
+    bufs = [torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True).numpy() for _ in range(4)]
+    for b in bufs:
+        r.render_to_host_async(fp, b)
+    r.sync()
+    oimg, okeys, oids, quads = O.render(O.Packed(s), O.frame_params(cam, w, h), O.default_options(front_to_back=1), want_quads=True)
+    cmax = float(np.abs(quads["rgba"][:, :3]).max())
+    assert 2.0 ** -15 * cmax < RGBA_TOL
+    for b in bufs:
+        assert np.array_equal(b, bufs[0])  # the four slots produce the same bits
+    assert np.abs(bufs[0] - oimg).max() <= RGBA_TOL
+    img, st, ids, keys = r.render(fp, want_sorted=True)
+    assert np.array_equal(img, bufs[0]) and np.array_equal(ids, oids) and np.array_equal(keys, okeys)
+
+
+def test_config3_6m_deg3_4k_image_vs_oracle(gpu_renderer):
+    """BASELINE configs[2]: 6 M splats, SH3, 3840x2160, front to back — the alpha-blend tolerance check itself: the whole 4K
+    frame against the oracle (exact compositing), then the bench setting (eps 2^-15) against the same oracle frame."""
+    s = g.synth_scene(6_000_000, 3, 0x3D650002)
+    cam, w, h = g.default_camera(), 3840, 2160
+    r = gpu_renderer
+    img, oimg, st = _compare_frame(r, s, cam, w, h, front_to_back=1)
+    assert st.visible_count > 5_000_000 and oimg[..., 3].max() > 0.99
+    r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0 ** -15))
+    img_eps, _, _, _ = r.render(g.frame_params(cam, w, h))
+    assert np.abs(img_eps - oimg).max() <= RGBA_TOL
+    r.upload(g.synth_scene(1000, 0, 1), g.default_options())  # release the device buffers
+
+
 def test_config3_6m_deg3_4k_properties(gpu_renderer):
     img, st = _full_size_properties(gpu_renderer, 6_000_000, 3840, 2160, 0x3D650002, ftb=1)
     assert st.visible_count > 5_000_000
@@ -301,6 +374,70 @@ def test_frames_in_flight_match_sequential_frames(gpu_renderer):
     # the synchronous call still works with two slots and reports per-frame stats
     img, st, ids, _ = r.render(fps[1], want_sorted=True)
     assert np.array_equal(img, ref[1]) and st.visible_count == len(ids)
+
+
+def test_four_frames_in_flight_are_bit_identical_to_sequential(gpu_renderer):
+    """The default of the asynchronous API (and of bench.py): four frames in flight, eight frames per sync (every slot is
+    used twice), different cameras — each result equals the one-frame-at-a-time render bit for bit."""
+    import torch
+    s = g.synth_scene(300_000, 3, 0x3D65000F)
+    r = gpu_renderer
+    r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0 ** -15))
+    fps = [g.frame_params(g.orbit_camera(v, 8), 960, 540) for v in range(8)]
+    r.set_frames_in_flight(1)
+    ref = [r.render(fp)[0].copy() for fp in fps]
+    r.set_frames_in_flight(4)
+    bufs = [torch.empty((540, 960, 4), dtype=torch.float32, pin_memory=True).numpy() for _ in fps]
+    for rep in range(3):
+        for b in bufs:
+            b[:] = -1.0
+        for fp, b in zip(fps, bufs):
+            r.render_to_host_async(fp, b)
+        r.sync()
+        for k, (b, want) in enumerate(zip(bufs, ref)):
+            assert np.array_equal(b, want), (rep, k)
+
+
+def test_overflow_with_four_frames_in_flight_is_repaired_by_sync(gpu_renderer):
+    """Tile lists overflow while four frames are in flight: vkgs_sync grows the lists and renders the affected frames again
+    on their own slots, so every host buffer holds the complete frame when it returns. Reusing a slot before the sync
+    (8 frames, 4 slots) with an overflow in the earlier frame is reported instead (VKGS_ERR_OVERFLOW), and the next
+    batch then succeeds with the grown lists."""
+    import torch
+    n = 3000
+    s = g.synth_scene(n, 0, 0x3D65000B)
+    s.scale[:] = np.log(0.6)
+    s.opacity[:] = -3.0
+    r = gpu_renderer
+    cams = [g.orbit_camera(v, 8) for v in range(4)]
+    w, h = 1920, 1080
+    fps = [g.frame_params(c, w, h) for c in cams]
+    pk = O.Packed(s)
+    want = [O.render(pk, O.frame_params(c, w, h), O.default_options(front_to_back=1))[0] for c in cams]
+    bufs = [torch.empty((h, w, 4), dtype=torch.float32, pin_memory=True).numpy() for _ in range(8)]
+    # (a) one frame per slot between syncs: repaired transparently
+    r.upload(s, g.default_options(front_to_back=1))  # fresh lists: max(8N, 2^20) pairs
+    r.set_frames_in_flight(4)
+    for fp, b in zip(fps, bufs):
+        r.render_to_host_async(fp, b)
+    r.sync()
+    st = r.last_frame_stats()
+    assert st.tile_pairs > (1 << 20)
+    for b, o in zip(bufs, want):
+        assert np.abs(b - o).max() <= RGBA_TOL
+    # (b) slots reused before the sync: the earlier frames are gone, the call says so and the retry is complete
+    r.upload(s, g.default_options(front_to_back=1))
+    r.set_frames_in_flight(4)
+    for k, b in enumerate(bufs):
+        r.render_to_host_async(fps[k % 4], b)
+    with pytest.raises(g.VkgsError) as e:
+        r.sync()
+    assert e.value.code == A.VKGS_ERR_OVERFLOW
+    for k, b in enumerate(bufs):
+        r.render_to_host_async(fps[k % 4], b)
+    r.sync()
+    for k, b in enumerate(bufs):
+        assert np.abs(b - want[k % 4]).max() <= RGBA_TOL
 
 
 def test_caller_stream_sees_finished_frames(gpu_renderer):
@@ -656,3 +793,94 @@ def test_surface_info_quantized_normals_match_oracle(gpu_renderer):
     assert np.quantile(np.abs(nrm - onrm).max(axis=-1), 0.9) <= 2e-6
     assert 1e-6 < np.abs(onrm - onrm_full).max() < 3e-4
     assert (sid == osid).mean() > 0.9999
+
+
+# ---- CPU-sorting mode: frames drawn in a caller-supplied order ----------------------------------------------------------
+
+def test_presorted_order_matches_oracle_and_composes_config0(gpu_renderer):
+    """vkgs_render_presorted (the reference's SORTING_CPU_ASYNC_MULTI consumption, src/splat_set_manager_vk.cpp:3334-3416):
+    all N splats in the order the CPU sorter produced (SplatSorterAsync::innerSort restatement, plane distance, descending
+    for back-to-front), frustum culling forced to the raster stage. BASELINE configs[0] composed on the GPU: 100 k
+    Gaussians, SH0, 512x512, CPU sort order -> the same image as the oracle's CPU blend of that order."""
+    r = gpu_renderer
+    s = g.synth_scene(100_000, 0, 0x3D650000)
+    cam, w, h = g.default_camera(), 512, 512
+    eye = np.array(cam.eye, np.float32)
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    pk = O.Packed(s)
+    for ftb in (0, 1):
+        order, dist, _, _ = O.cpu_sort(s.positions, ident, np.array(cam.ctr, np.float32) - eye, eye, front_to_back=bool(ftb), mode=0, threads=1)
+        r.upload(s, g.default_options(front_to_back=ftb))
+        img, st = r.render_presorted(g.frame_params(cam, w, h), order)
+        oimg = O.render_presorted(pk, O.frame_params(cam, w, h), O.default_options(front_to_back=ftb), order)
+        assert st.visible_count == s.size()
+        d = np.abs(img - oimg)
+        if not ftb:
+            d[..., 3] /= np.maximum(1.0, np.abs(oimg[..., 3]))
+        assert d.max() <= RGBA_TOL
+        # the GPU-sorted frame of the same scene is the same picture up to the different depth key (plane distance vs NDC z)
+        img2, _, ids, _ = r.render(g.frame_params(cam, w, h), want_sorted=True)
+        assert float(np.mean((img2[..., :3] - img[..., :3]) ** 2)) < 1e-4
+    # a camera inside the scene: splats behind the camera are in the list and must be culled at the raster stage
+    cam_in = g.make_camera((0.1, 0.05, 0.2), (0.0, 0.0, -1.0))
+    eye = np.array(cam_in.eye, np.float32)
+    s3 = g.synth_scene(30_000, 3, 0x3D650017)
+    order, _, _, _ = O.cpu_sort(s3.positions, ident, np.array(cam_in.ctr, np.float32) - eye, eye, front_to_back=True, mode=0, threads=1)
+    r.upload(s3, g.default_options(front_to_back=1))
+    img, st = r.render_presorted(g.frame_params(cam_in, 400, 300), order)
+    oimg = O.render_presorted(O.Packed(s3), O.frame_params(cam_in, 400, 300), O.default_options(front_to_back=1), order)
+    assert np.abs(img - oimg).max() <= RGBA_TOL and oimg[..., 3].max() > 0.5
+    # a partial list (the first 5000 ids only) and an empty one
+    img, st = r.render_presorted(g.frame_params(cam_in, 400, 300), order[:5000])
+    oimg = O.render_presorted(O.Packed(s3), O.frame_params(cam_in, 400, 300), O.default_options(front_to_back=1), order[:5000])
+    assert st.visible_count == 5000 and np.abs(img - oimg).max() <= RGBA_TOL
+    img, st = r.render_presorted(g.frame_params(cam_in, 400, 300), order[:0])
+    assert st.visible_count == 0 and not img.any()
+    with pytest.raises(g.VkgsError):
+        r.render_presorted(g.frame_params(cam_in, 400, 300), np.array([30_000], np.uint32))  # id out of range
+
+
+def test_sort_pairs_device_in_place_with_device_count(gpu_renderer):
+    """vkgs_sort_pairs_device (vrdxCmdSortKeyValueIndirect, 3rdparty/vrdx/src/vk_radix_sort.cc:249-258): device buffers,
+    count read on the device (smaller than max_count), in place, on the caller's stream; elements past the count untouched."""
+    import torch
+    r = gpu_renderer
+    rng = np.random.default_rng(21)
+    for max_count, count in ((1_000_000, 777_777), (8192, 8192), (5000, 1), (100_000, 0), (300_000, 300_000)):
+        keys = rng.integers(0, 1 << 32, size=max_count, dtype=np.uint64).astype(np.uint32)
+        keys[: max_count // 3] &= np.uint32(0xff00ff)  # plenty of ties
+        vals = np.arange(max_count, dtype=np.uint32)
+        dk = torch.from_numpy(keys.view(np.int32)).cuda()
+        dv = torch.from_numpy(vals.view(np.int32)).cuda()
+        dc = torch.tensor([count], dtype=torch.int32).cuda()
+        nbytes = r.sort_pairs_storage_bytes(max_count)
+        storage = torch.full((nbytes,), 0xAB, dtype=torch.uint8, device="cuda")  # garbage on purpose
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        for rep in range(2):  # the second call sorts sorted data with the same (dirty) storage
+            r.sort_pairs_device(dk.data_ptr(), dv.data_ptr(), dc.data_ptr(), max_count, storage.data_ptr(), nbytes, stream.cuda_stream)
+        stream.synchronize()
+        k = dk.cpu().numpy().view(np.uint32)
+        v = dv.cpu().numpy().view(np.uint32)
+        order = np.argsort(keys[:count], kind="stable")
+        assert np.array_equal(k[:count], keys[:count][order]) and np.array_equal(v[:count], vals[:count][order])
+        assert np.array_equal(k[count:], keys[count:]) and np.array_equal(v[count:], vals[count:])
+
+
+def test_rgba16f_target_within_rop_rounding_bar(gpu_renderer):
+    """the reference's default colour target is R16G16B16A16_SFLOAT and its ROP rounds to fp16 after EVERY
+    blend; this path blends in fp32 and rounds once. Against an oracle render that rounds per blend, the RGBA16F frame stays
+    within 4/255 per channel (measured far below), for both compositing orders."""
+    r = gpu_renderer
+    s = g.synth_scene(150_000, 3, 0x3D650018)
+    cam, w, h = g.default_camera(), 800, 450
+    pk = O.Packed(s)
+    for ftb in (1, 0):
+        r.upload(s, g.default_options(front_to_back=ftb, target_format=A.FORMAT_FLOAT16))
+        img, _, _, _ = r.render(g.frame_params(cam, w, h))
+        assert img.dtype == np.float16
+        rop = O.render_rop16(pk, O.frame_params(cam, w, h), O.default_options(front_to_back=ftb))
+        d = np.abs(img.astype(np.float32)[..., :3] - rop[..., :3])
+        assert d.max() <= 4.0 / 255.0, d.max()
+        if ftb:
+            assert np.abs(img.astype(np.float32)[..., 3] - rop[..., 3]).max() <= 4.0 / 255.0

@@ -142,3 +142,34 @@ def test_header_promising_more_vertices_than_memory_is_an_error_not_an_abort(tmp
     with pytest.raises(g.VkgsError) as e:
         g.load_scene(path)
     assert e.value.code == A.VKGS_ERR_IO
+
+
+def test_vertex_counts_that_wrap_size_arithmetic_are_rejected(tmp_path):
+    """Crafted headers whose vertex count makes n * rowBytes (binary) or n * properties (ascii) wrap modulo 2^64 must be
+    refused before any allocation or copy (they used to pass the bounds check and write past a tiny vector)."""
+    from vk_gaussian_splatting_b200 import _abi as A
+    base = ["x", "y", "z", "opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3", "f_dc_0", "f_dc_1", "f_dc_2"]
+    rest = [f"f_rest_{k}" for k in range(45)]
+    cases = []
+    # 45 float properties: rowBytes = 180; ceil(2^64 / 45) rows make both n*180 and n*45 wrap to small numbers
+    n_wrap = (1 << 64) // 45 + 1
+    for fmt in ("binary_little_endian", "binary_big_endian", "ascii"):
+        hdr = f"ply\nformat {fmt} 1.0\nelement vertex {n_wrap}\n" + "".join(f"property float {p}\n" for p in rest) + "end_header\n"
+        cases.append(hdr.encode() + b"\0" * 64)
+    # a skipped element before the vertex element whose count * rowBytes wraps the file offset
+    hdr = (f"ply\nformat binary_little_endian 1.0\nelement junk {(1 << 64) // 4 + 3}\nproperty float a\nelement vertex 1\n"
+           + "".join(f"property float {p}\n" for p in base) + "end_header\n")
+    cases.append(hdr.encode() + b"\0" * 256)
+    # list element with an absurd list length
+    hdr = ("ply\nformat binary_little_endian 1.0\nelement face 1\nproperty list uint uint idx\nelement vertex 1\n"
+           + "".join(f"property float {p}\n" for p in base) + "end_header\n")
+    cases.append(hdr.encode() + (0xfffffff0).to_bytes(4, "little") + b"\0" * 128)
+    # just above the 2^31-1 splat limit of the upload
+    hdr = f"ply\nformat binary_little_endian 1.0\nelement vertex {1 << 31}\n" + "".join(f"property float {p}\n" for p in base) + "end_header\n"
+    cases.append(hdr.encode() + b"\0" * 128)
+    for i, blob in enumerate(cases):
+        path = tmp_path / f"wrap{i}.ply"
+        path.write_bytes(blob)
+        with pytest.raises(g.VkgsError) as e:
+            g.load_scene(path)
+        assert e.value.code == A.VKGS_ERR_IO, i

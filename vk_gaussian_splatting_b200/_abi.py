@@ -118,6 +118,9 @@ SYMBOLS = {
     "vkgs_device_framebuffer": (C.c_void_p, [C.c_void_p]),
     "vkgs_launch_count": (C.c_uint64, [C.c_void_p]),
     "vkgs_sort_pairs": (C.c_int, [C.c_void_p, u32p, u32p, C.c_uint64, u32p, u32p, C.c_int, f32p]),
+    "vkgs_sort_pairs_storage_bytes": (C.c_uint64, [C.c_uint64]),
+    "vkgs_sort_pairs_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "vkgs_render_presorted": (C.c_int, [C.c_void_p, C.POINTER(FrameParams), u32p, C.c_uint64, C.POINTER(Outputs)]),
     "vkgs_capture_frame": (C.c_int, [C.c_void_p]),
     "vkgs_compare_with_capture": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ImageMetrics)]),
     "vkgs_image_metrics_host": (C.c_int, [C.c_void_p, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(ImageMetrics)]),

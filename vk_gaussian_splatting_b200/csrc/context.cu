@@ -11,6 +11,7 @@
 // the previous frames' blends.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -62,19 +63,40 @@ void freeScene(vkgs_ctx* c)
 
 int allocTileLists(vkgs_ctx* c, FrameSlot& s, uint64_t capacity)
 {
-  for(int i = 0; i < 2; i++)
-    freeDev(s.dTileKeys[i]), freeDev(s.dTileVals[i]);
-  freeDev(s.dTileSortStatus);
   capacity = std::min<uint64_t>(capacity, 0xfffff000ull);
+  // allocate the new buffers first: if any cudaMalloc fails (the regrow after an overflow is the likely moment
+  // for an out-of-memory), the slot keeps its old, consistent lists and capacity
+  uint32_t *nk[2] = {nullptr, nullptr}, *nv[2] = {nullptr, nullptr};
+  uint64_t* nst   = nullptr;
+  const uint64_t parts = (capacity + SORT_PART - 1) / SORT_PART;
+  cudaError_t    e     = cudaSuccess;
+  for(int i = 0; i < 2 && e == cudaSuccess; i++)
+  {
+    e = cudaMalloc(&nk[i], capacity * sizeof(uint32_t));
+    if(e == cudaSuccess)
+      e = cudaMalloc(&nv[i], capacity * sizeof(uint32_t));
+  }
+  if(e == cudaSuccess)
+    e = cudaMalloc(&nst, parts * 256 * sizeof(uint64_t));
+  if(e == cudaSuccess)
+    e = cudaMemset(nst, 0, parts * 256 * sizeof(uint64_t));
+  if(e != cudaSuccess)
+  {
+    for(int i = 0; i < 2; i++)
+      freeDev(nk[i]), freeDev(nv[i]);
+    freeDev(nst);
+    c->lastError = std::string("tile-list allocation: ") + cudaGetErrorString(e);
+    cudaGetLastError();  // (clear the sticky-free error state of the failed cudaMalloc)
+    return e == cudaErrorMemoryAllocation ? VKGS_ERR_OUT_OF_MEMORY : VKGS_ERR_CUDA;
+  }
   for(int i = 0; i < 2; i++)
   {
-    CU_TRY(c, cudaMalloc(&s.dTileKeys[i], capacity * sizeof(uint32_t)));
-    CU_TRY(c, cudaMalloc(&s.dTileVals[i], capacity * sizeof(uint32_t)));
+    freeDev(s.dTileKeys[i]), freeDev(s.dTileVals[i]);
+    s.dTileKeys[i] = nk[i], s.dTileVals[i] = nv[i];
   }
-  const uint64_t parts = (capacity + SORT_PART - 1) / SORT_PART;
-  CU_TRY(c, cudaMalloc(&s.dTileSortStatus, parts * 256 * sizeof(uint64_t)));
-  CU_TRY(c, cudaMemset(s.dTileSortStatus, 0, parts * 256 * sizeof(uint64_t)));
-  s.tileCapacity = capacity;
+  freeDev(s.dTileSortStatus);
+  s.dTileSortStatus = nst;
+  s.tileCapacity    = capacity;
   return VKGS_OK;
 }
 
@@ -171,15 +193,34 @@ void frameConstants(const vkgs_frame_params& fp, float mv[16], float camModel[3]
                   + cp[3] * fp.model_inverse[12 + j];
 }
 
-// Enqueue one frame on the next slot; optionally a device->host copy of the finished frame.
-int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* slotOut, bool throughputMode)
+// What a frame was asked to do besides rendering into the slot's framebuffer (kept per slot so that a frame whose
+// tile lists overflowed can be enqueued again by vkgs_sync without the caller's help).
+struct FrameRequest
 {
+  void*           hostRgba       = nullptr;  // pinned host destination of the finished frame (or null)
+  bool            throughputMode = false;    // thin co-running front end (asynchronous API with several frames in flight)
+  int             forceSlot      = -1;       // re-render: the slot the frame was first enqueued on
+  const uint32_t* presortedIds   = nullptr;  // CPU-sorting mode: HOST ids to draw in this order (no dist cull, no sort)
+  uint32_t        presortedCount = 0;
+};
+
+// Enqueue one frame on the next slot; optionally a device->host copy of the finished frame.
+int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& rq, int* slotOut)
+{
+  void* const hostRgba       = rq.hostRgba;
+  const bool  throughputMode = rq.throughputMode;
+  const bool  presorted      = rq.presortedIds != nullptr;
   if(!c->uploaded)
     return fail(c, VKGS_ERR_NOT_UPLOADED, "vkgs_render before vkgs_upload");
   if(fp.width == 0 || fp.height == 0)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "zero-sized viewport");
+  // The quad offsets of the reference are scaled by basisViewport * 2 * inverseFocalAdjustment
+  // (threedgs_raster.mesh.slang:284, threedgut_raster.mesh.slang:248); the kernels are built for the values
+  // updateAndUploadFrameInfoUBO writes for a perspective camera at devicePixelRatio 1: (1/W, 1/H) and 1.
+  if(fp.inverse_focal_adjustment != 1.0f || fp.basis_viewport[0] != 1.0f / fp.viewport[0] || fp.basis_viewport[1] != 1.0f / fp.viewport[1])
+    return fail(c, VKGS_ERR_UNSUPPORTED, "inverse_focal_adjustment must be 1 and basis_viewport (1/W, 1/H) (orthographic focal adjustment / devicePixelRatio != 1 are outside the built path)");
   CU_TRY(c, cudaSetDevice(c->device));
-  const int  si = c->nextSlot;
+  const int  si = rq.forceSlot >= 0 ? rq.forceSlot : c->nextSlot;
   FrameSlot& s  = c->slots[si];
   if(int rc = ensureTargets(c, s, fp.width, fp.height))
     return rc;
@@ -191,7 +232,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
       cudaEventRecord(s.ev[slot], st);
   };
 
-  CU_TRY(c, cudaMemsetAsync(s.dCounters, 0, sizeof(FrameCounters), st));
+  CU_TRY(c, cudaMemsetAsync(&s.dCounters->visible, 0, sizeof(FrameCounters) - offsetof(FrameCounters, visible), st));
   // tile list ranges: begin = 0xffffffff, end = 0 (two arrays, two byte-pattern memsets)
   CU_TRY(c, cudaMemsetAsync(s.dRanges, 0xff, sizeof(uint32_t) * tx * ty, st));
   CU_TRY(c, cudaMemsetAsync(s.dRanges + tx * ty, 0, sizeof(uint32_t) * tx * ty, st));
@@ -214,6 +255,14 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
       std::memcpy(pa.fp.model_inverse, inst.transformInverse, sizeof(pa.fp.model_inverse));
     }
     pa.opt = c->opt;
+    if(presorted)
+    {
+      // CPU-sorting mode: no dist shader, so no dist-stage cull — every splat of the scene gets its record, the frustum
+      // test moves to the raster stage and size culling is off (src/gaussian_splatting_ui.cpp:1468-1490)
+      if(pa.opt.frustum_culling_mode == VKGS_FRUSTUM_CULLING_AT_DIST)
+        pa.opt.frustum_culling_mode = VKGS_FRUSTUM_CULLING_AT_RASTER;
+      pa.opt.size_culling_mode = VKGS_SIZE_CULLING_DISABLED;
+    }
     frameConstants(pa.fp, pa.mv, pa.camModel, pa.gutOrigin);
     pa.keys       = s.dKeys[0];
     pa.ids        = s.dIds[0];
@@ -236,7 +285,16 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
   mark(VKGS_K_SORT_SCAN + 1);  // (depth-key digit histograms are fused into the preprocess kernel)
 
   // ---- "GPU Sort": up to 4 x 8-bit stable passes over (key,id) -----------------------------------
-  for(int p = 0; p < 4; p++)
+  if(presorted)
+  {
+    // the caller's order replaces the sort (tryConsumeAndUploadCpuSortingResult: memcpy + vkCmdCopyBuffer of 4N bytes,
+    // src/splat_set_manager_vk.cpp:3396-3414); V = the number of ids handed in. sortSrc[3] stays 0: buffer 0.
+    CU_TRY(c, cudaMemcpyAsync(s.dIds[0], rq.presortedIds, sizeof(uint32_t) * rq.presortedCount, cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemcpyAsync(&s.dCounters->visible, &rq.presortedCount, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    for(int p = 0; p < 4; p++)
+      mark(VKGS_K_SORT_PASS0 + p + 1);
+  }
+  for(int p = 0; p < 4 && !presorted; p++)
   {
     SortPassArgs sa{};
     sa.keys[0] = s.dKeys[0], sa.keys[1] = s.dKeys[1];
@@ -368,7 +426,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     cudaEventRecord(s.ev[VKGS_K_BLEND + 1], s.streamBlend);
   s.evRecorded = c->profiling;
 
-  CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, 48, cudaMemcpyDeviceToHost, s.streamBlend));
+  CU_TRY(c, cudaMemcpyAsync(s.hCounters, s.dCounters, offsetof(FrameCounters, ticket), cudaMemcpyDeviceToHost, s.streamBlend));
   if(hostRgba)
     CU_TRY(c, cudaMemcpyAsync(hostRgba, s.dImage, 4ull * formatSize(c->opt.target_format) * fp.width * fp.height, cudaMemcpyDeviceToHost,
                               s.streamBlend));
@@ -381,24 +439,39 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, void* hostRgba, int* 
     CU_TRY(c, cudaStreamWaitEvent(c->userStream, s.evDone, 0));
   }
   CU_TRY(c, cudaGetLastError());
-  s.lastFp    = fp;
-  s.haveFrame = true;
+  s.lastFp        = fp;
+  s.lastHost      = hostRgba;
+  s.lastThin      = throughputMode;
+  s.lastPresorted = presorted;
+  s.haveFrame     = true;
+  s.framesSinceSync++;
   c->lastSlot = si;
-  c->nextSlot = (si + 1) % std::max(1, c->framesInFlight);
+  if(rq.forceSlot < 0)
+    c->nextSlot = (si + 1) % std::max(1, c->framesInFlight);
   if(slotOut)
     *slotOut = si;
   return VKGS_OK;
 }
 
-// After a sync: if a slot's tile lists overflowed, grow them so the caller can re-render.
-int checkOverflow(vkgs_ctx* c)
+// After a sync: if a frame of a slot overflowed its tile lists since the last look, grow the lists of every slot to
+// what that frame wanted. flagged[i] = the LAST frame of slot i must be rendered again; *lost = an earlier frame of some
+// slot overflowed too (several frames were enqueued on the slot between two syncs) and its result — already overwritten
+// in the slot, possibly copied to the caller's host buffer — came from truncated lists.
+// Returns VKGS_ERR_OVERFLOW when something was grown.
+int checkOverflow(vkgs_ctx* c, bool* flagged /*[MAX_FRAMES_IN_FLIGHT], optional*/, bool* lost = nullptr)
 {
   bool grown = false;
-  for(auto& s : c->slots)
+  for(int i = 0; i < MAX_FRAMES_IN_FLIGHT; i++)
   {
-    if(s.haveFrame && s.hCounters->overflow)
+    FrameSlot& s = c->slots[i];
+    if(flagged)
+      flagged[i] = false;
+    const uint32_t frames = s.framesSinceSync;
+    s.framesSinceSync     = 0;
+    if(s.haveFrame && (s.hCounters->overflow || s.hCounters->stickyOverflow))
     {
-      const uint64_t want = static_cast<uint64_t>(s.hCounters->tilePairs) * 5 / 4 + 65536;
+      const uint64_t pairs = std::max(s.hCounters->tilePairs, s.hCounters->stickyPairs);
+      const uint64_t want  = pairs * 5 / 4 + 65536;
       for(auto& t : c->slots)
         if(t.tileCapacity && t.tileCapacity < want)
         {
@@ -406,8 +479,13 @@ int checkOverflow(vkgs_ctx* c)
           if(int rc = allocTileLists(c, t, want))
             return rc;
         }
-      s.hCounters->overflow = 0;
-      grown                 = true;
+      if(lost && frames > 1)
+        *lost = true;
+      if(flagged)
+        flagged[i] = s.hCounters->overflow != 0;
+      s.hCounters->overflow = s.hCounters->stickyOverflow = s.hCounters->stickyPairs = 0;
+      cudaMemset(s.dCounters, 0, offsetof(FrameCounters, visible));  // clear the sticky words
+      grown = true;
     }
   }
   return grown ? fail(c, VKGS_ERR_OVERFLOW, "tile lists overflowed; capacity was grown, render the frame again") : VKGS_OK;
@@ -547,6 +625,7 @@ int vkgs_create(int device, vkgs_ctx** out)
       ok = ok && cudaEventCreate(&e) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.evDone, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&s.dCounters, sizeof(FrameCounters)) == cudaSuccess;
+    ok = ok && cudaMemset(s.dCounters, 0, sizeof(FrameCounters)) == cudaSuccess;  // (the sticky words are never cleared per frame)
     ok = ok && cudaMallocHost(&s.hCounters, sizeof(FrameCounters)) == cudaSuccess;
     if(ok)
       std::memset(s.hCounters, 0, sizeof(FrameCounters));
@@ -830,23 +909,59 @@ int vkgs_render_async(vkgs_ctx* c, const vkgs_frame_params* fp)
 {
   if(!c || !fp)
     return VKGS_ERR_INVALID_ARGUMENT;
-  return enqueueFrame(c, *fp, nullptr, nullptr, true);
+  FrameRequest rq;
+  rq.throughputMode = true;
+  return enqueueFrame(c, *fp, rq, nullptr);
 }
 
 int vkgs_render_to_host_async(vkgs_ctx* c, const vkgs_frame_params* fp, void* host_rgba)
 {
   if(!c || !fp || !host_rgba)
     return VKGS_ERR_INVALID_ARGUMENT;
-  return enqueueFrame(c, *fp, host_rgba, nullptr, true);
+  FrameRequest rq;
+  rq.hostRgba       = host_rgba;
+  rq.throughputMode = true;
+  return enqueueFrame(c, *fp, rq, nullptr);
 }
 
 int vkgs_sync(vkgs_ctx* c)
 {
   if(!c)
     return VKGS_ERR_INVALID_ARGUMENT;
-  if(int rc = syncAll(c))
-    return rc;
-  return checkOverflow(c);
+  // Tile-list overflow is handled here, out of the caller's sight: the lists of every slot are grown to what the
+  // overflowing frame wanted and the frames that were produced from truncated lists are enqueued again on their own
+  // slots (same parameters, same host destination), so that after a successful vkgs_sync every frame in flight is
+  // complete. Frames of OTHER slots are untouched: a slot's lists are private to it.
+  for(int attempt = 0; attempt < 4; attempt++)
+  {
+    if(int rc = syncAll(c))
+      return rc;
+    bool      flagged[MAX_FRAMES_IN_FLIGHT];
+    bool      lost = false;
+    const int rc   = checkOverflow(c, flagged, &lost);
+    if(rc != VKGS_ERR_OVERFLOW)
+      return rc;
+    if(lost)
+      return fail(c, VKGS_ERR_OVERFLOW, "tile lists overflowed in a frame whose slot was reused before vkgs_sync; capacity was grown, "
+                                        "render the frames since the previous vkgs_sync again");
+    const int last = c->lastSlot;
+    for(int i = 0; i < MAX_FRAMES_IN_FLIGHT; i++)
+      if(flagged[i])
+      {
+        FrameSlot& s = c->slots[i];
+        if(s.lastPresorted)
+          return fail(c, VKGS_ERR_OVERFLOW, "tile lists overflowed in a presorted frame; capacity was grown, render it again");
+        FrameRequest rq;
+        rq.hostRgba       = s.lastHost;
+        rq.throughputMode = s.lastThin;
+        rq.forceSlot      = i;
+        const vkgs_frame_params fp = s.lastFp;
+        if(int rc2 = enqueueFrame(c, fp, rq, nullptr))
+          return rc2;
+      }
+    c->lastSlot = last;
+  }
+  return fail(c, VKGS_ERR_OVERFLOW, "tile lists still overflow after regrowing");
 }
 
 int vkgs_last_frame_stats(vkgs_ctx* c, vkgs_outputs* out)
@@ -866,18 +981,21 @@ const void* vkgs_device_framebuffer(const vkgs_ctx* c)
   return (c && c->lastSlot >= 0) ? c->slots[c->lastSlot].dImage : nullptr;
 }
 
-int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
+static int renderSync(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out, const uint32_t* presortedIds, uint32_t presortedCount)
 {
-  if(!c || !fp || !out)
-    return VKGS_ERR_INVALID_ARGUMENT;
   for(int attempt = 0; attempt < 3; attempt++)
   {
-    int si = 0;
-    if(int rc = enqueueFrame(c, *fp, out->rgba, &si, false))  // synchronous call: nothing to overlap with
+    int          si = 0;
+    FrameRequest rq;
+    rq.hostRgba       = out->rgba;  // synchronous call: nothing to overlap with, full-occupancy front end
+    rq.presortedIds   = presortedIds;
+    rq.presortedCount = presortedCount;
+    if(int rc = enqueueFrame(c, *fp, rq, &si))
       return rc;
     FrameSlot& s = c->slots[si];
-    CU_TRY(c, cudaStreamSynchronize(s.stream));
-    const int rc = checkOverflow(c);
+    if(int rc = syncAll(c))  // (every slot: the overflow check below reads the counters of all of them)
+      return rc;
+    const int rc = checkOverflow(c, nullptr);
     if(rc == VKGS_ERR_OVERFLOW)
       continue;  // lists were regrown: run the frame again
     if(rc)
@@ -887,17 +1005,41 @@ int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
     const uint32_t sel = s.hCounters->sortSrc[3] & 1u;
     if(out->sorted_ids && v)
       CU_TRY(c, cudaMemcpy(out->sorted_ids, s.dIds[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if(out->sorted_keys && v)
+    if(out->sorted_keys && v && !presortedIds)
       CU_TRY(c, cudaMemcpy(out->sorted_keys, s.dKeys[sel], v * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return VKGS_OK;
   }
   return fail(c, VKGS_ERR_OVERFLOW, "tile lists still overflow after regrowing");
 }
 
+int vkgs_render(vkgs_ctx* c, const vkgs_frame_params* fp, vkgs_outputs* out)
+{
+  if(!c || !fp || !out)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  return renderSync(c, fp, out, nullptr, 0);
+}
+
+int vkgs_render_presorted(vkgs_ctx* c, const vkgs_frame_params* fp, const uint32_t* ids, uint64_t count, vkgs_outputs* out)
+{
+  if(!c || !fp || !out || (!ids && count))
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(!c->uploaded)
+    return fail(c, VKGS_ERR_NOT_UPLOADED, "vkgs_render_presorted before vkgs_upload");
+  if(count > c->totalSplats)
+    return fail(c, VKGS_ERR_INVALID_ARGUMENT, "more ids than splats in the scene");
+  for(uint64_t i = 0; i < count; i++)
+    if(ids[i] >= c->totalSplats)
+      return fail(c, VKGS_ERR_INVALID_ARGUMENT, "presorted id out of range");
+  static const uint32_t none = 0;
+  return renderSync(c, fp, out, count ? ids : &none, static_cast<uint32_t>(count));
+}
+
 int vkgs_read_records(vkgs_ctx* c, uint32_t* records12, uint64_t first, uint64_t count)
 {
   if(!c || !records12 || !c->uploaded || c->lastSlot < 0 || first + count > c->totalSplats)
     return VKGS_ERR_INVALID_ARGUMENT;
+  if(c->opt.pipeline == VKGS_PIPELINE_3DGUT)
+    return fail(c, VKGS_ERR_UNSUPPORTED, "vkgs_read_records: the 3DGUT pipeline keeps a different (24-word) per-splat record");
   FrameSlot& s = c->slots[c->lastSlot];
   CU_TRY(c, cudaStreamSynchronize(s.stream));
   CU_TRY(c, cudaMemcpy(records12, s.dRecords + first * RECORD_WORDS, count * RECORD_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost));

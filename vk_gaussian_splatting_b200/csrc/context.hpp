@@ -28,7 +28,7 @@ struct FrameSlot
   float2*        dOutDepthT  = nullptr;
   uint32_t*      dOutSplatId = nullptr;
   FrameCounters* dCounters   = nullptr;
-  FrameCounters* hCounters   = nullptr;  // pinned; first 32 bytes are copied back every frame
+  FrameCounters* hCounters   = nullptr;  // pinned; the first 48 bytes (through fragments[]) are copied back every frame
   uint64_t *     dPreStatus = nullptr, *dSortStatus = nullptr, *dBinStatus = nullptr, *dTileSortStatus = nullptr;
   uint32_t *     dTileKeys[2] = {nullptr, nullptr}, *dTileVals[2] = {nullptr, nullptr};
   uint64_t       tileCapacity = 0;
@@ -40,6 +40,10 @@ struct FrameSlot
   bool           evRecorded = false;
   bool           haveFrame  = false;
   vkgs_frame_params lastFp{};
+  void*          lastHost      = nullptr;  // host destination of the slot's last frame (re-render after a tile-list overflow)
+  bool           lastThin      = false;
+  bool           lastPresorted = false;
+  uint32_t       framesSinceSync = 0;        // frames enqueued on this slot since the host last checked for overflow
 };
 
 }  // namespace vkgs

@@ -430,6 +430,15 @@ bool loadPly(const std::string& path, vkgs_scene& out)
       const size_t n = el.count;
       // the rows as floats, by property index
       const size_t         np = el.props.size();
+      // Validate the count BEFORE any multiplication (a crafted header could wrap n * rowBytes or n * np modulo 2^64):
+      // the upload refuses more than 2^31-1 splats anyway, a binary file must hold n whole rows, and an ascii file
+      // needs at least two bytes per value.
+      if(n > 0x7fffffffull || np == 0)
+        return failLoad("ply vertex count out of range");
+      if(format != Ascii && (el.rowBytes == 0 || pos > data.size() || n > (data.size() - pos) / el.rowBytes))
+        return failLoad("binary ply ends early");
+      if(format == Ascii && (pos > data.size() || n > (data.size() - pos) / (2 * np) + 1))
+        return failLoad("ascii ply ends early");
       std::vector<float>   rows;
       const uint8_t*       base = nullptr;
       if(format == Ascii)
@@ -461,9 +470,7 @@ bool loadPly(const std::string& path, vkgs_scene& out)
       }
       else
       {
-        if(pos + n * el.rowBytes > data.size())
-          return failLoad("binary ply ends early");
-        base = data.data() + pos;
+        base = data.data() + pos;  // (n rows fit: checked above)
       }
       auto find = [&](const char* name) -> int {
         for(size_t k = 0; k < np; k++)
@@ -533,22 +540,33 @@ bool loadPly(const std::string& path, vkgs_scene& out)
           return failLoad("ascii ply ends early");
     }
     else if(el.fixedSize)
+    {
+      // checked skip: count * rowBytes must stay inside the file (and must not wrap)
+      if(pos > data.size() || (el.rowBytes != 0 && el.count > (data.size() - pos) / el.rowBytes))
+        return failLoad("binary ply ends early");
       pos += el.count * el.rowBytes;
+    }
     else
     {
       for(size_t i = 0; i < el.count; i++)
+      {
         for(const PlyProp& pr : el.props)
         {
           if(pr.countType == PlyType::None)
             pos += typeSize(pr.type);
           else
           {
-            if(pos + typeSize(pr.countType) > data.size())
+            if(pos > data.size() || typeSize(pr.countType) > data.size() - pos)
               return failLoad("binary ply ends early");
             const uint64_t c = scalarToCount(data.data() + pos, pr.countType, swap);
+            if(c > (data.size() - pos) / typeSize(pr.type))
+              return failLoad("binary ply ends early");
             pos += typeSize(pr.countType) + c * typeSize(pr.type);
           }
         }
+        if(pos > data.size())
+          return failLoad("binary ply ends early");
+      }
     }
     if(pos > data.size())
       return failLoad("binary ply ends early");

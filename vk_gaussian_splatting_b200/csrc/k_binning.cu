@@ -114,7 +114,11 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
         a.counters->tilePairs        = d;
         a.counters->tilePairsClamped = d < a.capacity ? d : a.capacity;
         if(d > a.capacity)
-          a.counters->overflow = 1u;
+        {
+          a.counters->overflow       = 1u;
+          a.counters->stickyOverflow = 1u;
+          atomicMax(&a.counters->stickyPairs, d);
+        }
       }
     }
   };

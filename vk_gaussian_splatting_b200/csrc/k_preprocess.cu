@@ -448,8 +448,9 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     }
     if(keep && sizeCul)
     {
-      const float sx = expf(sm.scale[3 * tid + 0]) * a.fp.splat_scale, sy = expf(sm.scale[3 * tid + 1]) * a.fp.splat_scale,
-                  sz = expf(sm.scale[3 * tid + 2]) * a.fp.splat_scale;
+      // (fixed-sequence exp shared with the oracle: the cull decision is bit-exact at the sizeCullingMinPixels threshold)
+      const float sx = expfExact(sm.scale[3 * tid + 0]) * a.fp.splat_scale, sy = expfExact(sm.scale[3 * tid + 1]) * a.fp.splat_scale,
+                  sz = expfExact(sm.scale[3 * tid + 2]) * a.fp.splat_scale;
       const float  radius = fmaxf(sx, fmaxf(sy, sz));
       float        extent = radius * 2.8284271247f * 2.0f;
       const float* m      = a.fp.model;

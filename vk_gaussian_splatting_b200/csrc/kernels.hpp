@@ -23,6 +23,10 @@ constexpr int      BLEND_THREADS   = TILE_W * BLEND_H / 2;  // one warp per 8x8 
 // Small per-frame control block in HBM, cleared with one memset at the start of every frame.
 struct FrameCounters
 {
+  // NOT cleared per frame (the per-frame memset starts at `visible`): set by any frame of the slot whose tile lists
+  // overflowed since the host last looked (vkgs_sync), with the largest pair count wanted
+  uint32_t stickyOverflow;
+  uint32_t stickyPairs;
   uint32_t visible;            // V: splats that passed the dist-stage cull (IndirectParams.instanceCount)
   uint32_t tilePairs;          // D: (splat,tile) pairs the binning wanted to emit
   uint32_t tilePairsClamped;   // min(D, capacity): what the tile sort actually processes
@@ -61,7 +65,7 @@ struct PreprocessArgs
   float             gutOrigin[3];// 3DGUT: ray origin (viewInverse translation) in model space
   uint32_t*         keys;        // [V] compacted, ascending splat id
   uint32_t*         ids;         // [V]
-  uint32_t*         records;     // [N][RECORD_WORDS], indexed by splat id
+  uint32_t*         records;     // [N][RECORD_WORDS] (3DGUT pipeline: [N][GUT_RECORD_WORDS]), indexed by splat id
   uint2*            bboxes;      // [N] copy of the two pixel-bbox words of the record: the binning gathers 8 B per splat
                                  // by sorted id, and a compact array stays L2-resident where the 48-byte records do not
   FrameCounters*    counters;

@@ -118,4 +118,68 @@ int vkgs_sort_pairs(vkgs_ctx* c, const uint32_t* keys, const uint32_t* values, u
   return VKGS_OK;
 }
 
+
+// ---- device-buffer entry: the drop-in for vrdxCmdSortKeyValueIndirect (3rdparty/vrdx/src/vk_radix_sort.cc:249-258) ------------
+// vrdx sorts a keys buffer and a values buffer in place, with the element count read from a device buffer ("indirect") and a
+// caller-provided storage buffer sized by vrdxGetSorterKeyValueStorageRequirements (:209-224). Same contract here:
+// stream-ordered (nothing is synchronised), stable, ascending, in place.
+namespace {
+struct DevSortCtl
+{
+  uint32_t ticket[4];
+  uint32_t hist[4][256];
+};
+constexpr uint64_t alignUp(uint64_t v, uint64_t a)
+{
+  return (v + a - 1) / a * a;
+}
+}  // namespace
+
+uint64_t vkgs_sort_pairs_storage_bytes(uint64_t max_count)
+{
+  const uint64_t parts = (max_count + SORT_PART - 1) / SORT_PART;
+  return alignUp(sizeof(DevSortCtl), 256) + alignUp(parts * 256 * sizeof(uint64_t), 256) + 2 * alignUp(max_count * sizeof(uint32_t), 256);
+}
+
+int vkgs_sort_pairs_device(vkgs_ctx* c, uint32_t* dKeys, uint32_t* dValues, const uint32_t* dCount, uint64_t maxCount, void* dStorage,
+                           uint64_t storageBytes, void* cudaStream)
+{
+  if(!c || !dKeys || !dValues || !dCount || !dStorage || maxCount > 0xfffff000ull)
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(storageBytes < vkgs_sort_pairs_storage_bytes(maxCount))
+    return VKGS_ERR_INVALID_ARGUMENT;
+  if(maxCount == 0)
+    return VKGS_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  cudaStream_t   st    = cudaStream ? static_cast<cudaStream_t>(cudaStream) : c->slots[0].stream;
+  const uint64_t parts = (maxCount + SORT_PART - 1) / SORT_PART;
+  unsigned char* base  = static_cast<unsigned char*>(dStorage);
+  DevSortCtl*    ctl   = reinterpret_cast<DevSortCtl*>(base);
+  uint64_t*      stat  = reinterpret_cast<uint64_t*>(base + alignUp(sizeof(DevSortCtl), 256));
+  uint32_t*      tk    = reinterpret_cast<uint32_t*>(base + alignUp(sizeof(DevSortCtl), 256) + alignUp(parts * 256 * sizeof(uint64_t), 256));
+  uint32_t*      tv    = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(tk) + alignUp(maxCount * sizeof(uint32_t), 256));
+  // the storage is the caller's: whatever it holds must not be mistaken for look-back words of this call
+  CU_TRY(c, cudaMemsetAsync(base, 0, alignUp(sizeof(DevSortCtl), 256) + parts * 256 * sizeof(uint64_t), st));
+  launchHistogram(dKeys, dCount, static_cast<uint32_t>(maxCount), &ctl->hist[0][0], 0, 4, st);
+  c->launches++;
+  for(int p = 0; p < 4; p++)
+  {
+    SortPassArgs sa{};
+    // four passes, fixed ping-pong (no pass is skipped): the result lands back in the caller's buffers
+    sa.keys[0] = (p & 1) ? tk : dKeys, sa.keys[1] = (p & 1) ? dKeys : tk;
+    sa.vals[0] = (p & 1) ? tv : dValues, sa.vals[1] = (p & 1) ? dValues : tv;
+    sa.countPtr  = dCount;
+    sa.maxCount  = static_cast<uint32_t>(maxCount);
+    sa.histogram = &ctl->hist[p][0];
+    sa.status    = stat;
+    sa.ticket    = &ctl->ticket[p];
+    sa.epoch     = static_cast<uint32_t>(p + 1);  // private, freshly cleared status array
+    sa.shift     = 8 * p;
+    launchSortPass(sa, st);
+    c->launches++;
+  }
+  CU_TRY(c, cudaGetLastError());
+  return VKGS_OK;
+}
+
 }  // extern "C"
