@@ -5,13 +5,13 @@
 // upsweep/spine/downsweep.slang). Same contract: ascending, stable, pair count read on the device.
 // vrdx is reduce-then-scan (3 dispatches and ~20 B/pair per pass). This is a single-pass
 // ("onesweep") design instead: the digit histograms of all passes are produced by whichever
-// kernel wrote the keys, and each pass is ONE kernel that ranks an 8192-pair partition in shared
+// kernel wrote the keys, and each pass is ONE kernel that ranks a 4096-pair partition in shared
 // memory, resolves its global digit offsets with a decoupled look-back over earlier partitions
 // (epoch-stamped 64-bit status words: nothing is cleared between passes or frames) and scatters
 // through shared memory so global writes leave in digit-contiguous runs. Traffic per pass is one
 // read + one write of the pairs (16 B/pair), i.e. 64 B/pair for 32-bit keys.
 //
-// Stability: a partition is ranked in (warp, item, lane) order, which is the input order because
+// Stability: a partition is ranked in (warp, row, lane) order, which is the input order because
 // each warp loads a contiguous chunk in a warp-striped arrangement; partitions are ordered by a
 // ticket taken at block start, which also guarantees the look-back never waits on a block that
 // has not been scheduled.
@@ -23,24 +23,47 @@ namespace vkgs {
 namespace {
 
 constexpr int NWARPS = SORT_THREADS / 32;
+static_assert(SORT_THREADS == 256, "one thread per digit: the publication, the scans and the look-back are written for 256 threads");
+static_assert(SORT_ITEMS % 2 == 0, "rows are ranked two at a time");
 
+// Shared memory of a partition. The ranking tables are dead once every key has its rank, and the staging area is only
+// written after that point, so the two alias.
 struct SortSmem
 {
   union
   {
-    uint32_t warpHist[NWARPS][256];  // per-warp digit counters, then per-warp exclusive offsets
-    uint32_t stageKeys[SORT_PART];   // (re-used after ranking) block-sorted keys
+    struct
+    {
+      // mask[w][p][r][d]: lanes of warp w whose key of row r of the current row pair has digit d (p = parity of the pair:
+      // a pair's masks are cleared while the next pair already fills the other copy)
+      uint32_t mask[NWARPS][2][2][256];
+      uint32_t cnt[NWARPS][256];  // keys with digit d in the rows warp w has ranked so far; then its exclusive offset over warps
+    } rank;
+    struct
+    {
+      uint32_t keys[SORT_PART];  // block-sorted pairs
+      uint32_t vals[SORT_PART];
+    } stage;
   };
-  uint32_t stageVals[SORT_PART];
-  uint32_t digitStart[256];   // first block-local position of each digit
-  uint32_t globalBase[256];   // global position of the first key of each digit of this partition
+  uint32_t digitCount[256];  // partition digit counts (counted right after the load), then each digit's first block-local position
+  uint32_t delta[256];       // global position of the digit's first key of this partition MINUS its block-local position
   uint32_t scan[NWARPS + 1];
+  uint32_t warpTot[NWARPS];
   uint32_t part;
 };
-static_assert(sizeof(uint32_t) * NWARPS * 256 <= sizeof(uint32_t) * SORT_PART, "warpHist must fit in the key staging area");
 
-template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_constant__ SortPassArgs a)
+// One 8-bit pass over one 4096-pair partition.
+//
+// Ranking. A key's position inside the partition is (keys with a smaller digit) + (keys with the same digit earlier in
+// the input). Each warp owns 512 consecutive pairs as 16 rows of 32 (lane = consecutive pair), so "earlier" means an
+// earlier row of the same warp, a lower lane of the same row, or a lower warp. Within a row the lanes that share a
+// digit find each other through shared memory: every lane ORs its lane bit into the row's mask word of its digit, and
+// after a warp barrier reads the word back — the peer mask — at a cost that does not depend on how many distinct digits
+// the row holds (8 ballots + 8 selects per key before; MATCH.ANY is serviced once per distinct value). The lowest peer
+// adds the group size to the warp's running digit counter and clears the word. Two rows are ranked per step (two mask
+// copies; the second row also reads the first row's mask of ITS digit), which halves the warp barriers.
+template <bool RANGES>
+__global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const __grid_constant__ SortPassArgs a)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   SortSmem&      sm   = *reinterpret_cast<SortSmem*>(smemRaw);
@@ -56,7 +79,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_cons
   if(a.srcSelOut)
   {
     // identity pass (every key has the same digit, e.g. the exponent byte of NDC depths): skip it
-    const int same = __syncthreads_or(count == 0u || a.histogram[tid & 255u] == count);
+    const int same = __syncthreads_or(count == 0u || a.histogram[tid] == count);
     if(same)
     {
       if(blockIdx.x == 0 && tid == 0)
@@ -70,10 +93,14 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_cons
   uint32_t* __restrict__       valsOut = a.vals[cur ^ 1u];
   if(tid == 0)
     sm.part = atomicAdd(a.ticket, 1u);
-  for(int i = tid; i < NWARPS * 256; i += SORT_THREADS)
-    (&sm.warpHist[0][0])[i] = 0u;
-  if(tid < 256)
-    sm.digitStart[tid] = 0u;  // (first used as the partition's digit counters, see below)
+  {
+    uint4* z = reinterpret_cast<uint4*>(&sm.rank);
+#pragma unroll
+    for(int i = 0; i < static_cast<int>(sizeof(sm.rank) / 16 / SORT_THREADS); i++)
+      z[i * SORT_THREADS + tid] = make_uint4(0u, 0u, 0u, 0u);
+    static_assert(sizeof(sm.rank) % (16 * SORT_THREADS) == 0, "whole uint4 rounds");
+  }
+  sm.digitCount[tid] = 0u;
   __syncthreads();
   const uint32_t part = sm.part;
   if(part >= parts)
@@ -87,46 +114,52 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_cons
   // ---- load keys (warp-striped: warp w owns SORT_ITEMS*32 consecutive pairs) ------------------
   const uint32_t partBase = part * SORT_PART;
   const uint32_t warpBase = partBase + warp * (SORT_ITEMS * 32);
+  const bool     full     = partBase + SORT_PART <= count;  // (block-uniform)
   uint32_t       keys[SORT_ITEMS];
-#pragma unroll
-  for(int i = 0; i < SORT_ITEMS; i++)
+  if(full)
   {
-    const uint32_t idx = warpBase + i * 32 + lane;
-    keys[i]            = idx < count ? keysIn[idx] : 0xffffffffu;  // padding sorts last, is never written back
+#pragma unroll
+    for(int i = 0; i < SORT_ITEMS; i++)
+      keys[i] = keysIn[warpBase + i * 32 + lane];
+  }
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      const uint32_t idx = warpBase + i * 32 + lane;
+      keys[i]            = idx < count ? keysIn[idx] : 0xffffffffu;  // padding sorts last, is never written back
+    }
   }
   VKGS_TL(part, 2);
 
   // ---- count the partition's digits FIRST (shared atomics, a few hundred cycles) and publish them:
-  // successors' look-backs only need these counts, so they must not wait for the ranking below
-  // (several thousand cycles, twice that on an SM shared by two partitions) ------------------------
+  // successors' look-backs only need these counts, so they must not wait for the ranking below ------
 #pragma unroll
   for(int i = 0; i < SORT_ITEMS; i++)
-    atomicAdd(&sm.digitStart[(keys[i] >> a.shift) & 0xffu], 1u);
+    atomicAdd(&sm.digitCount[(keys[i] >> a.shift) & 0xffu], 1u);
   __syncthreads();
-  uint32_t  realCount = 0;
-  uint64_t* mine      = a.status + static_cast<uint64_t>(part) * 256 + (tid & 255u);
-  if(tid < 256)
+  uint32_t  realCount = sm.digitCount[tid];
+  uint64_t* mine      = a.status + static_cast<uint64_t>(part) * 256 + tid;
   {
     // padding keys (digit 0xff of the last partition) are not counted
-    realCount = sm.digitStart[tid];
-    if(tid == 255 && partBase + SORT_PART > count)
+    if(tid == 255 && !full)
       realCount -= (partBase + SORT_PART - count);
     if(part == 0)
     {
       // exclusive scan of the global digit histogram = first global position of each digit.
       // (only partition 0 needs it; everyone else inherits it through the look-back chain)
       const uint32_t h   = a.histogram[tid];
-      uint32_t       inc = warp_inclusive_scan(h, lane);
-      __shared__ uint32_t warpTot[8];
+      const uint32_t inc = warp_inclusive_scan(h, lane);
       if(lane == 31)
-        warpTot[warp] = inc;
-      asm volatile("bar.sync 1, 256;");
+        sm.warpTot[warp] = inc;
+      __syncthreads();  // (block-uniform branch)
       uint32_t add = 0;
       for(unsigned w = 0; w < warp; w++)
-        add += warpTot[w];
+        add += sm.warpTot[w];
       const uint32_t excl = inc - h + add;
       lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
-      sm.globalBase[tid] = excl;
+      sm.delta[tid] = excl;
       if(tid == 0 && a.srcSelOut)
         *a.srcSelOut = cur ^ 1u;
     }
@@ -134,71 +167,54 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_cons
       lb_store(mine, lb_pack(a.epoch, LB_AGGREGATE, realCount));
   }
 
-  // ---- rank within the warp (ballot multi-split) ------------------------------------------------
-  // peer masks first (see match_digit), then the dependent counter updates
-  uint32_t rank[SORT_ITEMS];
+  // ---- rank within the warp --------------------------------------------------------------------
+  uint32_t rank2[SORT_ITEMS / 2];  // two 16-bit ranks per word (a warp holds 512 keys)
   {
-    unsigned peers[SORT_ITEMS];
+    uint32_t*      cnt     = sm.rank.cnt[warp];
+    const uint32_t laneBit = 1u << lane, lower = laneBit - 1u;
 #pragma unroll
-    for(int i = 0; i < SORT_ITEMS; i++)
+    for(int ii = 0; ii < SORT_ITEMS / 2; ii++)
     {
-      const uint32_t digit = (keys[i] >> a.shift) & 0xffu;
-      peers[i]             = match_digit<BITS>(FULL_MASK, digit);
-      if(BITS < 8)
-      {
-        // real digits are < 2^BITS; the padding digit 0xff is told apart by its top bit
-        const bool     top = (digit >> 7) & 1u;
-        const unsigned v   = __ballot_sync(FULL_MASK, top);
-        peers[i] &= top ? v : ~v;
-      }
-    }
-#pragma unroll
-    for(int i = 0; i < SORT_ITEMS; i++)
-    {
-      const uint32_t digit  = (keys[i] >> a.shift) & 0xffu;
-      const unsigned leader = __ffs(peers[i]) - 1;
-      uint32_t       before = 0;
-      if(lane == leader)
-      {
-        before                   = sm.warpHist[warp][digit];
-        sm.warpHist[warp][digit] = before + __popc(peers[i]);
-      }
-      before  = __shfl_sync(FULL_MASK, before, leader);
-      rank[i] = before + __popc(peers[i] & ((1u << lane) - 1u));
+      uint32_t*      m0 = sm.rank.mask[warp][ii & 1][0];
+      uint32_t*      m1 = sm.rank.mask[warp][ii & 1][1];
+      const uint32_t d0 = (keys[2 * ii] >> a.shift) & 0xffu, d1 = (keys[2 * ii + 1] >> a.shift) & 0xffu;
+      atomicOr(&m0[d0], laneBit);
+      atomicOr(&m1[d1], laneBit);
       __syncwarp();
+      const uint32_t peers0 = m0[d0], peers1 = m1[d1], row0same = m0[d1];
+      const uint32_t b0 = cnt[d0], b1 = cnt[d1];
+      __syncwarp();
+      const uint32_t r0 = b0 + __popc(peers0 & lower);
+      const uint32_t r1 = b1 + __popc(row0same) + __popc(peers1 & lower);
+      rank2[ii]         = r0 | (r1 << 16);
+      if((peers0 & lower) == 0u)  // lowest lane of the group (two groups of a pair may share a digit: atomic add)
+      {
+        atomicAdd(&cnt[d0], static_cast<uint32_t>(__popc(peers0)));
+        m0[d0] = 0u;
+      }
+      if((peers1 & lower) == 0u)
+      {
+        atomicAdd(&cnt[d1], static_cast<uint32_t>(__popc(peers1)));
+        m1[d1] = 0u;
+      }
     }
-  }
-  // values are only needed for staging: issue their loads now so the latency hides behind the scans
-  uint32_t vals[SORT_ITEMS];
-#pragma unroll
-  for(int i = 0; i < SORT_ITEMS; i++)
-  {
-    const uint32_t idx = warpBase + i * 32 + lane;
-    vals[i]            = idx < count ? valsIn[idx] : 0u;
   }
   __syncthreads();
   VKGS_TL(part, 3);
 
-  // ---- per-digit: exclusive scan over warps, block totals ------------------------------------------
-  uint32_t digitCount = 0;
-  if(tid < 256)
+  // ---- per digit: exclusive scan over warps; exclusive scan over digits --------------------------
   {
     uint32_t run = 0;
 #pragma unroll
     for(int w = 0; w < NWARPS; w++)
     {
-      const uint32_t c    = sm.warpHist[w][tid];
-      sm.warpHist[w][tid] = run;
+      const uint32_t c     = sm.rank.cnt[w][tid];
+      sm.rank.cnt[w][tid]  = run;
       run += c;
     }
-    digitCount = run;
-  }
-  // exclusive scan of the 256 digit totals -> block-local start of each digit
-  {
     uint32_t       total;
-    const uint32_t excl = block_exclusive_scan<NWARPS>(tid < 256 ? digitCount : 0u, sm.scan, total);
-    if(tid < 256)
-      sm.digitStart[tid] = excl;
+    const uint32_t excl = block_exclusive_scan<NWARPS>(run, sm.scan, total);
+    sm.digitCount[tid]  = excl;  // from here on: first block-local position of the digit
   }
   __syncthreads();
   VKGS_TL(part, 4);
@@ -209,23 +225,45 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_cons
   for(int i = 0; i < SORT_ITEMS; i++)
   {
     const uint32_t digit = (keys[i] >> a.shift) & 0xffu;
-    pos[i]               = sm.digitStart[digit] + sm.warpHist[warp][digit] + rank[i];
+    pos[i]               = sm.digitCount[digit] + sm.rank.cnt[warp][digit] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
   }
-  __syncthreads();  // warpHist is dead from here: its storage becomes stageKeys
+  __syncthreads();  // the ranking tables are dead from here: their storage becomes the staging area
 #pragma unroll
   for(int i = 0; i < SORT_ITEMS; i++)
+    sm.stage.keys[pos[i]] = keys[i];
+  // values go straight from global to their staged position
+  if(full)
   {
-    sm.stageKeys[pos[i]] = keys[i];
-    sm.stageVals[pos[i]] = vals[i];
+    uint32_t vals[SORT_ITEMS];
+#pragma unroll
+    for(int i = 0; i < SORT_ITEMS; i++)
+      vals[i] = valsIn[warpBase + i * 32 + lane];
+#pragma unroll
+    for(int i = 0; i < SORT_ITEMS; i++)
+      sm.stage.vals[pos[i]] = vals[i];
+  }
+  else
+  {
+#pragma unroll
+    for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      const uint32_t idx    = warpBase + i * 32 + lane;
+      sm.stage.vals[pos[i]] = idx < count ? valsIn[idx] : 0u;
+    }
   }
   VKGS_TL(part, 5);
 
-  // ---- global digit offsets: decoupled look-back, one chain per digit --------------------------
-  if(tid < 256 && part != 0)
+  // ---- global digit offsets: decoupled look-back, one chain per digit (= per thread) -------------
   {
-    const uint32_t excl = lb_lookback<16>(a.status + tid, part, 256, a.epoch);
-    lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
-    sm.globalBase[tid] = excl;
+    uint32_t excl;
+    if(part != 0)
+    {
+      excl = lb_lookback<16>(a.status + tid, part, 256, a.epoch);
+      lb_store(mine, lb_pack(a.epoch, LB_INCLUSIVE, excl + realCount));
+    }
+    else
+      excl = sm.delta[tid];
+    sm.delta[tid] = excl - sm.digitCount[tid];
   }
   VKGS_TL(part, 6);
   __syncthreads();
@@ -239,18 +277,17 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) k_sort_pass(const __grid_cons
     const uint32_t j = i * SORT_THREADS + tid;
     if(j < valid)
     {
-      const uint32_t k     = sm.stageKeys[j];
-      const uint32_t digit = (k >> a.shift) & 0xffu;
-      const uint32_t dst   = sm.globalBase[digit] + (j - sm.digitStart[digit]);
-      keysOut[dst]         = k;
-      valsOut[dst]         = sm.stageVals[j];
-      if(a.rangeBegin)
+      const uint32_t k   = sm.stage.keys[j];
+      const uint32_t dst = j + sm.delta[(k >> a.shift) & 0xffu];
+      keysOut[dst]       = k;
+      valsOut[dst]       = sm.stage.vals[j];
+      if(RANGES)
       {
-        // equal keys are contiguous in the staged (block-sorted) order: the input of the last pass is
-        // ordered by the low digit, so inside every high-digit run the full key is non-decreasing
-        if(j == 0 || sm.stageKeys[j - 1] != k)
+        // Final pass of the tile sort: equal keys are contiguous in the staged (block-sorted) order — the input of the
+        // last pass is ordered by the low digit, so inside every high-digit run the full key is non-decreasing
+        if(j == 0 || sm.stage.keys[j - 1] != k)
           atomicMin(a.rangeBegin + k, dst);
-        if(j + 1 == valid || sm.stageKeys[j + 1] != k)
+        if(j + 1 == valid || sm.stage.keys[j + 1] != k)
           atomicMax(a.rangeEnd + k, dst + 1u);
       }
     }
@@ -314,10 +351,10 @@ void launchSortPass(const SortPassArgs& args, cudaStream_t stream)
   const uint32_t parts = (args.maxCount + SORT_PART - 1) / SORT_PART;
   if(parts == 0)
     return;
-  if(args.digitBits > 0 && args.digitBits <= 5)
-    k_sort_pass<5><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
+  if(args.rangeBegin)
+    k_sort_pass<true><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
   else
-    k_sort_pass<8><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
+    k_sort_pass<false><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
 }
 
 void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t maxCount, uint32_t* hist, int firstShift, int passes,
@@ -335,8 +372,8 @@ void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t ma
 
 void initSortKernels()
 {
-  cudaFuncSetAttribute(k_sort_pass<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
-  cudaFuncSetAttribute(k_sort_pass<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
+  cudaFuncSetAttribute(k_sort_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
+  cudaFuncSetAttribute(k_sort_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SortSmem)));
 }
 
 }  // namespace vkgs

@@ -11,9 +11,9 @@ namespace vkgs {
 constexpr int      PRE_TILE        = 256;   // splats per preprocess tile (= block size)
 constexpr int      RECORD_WORDS    = 12;    // per-splat record, 48 B
 constexpr int      GUT_RECORD_WORDS = 24;   // 3DGUT pipeline: 96 B, see k_preprocess.cu
-constexpr int      SORT_THREADS    = 512;
+constexpr int      SORT_THREADS    = 256;
 constexpr int      SORT_ITEMS      = 16;    // keys per thread
-constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 8192 pairs per partition (16 per thread: half the CTAs and look-back words of 8 per thread; measured +3.5 % fps)
+constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per partition, four partitions resident per SM
 constexpr int      BIN_THREADS     = 256;
 constexpr int      TILE_W          = 32;
 constexpr int      TILE_H          = 32;    // binning / tile-sort granularity: 32x32 pixels (fewest (tile, splat) pairs) ...
