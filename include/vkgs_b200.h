@@ -93,9 +93,12 @@ typedef struct vkgs_options
   uint32_t point_cloud_mode;         /* POINT_CLOUD_MODE */
   uint32_t show_sh_only;             /* SHOW_SH_ONLY */
   uint32_t disable_opacity_gaussian; /* DISABLE_OPACITY_GAUSSIAN */
-  float    transmittance_epsilon;    /* front_to_back only: stop compositing a pixel once the
-                                        remaining transmittance 1-A drops below this (0 = never,
-                                        the reference's exact behaviour). Error bound: eps*max|rgb|. */
+  float    transmittance_epsilon;    /* stop compositing a pixel once the remaining transmittance drops below this
+                                        (0 = never, the reference's exact behaviour). Colour error bound: eps*max|rgb|;
+                                        front_to_back alpha (1-T) is within eps. Back-to-front frames are composited
+                                        from the near end of the list, so they can stop early too, but their alpha is
+                                        the reference's SUM of opacities: with eps > 0 it only sums the fragments
+                                        composited before the stop (use 0 when that channel matters). */
   uint32_t target_format;            /* colour target of the frame: VKGS_FORMAT_FLOAT32 (default; parity tests),
                                         VKGS_FORMAT_FLOAT16 (the reference's default COLOR_MAIN format,
                                         R16G16B16A16_SFLOAT, src/gaussian_splatting.h:338) or VKGS_FORMAT_UINT8
@@ -184,8 +187,9 @@ typedef struct vkgs_outputs
   float     ms_total;        /* first kernel to framebuffer complete (device time) */
   float     ms_kernel[16];   /* per-kernel device time, see VKGS_K_* */
   uint64_t  bytes_algorithmic; /* 12N + (132+SH(d))V + 16P, SURVEY.md §8(d) */
-  /* profiling only, 0 unless options._reserved[0] & 128: (list entry, 8x8 pixel block) pairs the blend evaluated, and
-   * fragments that passed both discards and were blended (the reference's ROP invocations) */
+  /* profiling only, 0 unless options._reserved[0] & 128: pixel evaluations of the blend in units of 64 pixels (a list entry
+   * evaluated against a whole 8x8 pixel block counts 1), and fragments that passed both discards and were blended (the
+   * reference's ROP invocations) */
   uint64_t  list_entries_evaluated;
   uint64_t  fragments_blended;
 } vkgs_outputs;

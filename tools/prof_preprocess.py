@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import vk_gaussian_splatting_b200 as g
 ab = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 s = g.synth_scene(1_000_000, 3, 0x3D650001)

@@ -10,7 +10,9 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libvkgs_b200.so"
+import os as _os
+# VKGS_LIB: tuning builds only (tools/ab_variants.py); the product library is lib/libvkgs_b200.so
+LIB_PATH = Path(_os.environ["VKGS_LIB"]) if _os.environ.get("VKGS_LIB") else PKG / "lib" / "libvkgs_b200.so"
 
 VKGS_OK = 0
 VKGS_ERR_INVALID_ARGUMENT = -1

@@ -46,9 +46,27 @@ def _newer(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build_lib(verbose: bool = False, force: bool = False) -> Path:
+def build_variant(tag: str, defines, verbose: bool = False) -> Path:
+    """Tuning builds: lib/libvkgs_b200_<tag>.so compiled with extra -D defines (tools/ab_variants.py benchmarks several of
+    them in one GPU call; a process picks one with VKGS_LIB=<path>). Never used by the product path."""
+    return build_lib(verbose, force=False, tag=tag, defines=list(defines))
+
+
+def build_lib(verbose: bool = False, force: bool = False, tag: str = "", defines=()) -> Path:
     OUT_DIR.mkdir(exist_ok=True)
-    OBJ_DIR.mkdir(exist_ok=True)
+    global OBJ_DIR, LIB
+    obj_dir_saved, lib_saved = OBJ_DIR, LIB
+    if tag:
+        OBJ_DIR = PKG / "build" / f"variant_{tag}"
+        LIB = OUT_DIR / f"libvkgs_b200_{tag}.so"
+    try:
+        return _build_lib(verbose, force, [f"-D{d}" for d in defines])
+    finally:
+        OBJ_DIR, LIB = obj_dir_saved, lib_saved
+
+
+def _build_lib(verbose: bool, force: bool, extra_defines) -> Path:
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
     headers = list(CSRC.glob("*.hpp")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "vkgs_b200.h"]
     objs = []
@@ -57,7 +75,7 @@ def build_lib(verbose: bool = False, force: bool = False) -> Path:
         o = OBJ_DIR / (src + ".o")
         objs.append(o)
         if force or _newer(o, [s, *headers, Path(__file__)]):
-            cmd = [nvcc, "-ccbin", _host_cxx(), *ARCH, *COMMON, *EXTRA.get(src, []), "-x", "cu", "-c", str(s), "-o", str(o)]
+            cmd = [nvcc, "-ccbin", _host_cxx(), *ARCH, *COMMON, *EXTRA.get(src, []), *extra_defines, "-x", "cu", "-c", str(s), "-o", str(o)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

@@ -17,7 +17,10 @@ constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 4096 pairs p
 constexpr int      BIN_THREADS     = 256;
 constexpr int      TILE_W          = 32;
 constexpr int      TILE_H          = 32;    // binning / tile-sort granularity: 32x32 pixels (fewest (tile, splat) pairs) ...
-constexpr int      BLEND_H         = 16;    // ... blended by TILE_H / BLEND_H CTAs per tile, each a 32x16 band reading the same list
+#ifndef VKGS_BLEND_H
+#define VKGS_BLEND_H 16
+#endif
+constexpr int      BLEND_H         = VKGS_BLEND_H;  // ... blended by TILE_H / BLEND_H CTAs per tile, each a 32 x BLEND_H band reading the same list
 constexpr int      BLEND_THREADS   = TILE_W * BLEND_H / 2;  // one warp per 8x8 pixel block of the band, two pixels per thread
 
 // Small per-frame control block in HBM, cleared with one memset at the start of every frame.
