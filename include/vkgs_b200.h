@@ -187,9 +187,8 @@ typedef struct vkgs_outputs
   float     ms_total;        /* first kernel to framebuffer complete (device time) */
   float     ms_kernel[16];   /* per-kernel device time, see VKGS_K_* */
   uint64_t  bytes_algorithmic; /* 12N + (132+SH(d))V + 16P, SURVEY.md §8(d) */
-  /* profiling only, 0 unless options._reserved[0] & 128: pixel evaluations of the blend in units of 64 pixels (a list entry
-   * evaluated against a whole 8x8 pixel block counts 1), and fragments that passed both discards and were blended (the
-   * reference's ROP invocations) */
+  /* profiling only, 0 unless options._reserved[0] & 128: (list entry, 8x8 pixel block) pairs the blend evaluated, and
+   * fragments that passed both discards and were blended (the reference's ROP invocations) */
   uint64_t  list_entries_evaluated;
   uint64_t  fragments_blended;
 } vkgs_outputs;

@@ -505,7 +505,7 @@ void fillStats(vkgs_ctx* c, FrameSlot& s, vkgs_outputs* out)
 {
   out->visible_count = s.hCounters->visible;
   out->tile_pairs    = s.hCounters->tilePairs;
-  out->list_entries_evaluated = s.hCounters->fragments[0] / 32;  // per-lane evaluations (2 pixels each) -> units of 64 pixels
+  out->list_entries_evaluated = s.hCounters->fragments[0];
   out->fragments_blended      = s.hCounters->fragments[1];
   const uint64_t n = c->totalSplats, v = out->visible_count, p = static_cast<uint64_t>(s.lastFp.width) * s.lastFp.height;
   // SH bytes per visible splat: exact for one set, splat-count weighted over the instances otherwise

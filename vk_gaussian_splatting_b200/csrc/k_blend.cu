@@ -124,96 +124,22 @@ __device__ __forceinline__ void cpAsyncWaitAll()
 }
 
 // record, 48 B: cx cy w1x w1y | w2x w2y r g | b a bbox bbox   (3DGUT: 96 B, see k_preprocess.cu)
-constexpr int BLEND_WARPS = BLEND_THREADS / 32;  // blending (consumer) warps of a CTA; one more warp stages the list
-constexpr int BLEND_CTA_THREADS = BLEND_THREADS + 32;
-#ifndef VKGS_BLEND_SUBS
-#define VKGS_BLEND_SUBS 2
-#endif
-#ifndef VKGS_BLEND_LOOKAHEAD
-#define VKGS_BLEND_LOOKAHEAD 4
-#endif
-#ifndef VKGS_BLEND_RING
-#define VKGS_BLEND_RING 12
-#endif
-#ifndef VKGS_BLEND_MINCTAS
-#define VKGS_BLEND_MINCTAS (1152 / BLEND_CTA_THREADS)
-#endif
-constexpr int STAGE       = 32;  // list entries per ring stage: one per lane of the staging warp
-constexpr int RING_STAGES = VKGS_BLEND_RING;       // stages in the shared ring
-constexpr int LOOKAHEAD   = VKGS_BLEND_LOOKAHEAD;  // stages whose record gathers are in flight while the staging warp classifies an older one
-constexpr int ID_AHEAD    = LOOKAHEAD + 2;         // the list itself (splat ids) is fetched this many stages ahead of the record gathers
-constexpr int ID_RING     = 16;                    // stages of ids in shared memory
-static_assert(ID_AHEAD < ID_RING && LOOKAHEAD < RING_STAGES, "ring depths");
-constexpr int SUBS        = VKGS_BLEND_SUBS;  // lane groups of a blending warp that walk their OWN hit list: a group owns 8 x (8 / SUBS) pixels
-constexpr int SUB_ROWS    = 8 / SUBS;
-constexpr int NBLOCKS     = BLEND_WARPS * SUBS;  // hit masks per stage
-static_assert(SUBS == 1 || SUBS == 2 || SUBS == 4, "lane groups are whole multiples of a row pair");
-static_assert(NBLOCKS <= 32, "one hit bit per sub-block in a 32-bit word");
-constexpr int      BLOCKS_X    = TILE_W / 8;  // the band is split into BLOCKS_X x BLOCKS_Y warp blocks of 8x8 pixels
+constexpr int      BLEND_WARPS = BLEND_THREADS / 32;
+constexpr int      BATCH       = 128;  // list entries staged per round, one per thread of the first BATCH/32 warps. Smaller than
+                                       // the CTA on purpose: with early termination most tiles finish inside their first
+                                       // batches, and whatever is classified beyond that point is wasted
+static_assert(BATCH % 32 == 0 && BATCH <= BLEND_THREADS, "whole staging warps");
+constexpr int      BLOCKS_X    = TILE_W / 8;  // the tile is split into BLOCKS_X x BLOCKS_Y warp blocks of 8x8 pixels
 constexpr int      BLOCKS_Y    = BLEND_H / 8;
 constexpr int      BANDS       = TILE_H / BLEND_H;  // CTAs per tile (consecutive block indices: they share the list in L2)
 static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && BLEND_H % 8 == 0 && TILE_H % BLEND_H == 0, "one warp per 8x8 pixel block");
 
-// dynamic shared memory of a blend CTA: record ring | hit masks | full barriers | consumer progress words |
-// (surface info) normal + id rings | (3DGUT) instance index ring + the world-space ray directions of every thread's two pixels
+// dynamic shared memory of a blend CTA: records ring, hit masks, (surface info) normal + id rings, (3DGUT) instance index
+// ring + the world-space ray directions of every thread's two pixels (multi-instance scenes only)
 __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
 {
-  return RING_STAGES * STAGE * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + RING_STAGES * NBLOCKS * 4u + RING_STAGES * 8u + 64u
-         + ID_RING * STAGE * 4u + (surf ? RING_STAGES * STAGE * 20u : 0u) + (gut ? RING_STAGES * STAGE * 4u + BLEND_THREADS * 32u : 0u);
-}
-
-// mbarrier helpers of the ring (shared::cta addresses)
-__device__ __forceinline__ void mbarInit(uint32_t addr, uint32_t count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count));
-}
-__device__ __forceinline__ void mbarArrive(uint32_t addr)
-{
-  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-// Wait for the phase with the given parity. A waiting warp must not compete for issue slots with the staging warp it
-// is waiting for (the schedulers are fair: nine spinning warps leave the one working warp a ninth of the slots), so the
-// test is the suspending form with a time hint and a failed test is followed by a sleep, not by another test.
-__device__ __forceinline__ void mbarWaitParity(uint32_t addr, uint32_t parity)
-{
-  uint32_t done;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(done)
-      : "r"(addr), "r"(parity), "r"(20000u)
-      : "memory");
-  while(!done)
-  {
-    __nanosleep(200);
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(20000u)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void stsRelease(uint32_t addr, uint32_t v)
-{
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ldsAcquire(uint32_t addr)
-{
-  uint32_t v;
-  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-template <int N>
-__device__ __forceinline__ void cpAsyncWaitGroup()
-{
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+  return 2u * BATCH * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u)
+         + (gut ? 2u * BATCH * 4u + BLEND_THREADS * 32u : 0u);
 }
 
 // ---- 3DGUT fragment helpers -----------------------------------------------------------------------------------------
@@ -278,64 +204,57 @@ __device__ __noinline__ float gutExactPixel(const GutFrameConstants& g, uint32_t
   return ok ? (NOGAUSS ? -1.0f : -alpha) : 0.0f;
 }
 
-// One CTA per band of a tile: BLEND_WARPS blending warps + one staging warp.
+// One CTA (BLEND_WARPS warps) per band of a tile; a warp owns an 8x8 pixel block and every thread TWO pixels of
+// it (same column, rows ly and ly+4), evaluated together with packed fp32 instructions: the loads,
+// the loop control and the x-dependent products are shared by the pair and every FFMA2 retires two
+// IEEE-rounded results in one issue slot (the kernel is issue/latency bound, not FMA-pipe bound).
 //
-// A blending warp owns an 8x8 pixel block and every thread TWO pixels of it (same column, adjacent rows), evaluated
-// together with packed fp32 instructions: the loads, the loop control and the x-dependent products are shared by the
-// pair and every FFMA2 retires two IEEE-rounded results in one issue slot (the kernel is issue bound, not FMA-pipe
-// bound). The warp's lanes form SUBS groups (half warps by default) that each own 8 x (8/SUBS) pixels and walk their OWN
-// hit list: the groups of a warp run in lock step but read different list entries, so an entry that only touches the
-// upper half of the block costs the lower half nothing — the loop runs max(hits) trips over the groups instead of the
-// hits of their union, and the hit test is twice as fine.
+// The tile's list is consumed in batches of 128 entries through a double-buffered shared ring:
+// every thread gathers ONE 48-byte record of the next batch straight into shared memory with
+// cp.async (no staging registers) while the current batch is blended, then classifies its entry —
+// which of the four warp blocks can the splat touch (pixel bbox, then a separating-axis test along
+// the splat's own axes against the opacity-limited radius) — and the warp ballots of those bits
+// become per-warp hit masks, so the blending warps iterate set bits only. One barrier per batch.
 //
-// The tile's depth-ordered list travels through a shared ring of RING_STAGES x 32 records. The staging warp gathers the
-// 48-byte records of a stage with cp.async (LOOKAHEAD stages in flight), classifies each landed entry against every
-// sub-block of the band — pixel bbox, then a separating-axis test along the splat's own axes against the opacity-limited
-// radius — and publishes the per-sub-block hit masks with an mbarrier (full[stage]). Blending warps wait on that barrier,
-// iterate set bits only and report the stages they have finished through a progress word; the staging warp refills a
-// stage once every warp is past it. Nothing in the loop is a CTA-wide barrier: a warp with few hits runs ahead, a warp
-// with many falls behind by up to the ring, and a saturated warp (front-to-back early termination) simply stops.
+// Inner loop: two list entries are evaluated per trip, branch-free up to the blend (discards are
+// zeros), so their shared loads, SFU ex2 and dependent FMA chains interleave; only the final
+// transmittance update is ordered. Signs are arranged so that no negation is needed per hit:
+// the loop works on c - p (A is even in it), carries MINUS the opacity, and accumulates MINUS the
+// colour.
 //
-// Order. Every pixel sees its fragments in list order. Back-to-front frames (the reference default) are composited from
-// the END of the list with the same "under" update as front-to-back frames — identical in exact arithmetic to the
-// reference's "over" blend — and keep the reference's additive alpha (sum of the fragment opacities).
+// Order. Every pixel sees its fragments in list order. Back-to-front frames (the reference default) are
+// composited from the END of the list with the same "under" update as front-to-back frames — identical
+// in exact arithmetic to the reference's "over" blend — and keep the reference's additive alpha (the sum of
+// the fragment opacities); so both orders can stop at a saturated pixel (transmittance_epsilon).
 //
-// Inner loop: two list entries are evaluated per trip, branch-free up to the blend (discards are zeros), so their shared
-// loads, SFU ex2 and dependent FMA chains interleave; only the final transmittance update is ordered. Signs are arranged so
-// that no negation is needed per hit: the loop works on c - p (A is even in it), carries MINUS the opacity, and
-// accumulates MINUS the colour.
+// Discards. The fragment survives iff A <= 8 and exp(-A/2) * alpha > 1/255, i.e. A < A* = 2 ln(255 alpha).
+// The staging thread leaves cut = min(8, A* - band) and A* in the staged record (over the bbox words, which
+// only the classification reads): A <= cut is a sure keep, and only a pixel whose A lies within the band of
+// A* is sent to the exact path (the oracle's fixed-sequence exp), so both discards cost one comparison.
 template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT, bool GUTX = false>
-__global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA_THREADS > 300 ? 1 : 2) : VKGS_BLEND_MINCTAS)) k_blend(const __grid_constant__ BlendArgs a)
+__global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
 {
-  // record ring | hit masks | full barriers | progress | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
-  constexpr uint32_t REC_BYTES  = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
-  constexpr uint32_t RING_ENTRIES = RING_STAGES * STAGE;
-  constexpr uint32_t SMEM_HIT   = RING_ENTRIES * REC_BYTES;             // hit masks: [stage][sub-block]
-  constexpr uint32_t SMEM_FULL  = SMEM_HIT + RING_STAGES * NBLOCKS * 4;  // one mbarrier per stage
-  constexpr uint32_t SMEM_PROG  = SMEM_FULL + RING_STAGES * 8;           // stages finished by each blending warp
-  constexpr uint32_t SMEM_IDS   = SMEM_PROG + 64;                        // splat ids of the next stages: [ID_RING][32]
-  constexpr uint32_t SMEM_SURF  = SMEM_IDS + ID_RING * STAGE * 4;
-  constexpr uint32_t SMEM_SID   = SMEM_SURF + RING_ENTRIES * 16;
-  constexpr uint32_t SMEM_INST  = SURF ? SMEM_SID + RING_ENTRIES * 4 : SMEM_SURF;  // 3DGUT: instance index of every staged entry
-  constexpr uint32_t SMEM_WORLD = SMEM_INST + RING_ENTRIES * 4;  // 3DGUT: world-space ray directions, 32 bytes per thread
-  static_assert(SMEM_INST + (GUT ? RING_ENTRIES * 4 + BLEND_THREADS * 32 : 0) == blendSmemBytes(SURF, GUT), "launch-side size");
-  static_assert(BLEND_WARPS * 4 <= 64, "progress words");
-  static_assert(SMEM_HIT % 16 == 0 && SMEM_FULL % 8 == 0, "alignment");
+  // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
+  constexpr uint32_t REC_BYTES = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
+  constexpr uint32_t SMEM_REC  = BATCH * REC_BYTES;  // bytes of one record buffer
+  constexpr uint32_t SMEM_HIT  = 2 * SMEM_REC;       // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
+  constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
+  constexpr uint32_t SMEM_SID  = SMEM_SURF + 2 * BATCH * 16;
+  constexpr uint32_t SMEM_INST = SURF ? SMEM_SID + 2 * BATCH * 4 : SMEM_SURF;  // 3DGUT: instance index of every staged entry
+  constexpr uint32_t SMEM_WORLD = SMEM_INST + 2 * BATCH * 4;  // 3DGUT: world-space ray directions, 32 bytes per thread
+  static_assert(SMEM_INST + (GUT ? 2 * BATCH * 4 + BLEND_THREADS * 32 : 0) == blendSmemBytes(SURF, GUT), "launch-side size");
   extern __shared__ __align__(16) unsigned char s_raw[];
   const uint32_t sbase = smemBaseOpaque(s_raw);
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const bool     producer = warp == BLEND_WARPS;  // (warp-uniform) the staging warp
-  const uint32_t bwarp = producer ? 0u : warp;    // blending warp index (pixel block)
   const uint32_t tile = blockIdx.x / BANDS, band = blockIdx.x % BANDS;
   const uint32_t tx = tile % a.tilesX, ty = tile / a.tilesX;
   const uint32_t tileX0 = tx * TILE_W, tileY0 = ty * TILE_H + band * BLEND_H;  // origin of this CTA's band
-  // two pixels of adjacent rows per thread: lane >> 3 = row pair, so lanes [g * 32 / SUBS, (g + 1) * 32 / SUBS) own rows [g * SUB_ROWS, (g + 1) * SUB_ROWS)
-  const uint32_t px = tileX0 + (bwarp % BLOCKS_X) * 8u + (lane & 7u), pyA = tileY0 + (bwarp / BLOCKS_X) * 8u + 2u * (lane >> 3), pyB = pyA + 1u;
-  const uint32_t group = lane / (32u / SUBS);
+  const uint32_t px = tileX0 + (warp % BLOCKS_X) * 8u + (lane & 7u), pyA = tileY0 + (warp / BLOCKS_X) * 8u + (lane >> 3), pyB = pyA + 4u;
   const bool     insideA = px < a.width && pyA < a.height, insideB = px < a.width && pyB < a.height;
   const float    nfx = -(static_cast<float>(px) + 0.5f);
   const f32x2    nfy2 = pk(-(static_cast<float>(pyA) + 0.5f), -(static_cast<float>(pyB) + 0.5f));
+  const float    tileCx = static_cast<float>(tileX0) + 4.0f, tileCy = static_cast<float>(tileY0) + 4.0f;  // centre of warp block 0
   // 3DGUT: the model-space ray directions of this thread's two pixels (generatePinholeRay, cameras.h.slang:27-44,
   // called with SV_Position.xy AND a sub-pixel offset of 0.5, threedgut_raster.frag.slang:92 — restated as written;
   // then threedgut_raster.frag.slang:117-121), in the operation order of orc_gut_fragment
@@ -393,7 +312,7 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
       {
 #pragma unroll
         for(int j = 0; j < 3; j++)
-          stsU32(sbase + SMEM_WORLD + (tid & (BLEND_THREADS - 1u)) * 32u + (3u * p + j) * 4u, __float_as_uint(rd[j]));
+          stsU32(sbase + SMEM_WORLD + tid * 32u + (3u * p + j) * 4u, __float_as_uint(rd[j]));
       }
       float       dm[3];
 #pragma unroll
@@ -418,26 +337,27 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
   f32x2       acc = pk(1.0f, 1.0f);                           // transmittance T of the two pixels (both compositing orders)
   f32x2       asum = pk(0.f, 0.f);                            // back-to-front frames: MINUS the sum of the fragment opacities
   const f32x2 kExp = pk(-0.72134752044448170368f, -0.72134752044448170368f);  // exp(-A/2) = 2^(-A/2 * log2 e)
-  const float THRESHOLD = 1.0f / 255.0f;
-  const float BAND      = 3e-5f;  // half width of the band of A around A* = 2 ln(255 alpha) that is decided by the exact path (see the staging warp)
+  const float BAND      = 3e-5f;  // half width of the band of A around A* = 2 ln(255 alpha) that the exact path decides
   const float eps       = a.transmittanceEpsilon;
+  bool        warpDone  = __all_sync(FULL_MASK, !insideA && !insideB);
   uint32_t    nEvaluated = 0, nBlended = 0;  // COUNT only
   // SURF only: MINUS the integrated normals, picked depth and last blended splat id of the two pixels
   f32x2    sn0 = pk(0.f, 0.f), sn1 = sn0, sn2 = sn0;
   float    depthA = 0.0f, depthB = 0.0f;
   uint32_t sidA = 0xffffffffu, sidB = 0xffffffffu;
+  uint32_t surfBuf = 0;  // which ring buffer the blending loop is reading
 
-  // ---- staging warp: asynchronous gather of this lane's entry of a stage into ring entry `e` -----------------
-  auto gather = [&](uint32_t id, uint32_t e) {
+  // asynchronous gather of this thread's entry of a batch into record buffer `buf`
+  auto gather = [&](uint32_t id, uint32_t buf, uint32_t slot) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.records) + static_cast<uint64_t>(id) * REC_BYTES;
-    const uint32_t       dst = sbase + e * REC_BYTES;
+    const uint32_t       dst = sbase + buf * SMEM_REC + slot * REC_BYTES;
 #pragma unroll
     for(uint32_t k = 0; k < REC_BYTES; k += 16)
       cpAsync16(dst + k, src + k);
     if(SURF)
     {
-      cpAsync16(sbase + SMEM_SURF + e * 16u, a.surface + id);
-      stsU32(sbase + SMEM_SID + e * 4u, id);
+      cpAsync16(sbase + SMEM_SURF + (buf * BATCH + slot) * 16u, a.surface + id);
+      stsU32(sbase + SMEM_SID + (buf * BATCH + slot) * 4u, id);
     }
     if(GUT && GUTX)
     {
@@ -446,83 +366,82 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
 #pragma unroll
       for(int k = 1; k < GUT_MAX_INSTANCES; k++)
         inst += (static_cast<uint32_t>(k) < a.gut.instanceCount && id >= a.gut.instanceOffset[k]) ? 1u : 0u;
-      stsU32(sbase + SMEM_INST + e * 4u, inst);
+      stsU32(sbase + SMEM_INST + (buf * BATCH + slot) * 4u, inst);
     }
   };
-  // ---- staging warp: classify this lane's (landed) ring entry `e`: which sub-blocks of the band can it touch?
-  // Sub-block b = (block row * BLOCKS_X + block column) * SUBS + lane group: 8 x SUB_ROWS pixels. Returns the hit bits.
-  auto classify = [&](bool have, uint32_t e) -> uint32_t {
-    uint32_t       bits   = 0;
-    const float    cx0    = static_cast<float>(tileX0) + 4.0f;                           // x centre of the pixel centres of block column 0
-    const float    cy0    = static_cast<float>(tileY0) + 0.5f * static_cast<float>(SUB_ROWS);  // y centre of sub-block row 0
-    const float    halfY  = 0.5f * static_cast<float>(SUB_ROWS - 1);
+  // classify this thread's (landed) entry: per-warp-block hit bits -> per-warp hit masks
+  auto classify = [&](bool have, uint32_t buf, uint32_t slot) {
+    uint32_t bits = 0;
     if(have && GUT)
     {
       // 3DGUT quad: axis-aligned rectangle centre +- extent (EXTENT_CONIC); a block of pixel centres
       // [x0+0.5, x0+7.5] overlaps it iff |block centre - c| <= extent + 3.5 on both axes
-      float4 r0 = ldsV4(sbase + e * REC_BYTES);  // cx cy ex ey
+      float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * REC_BYTES);  // cx cy ex ey
       if(GUTX && a.gut.extentEigen)
       {
         // words 2,3 hold w1 = b1 / |b1|^2, word 11 k = |w2| / |w1|, w2 = k (w1.y, -w1.x): bounding box of centre +- b1 +- b2
-        const float k   = __uint_as_float(ldsU32(sbase + e * REC_BYTES + 44));
+        const float k   = __uint_as_float(ldsU32(sbase + buf * SMEM_REC + slot * REC_BYTES + 44));
         const float i1  = 1.0f / (r0.z * r0.z + r0.w * r0.w), i2 = i1 / k;  // 1/|w1|^2, and b2 = w2 / |w2|^2 = (w1.y, -w1.x) / (k |w1|^2)
         const float b1x = r0.z * i1, b1y = r0.w * i1, b2x = r0.w * i2, b2y = -r0.z * i2;
         r0.z = (fabsf(b1x) + fabsf(b2x)) * 1.0001f, r0.w = (fabsf(b1y) + fabsf(b2y)) * 1.0001f;
       }
 #pragma unroll
-      for(uint32_t b = 0; b < NBLOCKS; b++)
+      for(uint32_t b = 0; b < BLEND_WARPS; b++)
       {
-        const uint32_t blk = b / SUBS, sub = b % SUBS;
-        const float ddx = cx0 + static_cast<float>(8u * (blk % BLOCKS_X)) - r0.x;
-        const float ddy = cy0 + static_cast<float>(8u * (blk / BLOCKS_X) + SUB_ROWS * sub) - r0.y;
-        if(fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + halfY + 0.001f)
+        const float ddx = tileCx + static_cast<float>(8u * (b % BLOCKS_X)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b / BLOCKS_X)) - r0.y;
+        if(fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + 3.501f)
           bits |= 1u << b;
       }
     }
     else if(have)
     {
-      const uint32_t src = sbase + e * REC_BYTES;
+      const uint32_t src = sbase + buf * SMEM_REC + slot * REC_BYTES;
       const float4   r0 = ldsV4(src), r1 = ldsV4(src + 16), r2 = ldsV4(src + 32);
       const uint32_t bb0 = __float_as_uint(r2.z), bb1 = __float_as_uint(r2.w);
       const uint32_t x0 = bb0 & 0xffffu, y0 = bb0 >> 16, x1 = bb1 & 0xffffu, y1 = bb1 >> 16;
-      // Separating-axis test along the splat's own axes: over a block of pixel centres (half extents 3.5 x halfY) the
-      // fragPos component f_i = dot(p - c, w_i) stays within f_i(centre) +- e_i, and |f_i| > L everywhere means A > L^2
-      // everywhere. A fragment survives only if A <= 8 and exp(-A/2) * alpha > 1/255, i.e. A < 2 ln(255 alpha):
-      // L^2 = min(8, 2 ln(255 alpha)), with margins for the approximate log / sqrt and the rounding of f_i.
+      // warp blocks whose 8x8 pixels the pixel bbox overlaps (bit b = block (b % BLOCKS_X, b / BLOCKS_X))
+#pragma unroll
+      for(uint32_t b = 0; b < BLEND_WARPS; b++)
+      {
+        const uint32_t bx = tileX0 + 8u * (b % BLOCKS_X), by = tileY0 + 8u * (b / BLOCKS_X);
+        if(x0 <= bx + 7u && x1 >= bx && y0 <= by + 7u && y1 >= by)
+          bits |= 1u << b;
+      }
+      // Separating-axis test along the splat's own axes: over an 8x8 block of pixel centres (half
+      // extents 3.5) the fragPos component f_i = dot(p - c, w_i) stays within f_i(centre) +- e_i, and
+      // |f_i| > L everywhere means A > L^2 everywhere. A fragment survives only if A <= 8 and
+      // exp(-A/2) * alpha > 1/255, i.e. A < 2 ln(255 alpha): L^2 = min(8, 2 ln(255 alpha)), with margins
+      // for the approximate log / sqrt and the rounding of f_i.
       float lim = 2.8292f;
       if(!NOGAUSS)
       {
         const float amax = 1.3862943611f * __log2f(255.0f * r2.y) * 1.0001f + 1e-3f;
         lim              = amax > 0.0f ? __fsqrt_rn(fminf(amax, 8.0f)) * 1.0002f + 2e-4f : -1.0f;
       }
-      const float l1 = lim + 3.5f * fabsf(r0.z) + halfY * fabsf(r0.w), l2 = lim + 3.5f * fabsf(r1.x) + halfY * fabsf(r1.y);
-      // f_i at the centre of sub-block (column bx, row sy) = gx_i[bx] + gy_i[sy]
-      float gx1[BLOCKS_X], gx2[BLOCKS_X];
+      const float e1 = 3.5f * (fabsf(r0.z) + fabsf(r0.w)), e2 = 3.5f * (fabsf(r1.x) + fabsf(r1.y));
 #pragma unroll
-      for(uint32_t bx = 0; bx < BLOCKS_X; bx++)
+      for(uint32_t b = 0; b < BLEND_WARPS; b++)
       {
-        const float ddx = cx0 + static_cast<float>(8u * bx) - r0.x;
-        gx1[bx] = ddx * r0.z, gx2[bx] = ddx * r1.x;
+        const float ddx = tileCx + static_cast<float>(8u * (b % BLOCKS_X)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b / BLOCKS_X)) - r0.y;
+        const float f1 = fabsf(ddx * r0.z + ddy * r0.w) - e1, f2 = fabsf(ddx * r1.x + ddy * r1.y) - e2;
+        if(!(fmaxf(f1, f2) <= lim))
+          bits &= ~(1u << b);
       }
-#pragma unroll
-      for(uint32_t sy = 0; sy < BLOCKS_Y * SUBS; sy++)
-      {
-        const uint32_t rowY = tileY0 + SUB_ROWS * sy;  // first pixel row of the sub-block row
-        const float    ddy  = cy0 + static_cast<float>(SUB_ROWS * sy) - r0.y;
-        const float    gy1 = ddy * r0.w, gy2 = ddy * r1.y;
-        const bool     rowHit = y0 <= rowY + (SUB_ROWS - 1u) && y1 >= rowY;
-#pragma unroll
-        for(uint32_t bx = 0; bx < BLOCKS_X; bx++)
-        {
-          const uint32_t colX = tileX0 + 8u * bx;
-          const bool     hit  = rowHit && x0 <= colX + 7u && x1 >= colX && fabsf(gx1[bx] + gy1) <= l1 && fabsf(gx2[bx] + gy2) <= l2;
-          // sub-block index: ((block row * BLOCKS_X + bx) * SUBS + group), block row = sy / SUBS, group = sy % SUBS
-          if(hit)
-            bits |= 1u << (((sy / SUBS) * BLOCKS_X + bx) * SUBS + (sy % SUBS));
-        }
-      }
+      // the bbox words of the staged record have served their purpose: they become the fragment stage's discard
+      // thresholds in A (see evalFrag). A* through the SFU log (error < 3e-6 in A); the oracle's own decision
+      // exp(-A/2) * alpha > 1/255 flips within 1e-6 of A*, so anything farther than the 3e-5 band from A* is decided
+      // the same way by both, and the band itself goes to the exact path.
+      const float aStar = NOGAUSS ? 3.0e38f : 1.3862943611198906f * __log2f(255.0f * r2.y);
+      stsU32(src + 40, __float_as_uint(fminf(8.0f, aStar - 3e-5f)));
+      stsU32(src + 44, __float_as_uint(aStar));
     }
-    return bits;
+#pragma unroll
+    for(uint32_t b = 0; b < BLEND_WARPS; b++)
+    {
+      const unsigned mb = __ballot_sync(FULL_MASK, (bits >> b) & 1u);
+      if(lane == b)  // hit[buf][blend warp b][word = slot / 32]
+        stsU32(sbase + SMEM_HIT + ((buf * BLEND_WARPS + b) * (BATCH / 32) + (slot >> 5)) * 4u, mb);
+    }
   };
 
   // One list entry against this thread's two pixels, up to (not including) the ordered blend.
@@ -531,7 +450,7 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
   struct Frag
   {
     f32x2  A2, n2;  // A of the two pixels; minus opacity (masked)
-    float  gmin;    // distance of the nearer of the two A values to A* (the caller sends near misses to the exact path)
+    float  gmin;    // distance of the nearer of the two A values to A* (near misses go to the exact path)
     float  astar;
     float  r, g, b, alpha;
     uint32_t addr;  // shared address of the staged record (SURF: locates the entry's normal / id)
@@ -556,12 +475,12 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
       float dmA[3] = {gutDirA[0], gutDirA[1], gutDirA[2]}, dmB[3] = {gutDirB[0], gutDirB[1], gutDirB[2]};
       if(GUTX && a.gut.instanceCount > 1u)
       {
-        const uint32_t e    = (addr - sbase) / REC_BYTES;  // ring entry
-        const float*   mi   = a.gut.instanceInverse[ldsU32(sbase + SMEM_INST + e * 4u)];
+        const uint32_t slot = (addr - (sbase + surfBuf * SMEM_REC)) / REC_BYTES;
+        const float*   mi   = a.gut.instanceInverse[ldsU32(sbase + SMEM_INST + (surfBuf * BATCH + slot) * 4u)];
 #pragma unroll
         for(int p = 0; p < 2; p++)
         {
-          const uint32_t wAddr = sbase + SMEM_WORLD + (tid & (BLEND_THREADS - 1u)) * 32u + 12u * p;
+          const uint32_t wAddr = sbase + SMEM_WORLD + tid * 32u + 12u * p;
           const float    rd[3] = {__uint_as_float(ldsU32(wAddr)), __uint_as_float(ldsU32(wAddr + 4u)), __uint_as_float(ldsU32(wAddr + 8u))};
           float          dm[3];
 #pragma unroll
@@ -625,7 +544,7 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
     }
     const float4 ra  = ldsV4(addr);       // cx cy w1x w1y
     const float4 rb  = ldsV4(addr + 16);  // w2x w2y r g
-    const float4 rc  = ldsV4(addr + 32);  // b a | cut, A* (written over the bbox words by the staging warp)
+    const float4 rc  = ldsV4(addr + 32);  // b a | cut, A* (written over the bbox words by the staging thread)
     const float  ndx = __fadd_rn(ra.x, nfx);            // -(px - cx): A is even in (dx,dy)
     const f32x2  ndy2 = add2(pk(ra.y, ra.y), nfy2);
     const float  t = __fmul_rn(ndx, ra.z), u = __fmul_rn(ndx, rb.x);
@@ -633,15 +552,12 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
     const f32x2  fpy2 = fma2(ndy2, pk(rb.y, rb.y), pk(u, u));
     f.A2              = fma2(fpy2, fpy2, mul2(fpx2, fpx2));
     f.r = rb.z, f.g = rb.w, f.b = rc.x, f.alpha = rc.y;
-    // Both discards of the fragment stage in one comparison per pixel: the fragment survives iff A <= 8 and
-    // exp(-A/2) * alpha > 1/255, i.e. A < A* = 2 ln(255 alpha). The staging warp left cut = min(8, A* - band) in the
-    // record: A <= cut is a sure keep, and only a pixel whose A lies within the band of A* is sent to the exact path.
-    float Alo, Ahi;
+    float Alo, Ahi, dlo, dhi;
     upk(f.A2, Alo, Ahi);
     const bool vA = Alo <= rc.z, vB = Ahi <= rc.z;
-    float      dlo, dhi;
     upk(add2(f.A2, pk(-rc.w, -rc.w)), dlo, dhi);
-    f.gmin = fminf(fabsf(dlo), fabsf(dhi));
+    f.gmin  = fminf(fabsf(dlo), fabsf(dhi));
+    f.astar = rc.w;
     if(NOGAUSS)
       f.n2 = pk(vA ? -1.0f : 0.0f, vB ? -1.0f : 0.0f);
     else
@@ -653,7 +569,6 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
       upk(n2, nlo, nhi);
       f.n2 = pk(vA ? nlo : 0.0f, vB ? nhi : 0.0f);
     }
-    f.astar = rc.w;
     return f;
   };
   // within the guard band of the 1/255 discard threshold (rare): decide exactly, like the oracle
@@ -677,7 +592,7 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
       nEvaluated += 1u;
       nBlended += (mlo != 0.0f && insideA ? 1u : 0u) + (mhi != 0.0f && insideB ? 1u : 0u);
     }
-    // "under" update in front-to-back traversal order: C += c * opacity * T, T -= opacity * T
+    // "under" update in traversal (front-to-back) order: C += c * opacity * T, T -= opacity * T
     const f32x2 nw2 = mul2(f.n2, acc);  // -(opacity * T)
     fma2acc(c0, nw2, pk(f.r, f.r));
     fma2acc(c1, nw2, pk(f.g, f.g));
@@ -689,9 +604,9 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
     {
       // threedgs_raster.frag.slang:316-350: normal * opacity under the same operator; first depth at
       // which the transmittance drops below the iso threshold; id of the last fragment that was kept
-      const uint32_t e    = (f.addr - sbase) / REC_BYTES;  // ring entry
-      const float4   sv   = ldsV4(sbase + SMEM_SURF + e * 16u);
-      const uint32_t id   = ldsU32(sbase + SMEM_SID + e * 4u);
+      const uint32_t slot = (f.addr - (sbase + surfBuf * SMEM_REC)) / REC_BYTES;
+      const float4   sv   = ldsV4(sbase + SMEM_SURF + (surfBuf * BATCH + slot) * 16u);
+      const uint32_t id   = ldsU32(sbase + SMEM_SID + (surfBuf * BATCH + slot) * 4u);
       fma2acc(sn0, nw2, pk(sv.x, sv.x));
       fma2acc(sn1, nw2, pk(sv.y, sv.y));
       fma2acc(sn2, nw2, pk(sv.z, sv.z));
@@ -713,126 +628,57 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
     }
   };
 
-  // ring control: stage barriers (one arrival: lane 0 of the staging warp, after a warp barrier), progress words
-  const uint32_t listLen = range.x < range.y ? range.y - range.x : 0u;
-  const uint32_t nStages = (listLen + STAGE - 1) / STAGE;
-  if(tid < RING_STAGES)
-    mbarInit(sbase + SMEM_FULL + tid * 8u, 1u);
-  if(tid < BLEND_WARPS)
-    stsU32(sbase + SMEM_PROG + tid * 4u, 0u);
-  __syncthreads();  // the only CTA-wide barrier
+  if(range.x < range.y)
+  {
+    // prologue: batch 0 lands and is classified; the list index of batch 1 is already on its way
+    const bool stager = tid < BATCH;  // (warp-uniform)
+    uint32_t   idNext = 0;
+    // list position of traversal position p (p = range.x + k): front-to-back frames read the list forwards,
+    // back-to-front frames from its end (nearest fragment first)
+    auto listAt = [&](uint32_t p) -> uint32_t { return FTB ? p : range.y - 1u - (p - range.x); };
+    if(stager)
+    {
+      if(range.x + tid < range.y)
+        gather(a.tileVals[listAt(range.x + tid)], 0, tid);
+      cpAsyncCommit();
+      idNext = (range.x + BATCH + tid < range.y) ? a.tileVals[listAt(range.x + BATCH + tid)] : 0u;
+      cpAsyncWaitAll();
+      classify(range.x + tid < range.y, 0, tid);
+    }
+    __syncthreads();
+    for(uint32_t base = range.x, buf = 0;; base += BATCH, buf ^= 1u)
+    {
+      const bool more = base + BATCH < range.y;
+      if(more)
+      {
+        // records of the next batch fly into the other buffer while this one is blended
+        if(stager)
+        {
+          if(base + BATCH + tid < range.y)
+            gather(idNext, buf ^ 1u, tid);
+          cpAsyncCommit();
+          if(base + 2 * BATCH + tid < range.y)
+            idNext = a.tileVals[listAt(base + 2 * BATCH + tid)];
+        }
+      }
 
-  if(producer)
-  {
-    // ================================ staging warp ==========================================================
-    // list position of entry (stage s, lane): front-to-back frames read the list forwards, back-to-front frames from its end
-    auto listIndex = [&](uint32_t s) -> uint32_t {
-      const uint32_t k = s * STAGE + lane;
-      return FTB ? range.x + k : range.y - 1u - k;
-    };
-    auto haveEntry = [&](uint32_t s) -> bool { return s * STAGE + lane < listLen; };
-    // The list (splat ids) runs ID_AHEAD stages ahead of the record gathers, through a small shared ring filled by 4-byte
-    // cp.async copies that travel in the same commit groups as the records: by the time stage s is issued, the group that
-    // carried its ids (iteration s - ID_AHEAD <= s - 1 - LOOKAHEAD) has been waited for. Every lane reads back its own word.
-    auto idSlot = [&](uint32_t s) -> uint32_t { return sbase + SMEM_IDS + ((s % ID_RING) * STAGE + lane) * 4u; };
-    {
-      uint32_t first[ID_AHEAD];
-#pragma unroll
-      for(uint32_t k = 0; k < ID_AHEAD; k++)
-        first[k] = haveEntry(k) ? a.tileVals[listIndex(k)] : 0u;
-#pragma unroll
-      for(uint32_t k = 0; k < ID_AHEAD; k++)
-        stsU32(idSlot(k), first[k]);
-    }
-    bool allDone = false;
-    for(uint32_t s = 0; s < nStages + LOOKAHEAD && !allDone; s++)
-    {
-      if(s < nStages)
+      if(!warpDone)
       {
-        // the stage's ring slot is free once every blending warp is past stage s - RING_STAGES
-        for(;;)
+        const uint32_t recBase = sbase + buf * SMEM_REC;
+        surfBuf                = buf;
+        const uint32_t hitBase = sbase + SMEM_HIT + (buf * BLEND_WARPS + warp) * (BATCH / 32) * 4u;
+#pragma unroll 1
+        for(uint32_t chunk = 0; chunk < BATCH / 32; chunk++)
         {
-          const uint32_t p    = lane < BLEND_WARPS ? ldsAcquire(sbase + SMEM_PROG + lane * 4u) : 0xffffffffu;
-          const uint32_t pmin = __reduce_min_sync(FULL_MASK, p);
-          if(pmin == 0xffffffffu)
-            allDone = true;  // every warp block is saturated: nobody needs the rest of the list
-          if(allDone || s < RING_STAGES || pmin + RING_STAGES > s)
-            break;
-          __nanosleep(40);
-        }
-        if(allDone)
-          break;
-        if(haveEntry(s))
-          gather(ldsU32(idSlot(s)), (s % RING_STAGES) * STAGE + lane);
-        if(haveEntry(s + ID_AHEAD))
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(idSlot(s + ID_AHEAD)), "l"(a.tileVals + listIndex(s + ID_AHEAD)) : "memory");
-      }
-      cpAsyncCommit();  // (an empty group past the end of the list keeps the wait arithmetic uniform)
-      if(s >= LOOKAHEAD)
-      {
-        const uint32_t t = s - LOOKAHEAD, slot = t % RING_STAGES;
-        cpAsyncWaitGroup<LOOKAHEAD>();  // this lane's record of stage t has landed
-        const uint32_t bits = classify(haveEntry(t), slot * STAGE + lane);
-        if(!GUT && haveEntry(t))
-        {
-          // the bbox words of the staged record have served their purpose: they become the fragment stage's discard
-          // thresholds in A (see evalFrag). A* = 2 ln(255 alpha) through the SFU log (error < 3e-6 in A); the oracle's own
-          // decision exp(-A/2) * alpha > 1/255 is within 1e-6 of A* in A, so anything farther than the 3e-5 band from A*
-          // is decided the same way by both, and the band itself goes to the exact path.
-          const uint32_t rec   = sbase + (slot * STAGE + lane) * REC_BYTES;
-          const float    alpha = __uint_as_float(ldsU32(rec + 36));
-          const float    aStar = NOGAUSS ? 3.0e38f : 1.3862943611198906f * __log2f(255.0f * alpha);
-          stsU32(rec + 40, __float_as_uint(fminf(8.0f, aStar - 3e-5f)));
-          stsU32(rec + 44, __float_as_uint(aStar));
-        }
-#pragma unroll
-        for(uint32_t b = 0; b < NBLOCKS; b++)
-        {
-          const unsigned mb = __ballot_sync(FULL_MASK, (bits >> b) & 1u);
-          if(lane == b)
-            stsU32(sbase + SMEM_HIT + (slot * NBLOCKS + b) * 4u, mb);
-        }
-        // one arrival per stage (every arrival is a wake-up event for all warps sleeping on the CTA's barriers): the warp
-        // barrier orders the other lanes' writes — records landed through cp.async, thresholds, hit masks — before
-        // lane 0's releasing arrive
-        __syncwarp();
-        if(lane == 0)
-          mbarArrive(sbase + SMEM_FULL + slot * 8u);
-      }
-    }
-    cpAsyncWaitAll();
-  }
-  else
-  {
-    // ================================ blending warps ========================================================
-    bool groupDone = !insideA && !insideB;  // per lane; made uniform over the group below
-    {
-      const unsigned out  = __ballot_sync(FULL_MASK, !insideA && !insideB);
-      const unsigned gsel = (SUBS == 1 ? 0xffffffffu : ((1u << (32u / SUBS)) - 1u)) << (group * (32u / SUBS));
-      groupDone           = (out & gsel) == gsel;
-      if(out == 0xffffffffu)
-        stsRelease(sbase + SMEM_PROG + warp * 4u, 0xffffffffu);  // nothing of this block is inside the image
-      else
-        for(uint32_t s = 0; s < nStages; s++)
-        {
-          const uint32_t slot = s % RING_STAGES;
-          mbarWaitParity(sbase + SMEM_FULL + slot * 8u, (s / RING_STAGES) & 1u);
-          unsigned       m         = groupDone ? 0u : ldsU32(sbase + SMEM_HIT + (slot * NBLOCKS + warp * SUBS + group) * 4u);
-          const uint32_t stageAddr = sbase + slot * STAGE * REC_BYTES;
-          // The lane groups of the warp walk their own hit masks in lock step: a trip evaluates the next entry (or the
-          // next two, when any group still has two) of every group; a group that has run out rides along with a
-          // discarded copy, so the warp stays converged and issues each instruction once.
-          for(;;)
+          unsigned       m         = ldsU32(hitBase + chunk * 4u);
+          const uint32_t chunkAddr = recBase + chunk * 32u * REC_BYTES;
+          while(m)
           {
-            const bool has0 = m != 0u;
-            if(!__any_sync(FULL_MASK, has0))
-              break;
-            const uint32_t addr0 = stageAddr + (has0 ? __ffs(m) - 1 : 0) * REC_BYTES;
+            const uint32_t addr0 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
             m &= m - 1;
-            const bool has1 = m != 0u;
-            if(__any_sync(FULL_MASK, has1))
+            if(m)
             {
-              const uint32_t addr1 = has1 ? stageAddr + (__ffs(m) - 1) * REC_BYTES : addr0;
+              const uint32_t addr1 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
               m &= m - 1;
               Frag f0 = evalFrag(addr0), f1 = evalFrag(addr1);
               if(fminf(f0.gmin, f1.gmin) <= BAND)
@@ -840,12 +686,6 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
                 fixFrag(f0);
                 fixFrag(f1);
               }
-              if(!has0)
-                f0.n2 = pk(0.f, 0.f);
-              if(!has1)
-                f1.n2 = pk(0.f, 0.f);
-              if(COUNT)
-                nEvaluated -= (has0 ? 0u : 1u) + (has1 ? 0u : 1u);  // (copies are not evaluations of the list)
               blendFrag(f0);
               blendFrag(f1);
             }
@@ -854,39 +694,41 @@ __global__ void __launch_bounds__(BLEND_CTA_THREADS, ((SURF || GUT) ? (BLEND_CTA
               Frag f0 = evalFrag(addr0);
               if(f0.gmin <= BAND)
                 fixFrag(f0);
-              if(!has0)
-                f0.n2 = pk(0.f, 0.f);
-              if(COUNT)
-                nEvaluated -= has0 ? 0u : 1u;
               blendFrag(f0);
             }
           }
-          __syncwarp();
-          // early termination (transmittance_epsilon > 0): a lane group whose pixels are all saturated stops reading the
-          // list; a warp whose groups are all done tells the staging warp so
-          float Tlo, Thi;
-          upk(acc, Tlo, Thi);
-          const unsigned sat  = __ballot_sync(FULL_MASK, (Tlo < eps || !insideA) && (Thi < eps || !insideB));
-          groupDone           = (sat & gsel) == gsel;
-          const bool warpDone = sat == 0xffffffffu;
-          if(lane == 0)
-            stsRelease(sbase + SMEM_PROG + warp * 4u, warpDone ? 0xffffffffu : s + 1u);
-          if(warpDone)
-            break;
+          {
+            // all pixels of the block saturated (remaining transmittance below eps) -> stop reading the list
+            float Tlo, Thi;
+            upk(acc, Tlo, Thi);
+            if(__all_sync(FULL_MASK, (Tlo < eps || !insideA) && (Thi < eps || !insideB)))
+            {
+              warpDone = true;
+              break;
+            }
+          }
         }
+      }
+      if(more && stager)
+      {
+        cpAsyncWaitAll();
+        classify(base + BATCH + tid < range.y, buf ^ 1u, tid);
+      }
+      // one barrier per batch: publishes the next batch, retires this one, and votes on whether any
+      // warp block of the tile still needs the rest of the list
+      const int active = __syncthreads_or(!warpDone);
+      if(!more || !active)
+        break;
     }
   }
 
-  if(producer)
-    return;  // (the staging warp owns no pixels)
-
   if(COUNT)
   {
-    // per-lane evaluations (each covers the lane's two pixels) and fragments blended, summed over the warp
-    const uint32_t evaluated = __reduce_add_sync(FULL_MASK, nEvaluated), blended = __reduce_add_sync(FULL_MASK, nBlended);
+    // list entries this warp block evaluated (one count per warp) and fragments blended (all lanes)
+    const uint32_t blended = __reduce_add_sync(FULL_MASK, nBlended);
     if(lane == 0)
     {
-      atomicAdd(a.fragmentCounters + 0, static_cast<unsigned long long>(evaluated));
+      atomicAdd(a.fragmentCounters + 0, static_cast<unsigned long long>(nEvaluated));
       atomicAdd(a.fragmentCounters + 1, static_cast<unsigned long long>(blended));
     }
   }
@@ -947,7 +789,7 @@ static void allowSmem()
 
 void initBlendKernels()
 {
-  // dynamic shared memory above the 48 KB default (96-byte 3DGUT records, surface-info side rings)
+  // dynamic shared memory above the 48 KB default (wide tiles, 96-byte 3DGUT records)
   allowSmem<true, true, false, false, false>(), allowSmem<true, false, false, false, false>();
   allowSmem<false, true, false, false, false>(), allowSmem<false, false, false, false, false>();
   allowSmem<true, true, true, false, false>(), allowSmem<true, false, true, false, false>();
@@ -968,9 +810,9 @@ void launchBlend(const BlendArgs& args, cudaStream_t stream)
     // surface-info variant: front to back only (the context rejects other combinations)
     constexpr uint32_t SMEM = blendSmemBytes(true, false);
     if(args.disableOpacityGaussian)
-      k_blend<true, true, false, true, false><<<tiles, BLEND_CTA_THREADS, SMEM, stream>>>(args);
+      k_blend<true, true, false, true, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
     else
-      k_blend<true, false, false, true, false><<<tiles, BLEND_CTA_THREADS, SMEM, stream>>>(args);
+      k_blend<true, false, false, true, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);
     return;
   }
   if(args.gut.enabled)
@@ -984,9 +826,9 @@ void launchBlend(const BlendArgs& args, cudaStream_t stream)
   do                                                                                                                             \
   {                                                                                                                              \
     if(general)                                                                                                                  \
-      k_blend<F, G, false, false, true, true><<<tiles, BLEND_CTA_THREADS, SMEM, stream>>>(args);                                      \
+      k_blend<F, G, false, false, true, true><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                      \
     else                                                                                                                         \
-      k_blend<F, G, false, false, true, false><<<tiles, BLEND_CTA_THREADS, SMEM, stream>>>(args);                                     \
+      k_blend<F, G, false, false, true, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                     \
   } while(0)
     if(args.frontToBack)
     {
@@ -1010,9 +852,9 @@ void launchBlend(const BlendArgs& args, cudaStream_t stream)
   do                                                                                                                             \
   {                                                                                                                              \
     if(count)                                                                                                                    \
-      k_blend<F, G, true, false, false><<<tiles, BLEND_CTA_THREADS, SMEM, stream>>>(args);                                                            \
+      k_blend<F, G, true, false, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                                            \
     else                                                                                                                         \
-      k_blend<F, G, false, false, false><<<tiles, BLEND_CTA_THREADS, SMEM, stream>>>(args);                                                           \
+      k_blend<F, G, false, false, false><<<tiles, BLEND_THREADS, SMEM, stream>>>(args);                                                           \
   } while(0)
   if(args.frontToBack)
   {
