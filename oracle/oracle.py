@@ -347,3 +347,40 @@ def cpu_sort(positions, model, direction, cop, front_to_back=False, mode=1, thre
 
 def hardware_concurrency() -> int:
     return lib().orc_hardware_concurrency()
+
+
+# ---- synthetic scene of SURVEY.md 8(d), restated in numpy (so that the CPU baselines need nothing from the product) ----------
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(z):
+    """splitmix64 finaliser on uint64 arrays (wrapping arithmetic)."""
+    z = np.asarray(z, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def _stream_bits(seed: int, stream: int, idx):
+    with np.errstate(over="ignore"):
+        base = _mix64(np.uint64(seed) ^ (np.uint64(stream) * np.uint64(0xD1342543DE82EF95)))
+        return _mix64(base + (np.asarray(idx, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15))
+
+
+def synth_positions(n: int, seed: int) -> np.ndarray:
+    """positions ~ U([-1,1]^3) of the deterministic synthetic scene (counter-based splitmix64, stream 1, 24-bit uniforms):
+    bit-identical to the product's generator (tests/test_config0_cpu.py), computed here with numpy only."""
+    u = (_stream_bits(seed, 1, np.arange(3 * n, dtype=np.uint64)) >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return (np.float32(2.0) * u - np.float32(1.0)).reshape(n, 3)
+
+
+def default_camera() -> A.Camera:
+    """The reference's default camera (src/camera_set.h:48-53): eye (1.7,1.5,1.7), centre 0, up +Y, vfov 60, near 0.1, far 2000."""
+    cam = A.Camera()
+    cam.eye[:] = [1.7, 1.5, 1.7]
+    cam.ctr[:] = [0.0, 0.0, 0.0]
+    cam.up[:] = [0.0, 1.0, 0.0]
+    cam.fov_deg, cam.znear, cam.zfar = 60.0, 0.1, 2000.0
+    return cam

@@ -65,3 +65,12 @@ def test_rop16_rounding_stays_within_the_stated_bar():
         d = np.abs(a[..., :3] - b[..., :3]).max()
         assert 0.0 < d <= 4.0 / 255.0
         assert np.array_equal(b, b.astype(np.float16).astype(np.float32))  # every texel is an fp16 value
+
+
+def test_numpy_scene_restatement_matches_the_product_generator():
+    """The CPU baselines generate their inputs without loading the product library: the numpy restatement of the
+    synthetic-scene positions and the default camera must equal the product's bit for bit."""
+    for n, seed in ((1000, 0x3D650001), (100_003, 0x3D650000)):
+        assert np.array_equal(O.synth_positions(n, seed).view(np.uint32), g.synth_scene(n, 0, seed).positions.view(np.uint32))
+    a, b = O.default_camera(), g.default_camera()
+    assert bytes(a) == bytes(b)

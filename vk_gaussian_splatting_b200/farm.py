@@ -27,6 +27,48 @@ def rank_info() -> RankInfo:
     return RankInfo(int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def _gpu_cpu_affinity(local_rank: int):
+    """CPUs next to the GPU as NVML reports them (ideal CPU affinity), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        return [c for c in cpus if c < (os.cpu_count() or 0)] or None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> bool:
+    """Pin this process to the CPUs next to its GPU before any pinned host buffer is allocated (first touch puts the pages
+    on that memory node): with eight ranks copying frames to the host at once, buffers on the wrong node all cross the
+    socket interconnect. No-op when the topology is unknown."""
+    cpus = _gpu_cpu_affinity(local_rank)
+    if not cpus:
+        return False
+    try:
+        allowed = os.sched_getaffinity(0)
+        want = set(cpus) & allowed
+        if want:
+            os.sched_setaffinity(0, want)
+            return True
+    except Exception:
+        pass
+    return False
+
+
+def numa_report(local_rank: int) -> dict:
+    cpus = _gpu_cpu_affinity(local_rank)
+    try:
+        now = sorted(os.sched_getaffinity(0))
+    except Exception:
+        now = []
+    def span(c):
+        return f"{c[0]}-{c[-1]} ({len(c)})" if c else None
+    return {"gpu_cpu_affinity": span(cpus) if cpus else None, "process_cpus": span(now)}
+
+
 def view_for_rank(rank: int, n_views: int = 8) -> A.Camera:
     """View v -> rank v mod G. Rank 0 renders the reference's default camera; rank r the default eye
     rotated by r * 360/n_views degrees about +Y (8 eyes on a circle looking at the origin)."""
