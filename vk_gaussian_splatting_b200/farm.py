@@ -94,7 +94,22 @@ class Farm:
             kw = {}
             if backend == "nccl":
                 kw["device_id"] = torch.device("cuda", self.info.local_rank)
-            dist.init_process_group(backend or "gloo", **kw)
+            # NCCL prints its version banner on STDOUT when the first communicator comes up (NCCL_DEBUG=VERSION, the
+            # default of some images); callers such as bench.py own stdout (one JSON line), so the file descriptor is
+            # pointed at stderr while the communicator is created and the first collective runs
+            import sys
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group(backend or "gloo", **kw)
+                dist.barrier()
+                if backend == "nccl":
+                    torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         if self.active:
