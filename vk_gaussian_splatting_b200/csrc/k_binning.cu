@@ -108,17 +108,20 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
     if(tid == 0)
     {
       s_base = excl;
+      // 32-bit pair positions: a frame that wants 2^32 pairs or more is an overflow, not a wrap-around (every partition
+      // checks its own end, so a carry in the middle of the frame is seen too)
+      const uint64_t d64 = static_cast<uint64_t>(excl) + total;
+      const uint32_t d   = d64 > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(d64);
+      if(d64 > a.capacity)
+      {
+        a.counters->overflow       = 1u;
+        a.counters->stickyOverflow = 1u;
+        atomicMax(&a.counters->stickyPairs, d);
+      }
       if(part == parts - 1)
       {
-        const uint32_t d             = excl + total;
         a.counters->tilePairs        = d;
         a.counters->tilePairsClamped = d < a.capacity ? d : a.capacity;
-        if(d > a.capacity)
-        {
-          a.counters->overflow       = 1u;
-          a.counters->stickyOverflow = 1u;
-          atomicMax(&a.counters->stickyPairs, d);
-        }
       }
     }
   };
@@ -145,8 +148,10 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
       if(n[i] > BIN_HUGE)
       {
         const uint32_t slot = atomicAdd(&a.counters->bigCount, 1u);
-        if(slot < a.bigCapacity && g0 + n[i] <= 0xffffffffull)
-          a.bigList[slot] = make_uint4(static_cast<uint32_t>(g0), id[i], x0[i] | (y0[i] << 16), nx[i] | ((n[i] / nx[i]) << 16));
+        if(slot < a.bigCapacity)
+          // (an entry whose pairs would end beyond 2^32 is unusable: the claimed slot gets a zero-size entry, never a stale one)
+          a.bigList[slot] = (g0 + n[i] <= 0xffffffffull) ? make_uint4(static_cast<uint32_t>(g0), id[i], x0[i] | (y0[i] << 16), nx[i] | ((n[i] / nx[i]) << 16))
+                                                         : make_uint4(0u, 0u, 0u, 0u);
         else
         {
           // list full: expand it here after all (slow, still correct)
