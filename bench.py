@@ -398,6 +398,12 @@ def main():
         return out
     link = host_link_probe()
     link["numa"] = F.numa_report(local)
+    # how much of the measured link the end-to-end figure uses (per GPU, all ranks copying at the same time)
+    link["e2e_d2h_gbs_per_gpu"] = d2h_bytes * (fps_e2e / world) / 1e9
+    link["e2e_frac_of_link"] = link["e2e_d2h_gbs_per_gpu"] / link["d2h_gbs_per_gpu"]
+    link["note"] = ("e2e is bounded by the host link: every step copies one RGBA16F frame to pinned host memory; with N ranks copying at "
+                    "once the box's aggregate device-to-host bandwidth is shared (d2h_gbs_aggregate), so e2e stops scaling where the "
+                    "device-resident `value` does not")
 
     # ---- cross-rank frame check: rank r's RGBA16F frame == view r rendered on rank 0 -----------------------------
     farm_check = None

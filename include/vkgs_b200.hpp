@@ -13,6 +13,8 @@
  *   onRender -> processSortingOnGPU + drawSplatPrimitives (:335,:1298,:1369)   GaussianSplatting::onRender
  *   prmRaster / prmData / prmRtx (src/parameters.h)                      GaussianSplatting::prm (vkgs_options)
  *   prmFrame (shaderio::FrameInfo)                                       GaussianSplatting::prmFrame (vkgs_frame_params)
+ *   tryConsumeAndUploadCpuSortingResult (src/splat_set_manager_vk.cpp:3334-3416)   GaussianSplatting::onRenderCpuSorted
+ *   vrdxCmdSortKeyValueIndirect (3rdparty/vrdx/src/vk_radix_sort.cc:249-258)       GaussianSplatting::cmdSortKeyValueIndirect
  *
  * Error behaviour follows the reference's convention (bool + a logged message): every call returns false on
  * failure and lastError() holds the text; nothing throws. There is no CPU fallback: without an sm_100 device
@@ -154,6 +156,25 @@ public:
     if(stats)
       *stats = o;
     return ok;
+  }
+  /* SORTING_CPU_ASYNC_MULTI: the frame drawn from an index buffer sorted on the host (SplatSorterAsync), every id in the
+   * caller's order, frustum culling at the raster stage */
+  bool onRenderCpuSorted(const std::vector<uint32_t>& sortedIndices, void* rgbaOut, vkgs_outputs* stats = nullptr)
+  {
+    vkgs_outputs o{};
+    o.rgba        = static_cast<float*>(rgbaOut);
+    const bool ok = check(vkgs_render_presorted(m_ctx, &prmFrame, sortedIndices.data(), sortedIndices.size(), &o));
+    if(stats)
+      *stats = o;
+    return ok;
+  }
+  /* the vrdx entry point on device buffers: in place, count read on the device, caller-provided storage
+   * (sortStorageBytes), stream-ordered on `cudaStream` (nullptr = the context's own stream) */
+  static uint64_t sortStorageBytes(uint64_t maxCount) { return vkgs_sort_pairs_storage_bytes(maxCount); }
+  bool cmdSortKeyValueIndirect(uint32_t* dKeys, uint32_t* dValues, const uint32_t* dCount, uint64_t maxCount, void* dStorage,
+                               uint64_t storageBytes, void* cudaStream = nullptr)
+  {
+    return check(vkgs_sort_pairs_device(m_ctx, dKeys, dValues, dCount, maxCount, dStorage, storageBytes, cudaStream));
   }
   /* the frames-in-flight loop of nvapp::Application: enqueue, then sync() */
   bool onRenderAsync(void* pinnedRgbaOut = nullptr)

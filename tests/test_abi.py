@@ -124,9 +124,17 @@ int main() {
   vkgs_camera cam; vkgs_default_camera(&cam);
   ok = gs.updateAndUploadFrameInfoUBO(cam) && ok;
   ok = gs.onRenderAsync() || gs.sync() || gs.lastFrameStats(nullptr) || ok;
+  ok = gs.onRenderCpuSorted({0u, 1u}, nullptr) || ok;
+  ok = gs.cmdSortKeyValueIndirect(nullptr, nullptr, nullptr, 16, nullptr, vkgs_b200::GaussianSplatting::sortStorageBytes(16)) || ok;
   return (a.size() == 8 && a.maxShDegree() == 3 && b.maxShDegree() == 0 && !ok && !gs.lastError().empty()) ? 0 : 1;
 }
 """)
+    # the C++ multi-view farm (one thread + one context per GPU) builds too and fails loudly without a device
+    farm_bin = tmp_path / "farm_host"
+    _compile(["g++", "-std=c++17", "-pthread", "-Wall", "-Wextra", "-Werror", str(root / "examples" / "farm_host.cpp"), "-o", str(farm_bin)] + link)
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(farm_bin), "--gpus", "1", "--synth", "1000", "--frames", "2"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
     all_bin = tmp_path / "all_members"
     _compile(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", str(allm), "-o", str(all_bin)] + link)
     assert subprocess.run([str(all_bin)]).returncode == 0

@@ -231,8 +231,11 @@ __device__ __noinline__ float gutExactPixel(const GutFrameConstants& g, uint32_t
 // The staging thread leaves cut = min(8, A* - band) and A* in the staged record (over the bbox words, which
 // only the classification reads): A <= cut is a sure keep, and only a pixel whose A lies within the band of
 // A* is sent to the exact path (the oracle's fixed-sequence exp), so both discards cost one comparison.
+#ifndef VKGS_BLEND_RESIDENT_THREADS
+#define VKGS_BLEND_RESIDENT_THREADS 1280
+#endif
 template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT, bool GUTX = false>
-__global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : 1280) / BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
+__global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLEND_RESIDENT_THREADS) / BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
 {
   // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
   constexpr uint32_t REC_BYTES = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
