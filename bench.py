@@ -504,6 +504,10 @@ def main():
                    "eps": config_block("configs[1] back-to-front, transmittance_epsilon 2^-15", N_SPLATS, WIDTH, HEIGHT, SEED, 200,
                                        front_to_back=0, transmittance_epsilon=EPS),
                    "ftb_exact": config_block("configs[1] front-to-back, exact (no early termination)", N_SPLATS, WIDTH, HEIGHT, SEED, 200, front_to_back=1)}
+            # the same frame through the VK3DGUT raster pipeline (unscented-transform projection, per-fragment
+            # ray / particle response), reference defaults of that pipeline (EXTENT_CONIC, quadratic kernel, pinhole)
+            configs["cfg2_3dgut"] = config_block("configs[1] through the VK3DGUT pipeline, front-to-back", N_SPLATS, WIDTH, HEIGHT, SEED, 100,
+                                                 pipeline=A.PIPELINE_3DGUT, **ftb_kw)
         else:
             farm_cfg4 = config_block(f"configs[3]: 6M splats, SH3, 1920x1080, {world} independent views farmed over {world} GPUs (one view per GPU)",
                                      6_000_000, 1920, 1080, 0x3D650003, 100, **ftb_kw)

@@ -402,33 +402,40 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
       const float4   r0 = ldsV4(src), r1 = ldsV4(src + 16), r2 = ldsV4(src + 32);
       const uint32_t bb0 = __float_as_uint(r2.z), bb1 = __float_as_uint(r2.w);
       const uint32_t x0 = bb0 & 0xffffu, y0 = bb0 >> 16, x1 = bb1 & 0xffffu, y1 = bb1 >> 16;
-      // warp blocks whose 8x8 pixels the pixel bbox overlaps (bit b = block (b % BLOCKS_X, b / BLOCKS_X))
-#pragma unroll
-      for(uint32_t b = 0; b < BLEND_WARPS; b++)
-      {
-        const uint32_t bx = tileX0 + 8u * (b % BLOCKS_X), by = tileY0 + 8u * (b / BLOCKS_X);
-        if(x0 <= bx + 7u && x1 >= bx && y0 <= by + 7u && y1 >= by)
-          bits |= 1u << b;
-      }
-      // Separating-axis test along the splat's own axes: over an 8x8 block of pixel centres (half
-      // extents 3.5) the fragPos component f_i = dot(p - c, w_i) stays within f_i(centre) +- e_i, and
-      // |f_i| > L everywhere means A > L^2 everywhere. A fragment survives only if A <= 8 and
-      // exp(-A/2) * alpha > 1/255, i.e. A < 2 ln(255 alpha): L^2 = min(8, 2 ln(255 alpha)), with margins
-      // for the approximate log / sqrt and the rounding of f_i.
+      // Warp blocks (bit b = block (b % BLOCKS_X, b / BLOCKS_X)) the splat can touch: the pixel bbox must overlap the block,
+      // and a separating-axis test along the splat's own axes must not exclude it. Over an 8x8 block of pixel centres
+      // (half extents 3.5) the fragPos component f_i = dot(p - c, w_i) stays within f_i(centre) +- e_i, and |f_i| > L
+      // everywhere means A > L^2 everywhere. A fragment survives only if A <= 8 and exp(-A/2) * alpha > 1/255, i.e.
+      // A < 2 ln(255 alpha): L^2 = min(8, 2 ln(255 alpha)), with margins for the approximate log / sqrt and the rounding
+      // of f_i. f_i(centre of block (bx, by)) = gx_i[bx] + gy_i[by]: one product per block column / row and axis.
       float lim = 2.8292f;
       if(!NOGAUSS)
       {
         const float amax = 1.3862943611f * __log2f(255.0f * r2.y) * 1.0001f + 1e-3f;
         lim              = amax > 0.0f ? __fsqrt_rn(fminf(amax, 8.0f)) * 1.0002f + 2e-4f : -1.0f;
       }
-      const float e1 = 3.5f * (fabsf(r0.z) + fabsf(r0.w)), e2 = 3.5f * (fabsf(r1.x) + fabsf(r1.y));
+      const float l1 = lim + 3.5f * (fabsf(r0.z) + fabsf(r0.w)), l2 = lim + 3.5f * (fabsf(r1.x) + fabsf(r1.y));
+      float       gx1[BLOCKS_X], gx2[BLOCKS_X];
+      bool        colHit[BLOCKS_X];
 #pragma unroll
-      for(uint32_t b = 0; b < BLEND_WARPS; b++)
+      for(uint32_t bx = 0; bx < BLOCKS_X; bx++)
       {
-        const float ddx = tileCx + static_cast<float>(8u * (b % BLOCKS_X)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b / BLOCKS_X)) - r0.y;
-        const float f1 = fabsf(ddx * r0.z + ddy * r0.w) - e1, f2 = fabsf(ddx * r1.x + ddy * r1.y) - e2;
-        if(!(fmaxf(f1, f2) <= lim))
-          bits &= ~(1u << b);
+        const float    ddx = tileCx + static_cast<float>(8u * bx) - r0.x;
+        const uint32_t X   = tileX0 + 8u * bx;
+        gx1[bx] = ddx * r0.z, gx2[bx] = ddx * r1.x;
+        colHit[bx] = x0 <= X + 7u && x1 >= X;
+      }
+#pragma unroll
+      for(uint32_t by = 0; by < BLOCKS_Y; by++)
+      {
+        const float    ddy = tileCy + static_cast<float>(8u * by) - r0.y;
+        const uint32_t Y   = tileY0 + 8u * by;
+        const float    gy1 = ddy * r0.w, gy2 = ddy * r1.y;
+        const bool     rowHit = y0 <= Y + 7u && y1 >= Y;
+#pragma unroll
+        for(uint32_t bx = 0; bx < BLOCKS_X; bx++)
+          if(rowHit && colHit[bx] && fabsf(gx1[bx] + gy1) <= l1 && fabsf(gx2[bx] + gy2) <= l2)
+            bits |= 1u << (by * BLOCKS_X + bx);
       }
       // the bbox words of the staged record have served their purpose: they become the fragment stage's discard
       // thresholds in A (see evalFrag). A* through the SFU log (error < 3e-6 in A); the oracle's own decision
