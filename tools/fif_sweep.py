@@ -1,5 +1,5 @@
 import sys, time, numpy as np, torch
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import vk_gaussian_splatting_b200 as g
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 w, h = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1920, 1080)
@@ -8,7 +8,11 @@ fp = g.frame_params(g.default_camera(), w, h)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 r = g.GaussianSplatting(0, stream=stream.cuda_stream)
 r.upload(s, g.default_options(front_to_back=1, transmittance_epsilon=2.0**-15))
-for fif in (1, 2, 3, 4):
+for fif in (1, 2, 3, 4, 5, 6, 8):
+    try:
+        r.set_frames_in_flight(fif)
+    except Exception:
+        break
     r.set_frames_in_flight(fif)
     for _ in range(10): r.render_async(fp)
     r.sync()

@@ -8,7 +8,10 @@
 
 namespace vkgs {
 
-constexpr int MAX_FRAMES_IN_FLIGHT = 4;
+#ifndef VKGS_MAX_FIF
+#define VKGS_MAX_FIF 4
+#endif
+constexpr int MAX_FRAMES_IN_FLIGHT = VKGS_MAX_FIF;
 
 // Everything one in-flight frame owns. Two slots let frame N+1's front end (preprocess, sorts,
 // binning — latency-bound kernels that leave most issue slots idle) overlap frame N's blend on the
@@ -56,7 +59,7 @@ struct vkgs_ctx
   uint64_t     launches  = 0;
   uint32_t     epoch     = 0;
   bool         profiling = false;
-  int          framesInFlight = vkgs::MAX_FRAMES_IN_FLIGHT;
+  int          framesInFlight = vkgs::MAX_FRAMES_IN_FLIGHT < 4 ? vkgs::MAX_FRAMES_IN_FLIGHT : 4;
   int          nextSlot  = 0;
   int          lastSlot  = -1;
 
