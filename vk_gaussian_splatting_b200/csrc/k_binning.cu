@@ -22,7 +22,10 @@ namespace {
 constexpr int BIN_WARPS    = BIN_THREADS / 32;
 constexpr int BIN_ITEMS = 4;                        // depth ranks per thread (one 16-byte id load)
 constexpr int BIN_PART  = BIN_THREADS * BIN_ITEMS;  // ranks per partition
-constexpr int BIN_CHUNK = 2048;                     // pairs staged in shared memory per round
+#ifndef VKGS_BIN_CHUNK
+#define VKGS_BIN_CHUNK 2048
+#endif
+constexpr int BIN_CHUNK = VKGS_BIN_CHUNK;           // pairs staged in shared memory per round
 constexpr uint32_t BIN_BIG = 32;                    // splats covering more tiles than this are expanded warp-cooperatively
 constexpr uint32_t BIN_HUGE = 256;                  // ... and more than this by a whole CTA of k_bin_big (see below)
 

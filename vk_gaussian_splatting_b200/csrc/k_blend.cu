@@ -686,7 +686,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
           {
             const uint32_t addr0 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
             m &= m - 1;
+#ifdef VKGS_BLEND_SINGLE
+            if(false)
+#else
             if(m)
+#endif
             {
               const uint32_t addr1 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
               m &= m - 1;
