@@ -54,6 +54,10 @@ def child(workloads):
         r.sync()
         dt = time.perf_counter() - t0
         r.set_frames_in_flight(1)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            r.render(fp, want_image=False)   # synchronous frames, one at a time, frame left on the device
+        sync_us = (time.perf_counter() - t0) / 50 * 1e6
         r.set_profiling(True)
         acc = {}
         for _ in range(5):
@@ -63,7 +67,7 @@ def child(workloads):
             for k, v in st.ms_kernel.items():
                 acc[k] = acc.get(k, 0) + v / 5
         r.set_profiling(False)
-        print(json.dumps({"lib": os.path.basename(os.environ.get("VKGS_LIB", "default")), "workload": w, "fps": round(steps / dt, 1),
+        print(json.dumps({"lib": os.path.basename(os.environ.get("VKGS_LIB", "default")), "workload": w, "fps": round(steps / dt, 1), "sync_us": round(sync_us, 1),
                           "kernel_us": {k: round(v * 1000, 1) for k, v in acc.items() if v > 0.004}}), flush=True)
     r.close()
 

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -231,6 +232,13 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
     if(c->profiling)
       cudaEventRecord(s.ev[slot], st);
   };
+  // Programmatic dependent launch along the front-end chain (kernel -> kernel on one stream), for the synchronous call
+  // only: one frame alone is a chain of latency-bound launches and the pre-launched prologues take 17 us off it (cfg2:
+  // 357 -> 340 us); with several frames in flight the pre-launched CTAs hold registers and shared memory the other
+  // frames' kernels could use (measured 4720 -> 4510 frames/s). Off while per-kernel events are recorded between the
+  // launches (the timings would overlap), and by VKGS_NO_PDL=1 (A/B measurements).
+  static const bool pdlEnv = []() { const char* e = getenv("VKGS_NO_PDL"); return !(e && *e == '1'); }();
+  const bool        pdl    = pdlEnv && !c->profiling && !throughputMode;
 
   CU_TRY(c, cudaMemsetAsync(&s.dCounters->visible, 0, sizeof(FrameCounters) - offsetof(FrameCounters, visible), st));
   // tile list ranges: begin = 0xffffffff, end = 0 (two arrays, two byte-pattern memsets)
@@ -308,7 +316,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
     sa.ticket    = &s.dCounters->ticket[1 + p];
     sa.epoch     = nextEpoch(c);
     sa.shift     = 8 * p;
-    launchSortPass(sa, st);
+    launchSortPass(sa, st, pdl && !(presorted));
     c->launches++;
     mark(VKGS_K_SORT_PASS0 + p + 1);
   }
@@ -332,8 +340,8 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
   ba.debugFlags = c->opt._reserved[0];
   ba.bigList     = s.dBigList;
   ba.bigCapacity = BIG_LIST_CAPACITY;
-  launchBinEmit(ba, st);
-  launchBinBig(ba, st);
+  launchBinEmit(ba, st, pdl && !presorted);  // (a presorted frame's binning follows the copy of the caller's ids, not a kernel)
+  launchBinBig(ba, st, pdl);
   c->launches += 2;
   mark(VKGS_K_BIN_EMIT + 1);
   mark(VKGS_K_TILE_HIST + 1);  // (tile-id digit histograms are fused into the emit kernel)
@@ -361,7 +369,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
       sa.rangeBegin = s.dRanges;
       sa.rangeEnd   = s.dRanges + tx * ty;
     }
-    launchSortPass(sa, st);
+    launchSortPass(sa, st, pdl);
     c->launches++;
     mark(VKGS_K_TILE_SORT0 + p + 1);
   }

@@ -73,6 +73,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol). The kernels of a frame's front end are a chain of short, latency-bound
+// launches on one stream: launched with the programmatic-stream-serialization attribute, a kernel's CTAs may become
+// resident while its predecessor drains, run the part of their prologue that does not depend on it (shared-memory
+// clears, barrier inits, the ticket draw) and block in pdl_wait() until the predecessor has completed and its writes are
+// visible. Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait()
+{
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Decoupled look-back status words.
 //   bits 63..34 : epoch (unique per kernel launch that uses the array; 0 is never used)
 //   bits 33..32 : state (1 = block aggregate available, 2 = inclusive prefix available)

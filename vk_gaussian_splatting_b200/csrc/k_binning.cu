@@ -38,13 +38,15 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
   __shared__ uint32_t s_part, s_base;
   const unsigned      tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-  const uint32_t count = a.counters->visible;
-  const uint32_t parts = (count + BIN_PART - 1) / BIN_PART;
-  const uint32_t* __restrict__ sortedIds = a.sortedIds[a.sortedSel ? *a.sortedSel : 0u];
   if(tid == 0)
     s_part = atomicAdd(&a.counters->ticket[a.ticketSlot], 1u);
   for(int i = tid; i < BIN_WARPS * 2 * 256; i += BIN_THREADS)
     (&s_whist[0][0][0])[i] = 0u;
+  pdl_wait();  // (everything above is independent of the depth sort before this kernel)
+  pdl_launch_dependents();
+  const uint32_t count = a.counters->visible;
+  const uint32_t parts = (count + BIN_PART - 1) / BIN_PART;
+  const uint32_t* __restrict__ sortedIds = a.sortedIds[a.sortedSel ? *a.sortedSel : 0u];
   __syncthreads();
   const uint32_t part = s_part;
   if(part >= parts)
@@ -292,6 +294,8 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_big(const __grid_constant__
 {
   __shared__ uint32_t s_whist[BIN_WARPS][2][256];
   const unsigned      tid = threadIdx.x, lane = tid & 31u;
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t      count = min(a.counters->bigCount, a.bigCapacity);
   if(blockIdx.x >= count)
     return;
@@ -328,18 +332,18 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_big(const __grid_constant__
 
 }  // namespace
 
-void launchBinBig(const BinArgs& args, cudaStream_t stream)
+void launchBinBig(const BinArgs& args, cudaStream_t stream, bool pdl)
 {
   // (launched every frame: the list length is only known on the device; CTAs beyond it exit at once)
-  k_bin_big<<<148 * 2, BIN_THREADS, 0, stream>>>(args);
+  launchKernelPdl(k_bin_big, 148 * 2, BIN_THREADS, 0, stream, args, pdl);
 }
 
-void launchBinEmit(const BinArgs& args, cudaStream_t stream)
+void launchBinEmit(const BinArgs& args, cudaStream_t stream, bool pdl)
 {
   const uint32_t parts = (args.maxCount + BIN_PART - 1) / BIN_PART;
   if(parts == 0)
     return;
-  k_bin_emit<<<parts, BIN_THREADS, 0, stream>>>(args);
+  launchKernelPdl(k_bin_emit, parts, BIN_THREADS, 0, stream, args, pdl);
 }
 
 }  // namespace vkgs

@@ -777,6 +777,8 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   }
   }  // persistent tile loop
 
+  // this CTA has no tile left: once every CTA of the launch is here, the first sort pass may start its prologue
+  pdl_launch_dependents();
   // the last tile's append
   __syncthreads();
   if(pendKeep)

@@ -73,6 +73,20 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const __grid_cons
 #ifdef VKGS_TIMELINE
   const long long tl0 = clock64();
 #endif
+  // what does not depend on the kernel before this one: the ticket (the counter was cleared at the start of the frame) and
+  // the shared-memory tables
+  if(tid == 0)
+    sm.part = atomicAdd(a.ticket, 1u);
+  {
+    uint4* z = reinterpret_cast<uint4*>(&sm.rank);
+#pragma unroll
+    for(int i = 0; i < static_cast<int>(sizeof(sm.rank) / 16 / SORT_THREADS); i++)
+      z[i * SORT_THREADS + tid] = make_uint4(0u, 0u, 0u, 0u);
+    static_assert(sizeof(sm.rank) % (16 * SORT_THREADS) == 0, "whole uint4 rounds");
+  }
+  sm.digitCount[tid] = 0u;
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t count = *a.countPtr;
   const uint32_t parts = (count + SORT_PART - 1) / SORT_PART;
   uint32_t       cur   = a.srcSelIn ? *a.srcSelIn : 0u;
@@ -91,16 +105,6 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const __grid_cons
   const uint32_t* __restrict__ valsIn  = a.vals[cur];
   uint32_t* __restrict__       keysOut = a.keys[cur ^ 1u];
   uint32_t* __restrict__       valsOut = a.vals[cur ^ 1u];
-  if(tid == 0)
-    sm.part = atomicAdd(a.ticket, 1u);
-  {
-    uint4* z = reinterpret_cast<uint4*>(&sm.rank);
-#pragma unroll
-    for(int i = 0; i < static_cast<int>(sizeof(sm.rank) / 16 / SORT_THREADS); i++)
-      z[i * SORT_THREADS + tid] = make_uint4(0u, 0u, 0u, 0u);
-    static_assert(sizeof(sm.rank) % (16 * SORT_THREADS) == 0, "whole uint4 rounds");
-  }
-  sm.digitCount[tid] = 0u;
   __syncthreads();
   const uint32_t part = sm.part;
   if(part >= parts)
@@ -346,15 +350,15 @@ __global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t* __re
 
 }  // namespace
 
-void launchSortPass(const SortPassArgs& args, cudaStream_t stream)
+void launchSortPass(const SortPassArgs& args, cudaStream_t stream, bool pdl)
 {
   const uint32_t parts = (args.maxCount + SORT_PART - 1) / SORT_PART;
   if(parts == 0)
     return;
   if(args.rangeBegin)
-    k_sort_pass<true><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
+    launchKernelPdl(k_sort_pass<true>, parts, SORT_THREADS, sizeof(SortSmem), stream, args, pdl);
   else
-    k_sort_pass<false><<<parts, SORT_THREADS, sizeof(SortSmem), stream>>>(args);
+    launchKernelPdl(k_sort_pass<false>, parts, SORT_THREADS, sizeof(SortSmem), stream, args, pdl);
 }
 
 void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t maxCount, uint32_t* hist, int firstShift, int passes,

@@ -118,7 +118,26 @@ struct SortPassArgs
   uint32_t*       rangeEnd;
 };
 
-void launchSortPass(const SortPassArgs& args, cudaStream_t stream);
+// `pdl`: launch with the programmatic-stream-serialization attribute (the preceding work on the stream is a kernel of this
+// library that calls pdl_launch_dependents / exits; see device_common.cuh)
+void launchSortPass(const SortPassArgs& args, cudaStream_t stream, bool pdl = false);
+
+// cudaLaunchKernelEx with (or without) the programmatic-stream-serialization attribute
+template <typename Kernel, typename Args>
+inline void launchKernelPdl(Kernel kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t stream, const Args& args, bool pdl)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim          = dim3(grid, 1, 1);
+  cfg.blockDim         = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream           = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs                                          = attr;
+  cfg.numAttrs                                       = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args);
+}
 
 // Digit histograms for `passes` 8-bit digits starting at bit `firstShift` (stand-alone sort only;
 // the frame pipeline fuses its histograms into the producing kernels).
@@ -144,8 +163,8 @@ struct BinArgs
   uint32_t        bigCapacity;
 };
 
-void launchBinEmit(const BinArgs& args, cudaStream_t stream);
-void launchBinBig(const BinArgs& args, cudaStream_t stream);  // expands the huge splats k_bin_emit set aside
+void launchBinEmit(const BinArgs& args, cudaStream_t stream, bool pdl = false);
+void launchBinBig(const BinArgs& args, cudaStream_t stream, bool pdl = false);  // expands the huge splats k_bin_emit set aside
 
 
 // per-frame constants of the VK3DGUT fragment stage (FrameInfo + SplatSetDesc fields it reads)
