@@ -211,15 +211,20 @@ __global__ void __launch_bounds__(BIN_THREADS) k_bin_emit(const __grid_constant_
       const bool     big = n[i] > BIN_BIG;
       if(lo < hi && !big)
       {
+        // (the integer division only when the splat's pairs straddle a staging round; the key advances incrementally:
+        //  +1 along a tile row, + tilesX - nx + 1 at its end)
         const uint32_t j  = lo - off;
-        uint32_t       ty = j / nx[i];
-        uint32_t       tx = j - ty * nx[i];
+        uint32_t       ty = 0, tx = 0;
+        if(j != 0u)
+          ty = j / nx[i], tx = j - ty * nx[i];
+        uint32_t key = (y0[i] + ty) * a.tilesX + x0[i] + tx;
         for(uint32_t p = lo; p < hi; p++)
         {
-          s_keys[p - w] = (y0[i] + ty) * a.tilesX + x0[i] + tx;
+          s_keys[p - w] = key;
           s_vals[p - w] = id[i];
+          key++;
           if(++tx == nx[i])
-            tx = 0, ty++;
+            tx = 0, key += a.tilesX - nx[i];
         }
       }
       // a splat covering many tiles (close to the camera: up to the whole screen) is expanded by its
