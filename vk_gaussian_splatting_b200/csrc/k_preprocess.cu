@@ -40,6 +40,11 @@ struct PreSmem
   uint64_t mbarA;  // centers (+ scales): all the dist/cull stage needs
   uint64_t mbarB;  // cov6, rgba, SH: the per-splat projection stage
   uint32_t hist[4][256];  // digit histograms of this tile's keys (all four sort passes)
+  // uint8 storage formats: the decoded value of every byte, v / 255 * 2 - 1 (SH) and v / 255 (rgba), evaluated once per CTA
+  // with the IEEE division the oracle uses (threedgs_particle_buffers.h.slang:119-131) — a table look-up per coefficient
+  // instead of a ten-instruction division each
+  float    u8Sh[256];
+  float    u8Unit[256];
   uint32_t warpScan[NWARPS + 1];
   uint32_t tile;
   uint32_t basePrefix[2];  // exclusive prefix of the tile processed in iteration parity 0 / 1
@@ -61,17 +66,17 @@ __device__ __forceinline__ void mulVecMat(const float v[4], const float* m, floa
 }
 
 template <int FMT>
-__device__ __forceinline__ float loadSh(const void* base, int idx)
+__device__ __forceinline__ float loadSh(const void* base, int idx, const float* u8Table)
 {
   if constexpr(FMT == VKGS_FORMAT_FLOAT32)
     return static_cast<const float*>(base)[idx];
   else if constexpr(FMT == VKGS_FORMAT_FLOAT16)
     return __half2float(static_cast<const __half*>(base)[idx]);
-  else  // threedgs_particle_buffers.h.slang:119-131: v / 255 * range - halfRange
-    return static_cast<float>(static_cast<const uint8_t*>(base)[idx]) / 255.0f * 2.0f - 1.0f;
+  else  // threedgs_particle_buffers.h.slang:119-131: v / 255 * range - halfRange, through the per-CTA table of all 256 values
+    return u8Table[static_cast<const uint8_t*>(base)[idx]];
 }
 
-__device__ __forceinline__ float4 loadRgba(const void* base, int t, uint32_t fmt)
+__device__ __forceinline__ float4 loadRgba(const void* base, int t, uint32_t fmt, const float* u8Unit)
 {
   if(fmt == VKGS_FORMAT_FLOAT32)
     return static_cast<const float4*>(base)[t];
@@ -81,13 +86,12 @@ __device__ __forceinline__ float4 loadRgba(const void* base, int t, uint32_t fmt
     return make_float4(__half2float(h[0]), __half2float(h[1]), __half2float(h[2]), __half2float(h[3]));
   }
   const uchar4 u = static_cast<const uchar4*>(base)[t];
-  return make_float4(static_cast<float>(u.x) / 255.0f, static_cast<float>(u.y) / 255.0f, static_cast<float>(u.z) / 255.0f,
-                     static_cast<float>(u.w) / 255.0f);
+  return make_float4(u8Unit[u.x], u8Unit[u.y], u8Unit[u.z], u8Unit[u.w]);
 }
 
 // fetchViewDependentRadiance, threedgs_particle_storage.h.slang:103-159
 template <int FMT>
-__device__ __forceinline__ void shRadiance(const void* row, int rowBase, uint32_t degree, float x, float y, float z, float rgb[3])
+__device__ __forceinline__ void shRadiance(const void* row, int rowBase, uint32_t degree, float x, float y, float z, float rgb[3], const float* u8Table)
 {
   const float C1    = 0.4886025119029199f;
   const float C2[5] = {1.0925484f, -1.0925484f, 0.3153916f, -1.0925484f, 0.5462742f};
@@ -96,7 +100,7 @@ __device__ __forceinline__ void shRadiance(const void* row, int rowBase, uint32_
 #pragma unroll
   for(int c = 0; c < 3; c++)
   {
-#define S(k) loadSh<FMT>(row, rowBase + 3 * (k) + c)
+#define S(k) loadSh<FMT>(row, rowBase + 3 * (k) + c, u8Table)
     float acc = 0.0f;
     acc += C1 * (-S(0) * y + S(1) * z - S(2) * x);
     if(degree >= 2)
@@ -399,6 +403,9 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   }
   for(int i = tid; i < 4 * 256; i += PRE_TILE)
     (&sm.hist[0][0])[i] = 0u;
+  sm.u8Sh[tid]   = static_cast<float>(tid) / 255.0f * 2.0f - 1.0f;
+  sm.u8Unit[tid] = static_cast<float>(tid) / 255.0f;
+  static_assert(PRE_TILE == 256, "one table entry per thread");
   __syncthreads();
   if(tid == 0)
     claimAndLoad();
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   if(GUT && keep)
   {
     // VK3DGUT: colour (+ SH) first, then the unscented-transform projection (threedgut_raster.mesh.slang:115-218)
-    float4 col = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
+    float4 col = loadRgba(sm.rgba, tid, a.set.rgbaFormat, sm.u8Unit);
     if(a.opt.show_sh_only)
       col.x = col.y = col.z = 0.5f;
     if(hasSh)
@@ -522,7 +529,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
       const float dinv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
       d[0] *= dinv, d[1] *= dinv, d[2] *= dinv;
       float rad[3];
-      shRadiance<SHFMT>(sm.sh, 45 * static_cast<int>(tid), min(a.set.shDegree, a.fp.sh_degree), d[0], d[1], d[2], rad);
+      shRadiance<SHFMT>(sm.sh, 45 * static_cast<int>(tid), min(a.set.shDegree, a.fp.sh_degree), d[0], d[1], d[2], rad, sm.u8Sh);
       col.x += rad[0], col.y += rad[1], col.z += rad[2];
     }
     float4         rec6[6];
@@ -542,7 +549,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
   }
   else if(!GUT && keep)
   {
-    float4   col   = loadRgba(sm.rgba, tid, a.set.rgbaFormat);
+    float4   col   = loadRgba(sm.rgba, tid, a.set.rgbaFormat, sm.u8Unit);
     bool     valid = !(col.w < a.fp.alpha_cull_threshold);  // mesh.slang:165
     float    cx = 0.f, cy = 0.f, w1x = 0.f, w1y = 0.f, w2x = 0.f, w2y = 0.f, ndcDepth = 0.f;
     uint32_t bb0 = 1u, bb1 = 0u;  // empty: x1 < x0
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
           d[0] *= dinv, d[1] *= dinv, d[2] *= dinv;
           const uint32_t degree = min(a.set.shDegree, a.fp.sh_degree);
           float          rad[3];
-          shRadiance<SHFMT>(sm.sh, 45 * static_cast<int>(tid), degree, d[0], d[1], d[2], rad);
+          shRadiance<SHFMT>(sm.sh, 45 * static_cast<int>(tid), degree, d[0], d[1], d[2], rad, sm.u8Sh);
           col.x += rad[0], col.y += rad[1], col.z += rad[2];
         }
         // threedgsCovarianceProjection, threedgs.h.slang:26-56
