@@ -43,6 +43,13 @@ __device__ __forceinline__ float ex2Approx(float x)
   return y;
 }
 
+__device__ __forceinline__ float rcpApprox(float x)
+{
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // shared-memory accesses through explicit 32-bit addresses (keeps address arithmetic out of the
 // inner loop: one IMAD per splat)
 __device__ __forceinline__ float4 ldsV4(uint32_t addr)
@@ -138,7 +145,7 @@ static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && BLEND_H %
 // ring + the world-space ray directions of every thread's two pixels (multi-instance scenes only)
 __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
 {
-  return 2u * BATCH * (gut ? GUT_RECORD_WORDS : RECORD_WORDS) * 4u + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u)
+  return 2u * BATCH * (gut ? GUT_RECORD_WORDS * 4u + 16u : RECORD_WORDS * 4u) + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u)
          + (gut ? 2u * BATCH * 4u + BLEND_THREADS * 32u : 0u);
 }
 
@@ -239,7 +246,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
 {
   // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
   constexpr uint32_t REC_BYTES = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
-  constexpr uint32_t SMEM_REC  = BATCH * REC_BYTES;  // bytes of one record buffer
+  // a staged entry: the record; 3DGUT: + 16 bytes the staging thread computes (the discard thresholds in the particle's
+  // squared distance, see evalFrag)
+  constexpr uint32_t SLOT_BYTES = GUT ? REC_BYTES + 16 : REC_BYTES;
+  constexpr uint32_t SMEM_REC  = BATCH * SLOT_BYTES;  // bytes of one record buffer
   constexpr uint32_t SMEM_HIT  = 2 * SMEM_REC;       // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
   constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
   constexpr uint32_t SMEM_SID  = SMEM_SURF + 2 * BATCH * 16;
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
   // asynchronous gather of this thread's entry of a batch into record buffer `buf`
   auto gather = [&](uint32_t id, uint32_t buf, uint32_t slot) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.records) + static_cast<uint64_t>(id) * REC_BYTES;
-    const uint32_t       dst = sbase + buf * SMEM_REC + slot * REC_BYTES;
+    const uint32_t       dst = sbase + buf * SMEM_REC + slot * SLOT_BYTES;
 #pragma unroll
     for(uint32_t k = 0; k < REC_BYTES; k += 16)
       cpAsync16(dst + k, src + k);
@@ -379,11 +389,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
     {
       // 3DGUT quad: axis-aligned rectangle centre +- extent (EXTENT_CONIC); a block of pixel centres
       // [x0+0.5, x0+7.5] overlaps it iff |block centre - c| <= extent + 3.5 on both axes
-      float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * REC_BYTES);  // cx cy ex ey
+      float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * SLOT_BYTES);  // cx cy ex ey
       if(GUTX && a.gut.extentEigen)
       {
         // words 2,3 hold w1 = b1 / |b1|^2, word 11 k = |w2| / |w1|, w2 = k (w1.y, -w1.x): bounding box of centre +- b1 +- b2
-        const float k   = __uint_as_float(ldsU32(sbase + buf * SMEM_REC + slot * REC_BYTES + 44));
+        const float k   = __uint_as_float(ldsU32(sbase + buf * SMEM_REC + slot * SLOT_BYTES + 44));
         const float i1  = 1.0f / (r0.z * r0.z + r0.w * r0.w), i2 = i1 / k;  // 1/|w1|^2, and b2 = w2 / |w2|^2 = (w1.y, -w1.x) / (k |w1|^2)
         const float b1x = r0.z * i1, b1y = r0.w * i1, b2x = r0.w * i2, b2y = -r0.z * i2;
         r0.z = (fabsf(b1x) + fabsf(b2x)) * 1.0001f, r0.w = (fabsf(b1y) + fabsf(b2y)) * 1.0001f;
@@ -395,10 +405,28 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
         if(fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + 3.501f)
           bits |= 1u << b;
       }
+      // Discard thresholds of the quadratic kernel's fast path, in the particle's squared distance d (response = exp(-d/2)):
+      //   alpha = min(clamp, response * density) > 1/255   <=>  d < D2 = 2 ln(255 density)      (clamp > 1/255)
+      //   response > kernelMinResponse                       <=>  d < D1 = -2 ln(kernelMinResponse)
+      // so a fragment is kept iff d < cut = min(D1, D2); a pixel whose d lies within `bd` of D1 or D2 is re-evaluated exactly.
+      // bd: the fast path's d differs from the oracle's by about 2^-24 |ro| sqrt(d) relative in the response (the canonical
+      // origin is hundreds of units long, so the cross product cancels), i.e. 2 (2e-3 + 4e-7 |ro|) in d, with a margin.
+      {
+        const uint32_t rec     = sbase + buf * SMEM_REC + slot * SLOT_BYTES;
+        const float    density = __uint_as_float(ldsU32(rec + 28));
+        const float4   q2      = ldsV4(rec + 32);
+        const float    roLen   = (GUTX && a.gut.extentEigen) ? sqrtf(q2.x * q2.x + q2.y * q2.y + q2.z * q2.z) : q2.w;
+        const bool     alive   = !(density <= a.gut.alphaCullThreshold) && a.gut.alphaClamp > 1.0f / 255.0f;
+        const float    d2      = 1.3862943611198906f * __log2f(255.0f * density);
+        const float    d1      = a.gut.kernelMinResponse > 0.0f ? -1.3862943611198906f * __log2f(a.gut.kernelMinResponse) : 3.0e38f;
+        const float    bd      = alive ? 2.2f * (2e-3f + 4e-7f * roLen) + 1e-5f : -1.0f;
+        const float    cut     = alive ? fminf(d1, d2) : -3.0e38f;
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rec + REC_BYTES), "f"(cut), "f"(d2), "f"(d1), "f"(bd) : "memory");
+      }
     }
     else if(have)
     {
-      const uint32_t src = sbase + buf * SMEM_REC + slot * REC_BYTES;
+      const uint32_t src = sbase + buf * SMEM_REC + slot * SLOT_BYTES;
       const float4   r0 = ldsV4(src), r1 = ldsV4(src + 16), r2 = ldsV4(src + 32);
       const uint32_t bb0 = __float_as_uint(r2.z), bb1 = __float_as_uint(r2.w);
       const uint32_t x0 = bb0 & 0xffffu, y0 = bb0 >> 16, x1 = bb1 & 0xffffu, y1 = bb1 >> 16;
@@ -485,7 +513,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
       float dmA[3] = {gutDirA[0], gutDirA[1], gutDirA[2]}, dmB[3] = {gutDirB[0], gutDirB[1], gutDirB[2]};
       if(GUTX && a.gut.instanceCount > 1u)
       {
-        const uint32_t slot = (addr - (sbase + surfBuf * SMEM_REC)) / REC_BYTES;
+        const uint32_t slot = (addr - (sbase + surfBuf * SMEM_REC)) / SLOT_BYTES;
         const float*   mi   = a.gut.instanceInverse[ldsU32(sbase + SMEM_INST + (surfBuf * BATCH + slot) * 4u)];
 #pragma unroll
         for(int p = 0; p < 2; p++)
@@ -516,8 +544,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
         // two evaluation orders differ by about 2^-24 |ro| sqrt(dist) relative in the response; a pixel whose
         // alpha or response lands within 2e-3 + 4e-7 |ro| (relative) of its discard threshold is re-evaluated
         // exactly, so accept / reject decisions never differ from the oracle.
-        const float roLen = (GUTX && a.gut.extentEigen) ? sqrtf(q2.x * q2.x + q2.y * q2.y + q2.z * q2.z) : q2.w;
-        const float band  = 2e-3f + 4e-7f * roLen;
+        const float4 qc = ldsV4(addr + REC_BYTES);  // cut = min(D1, D2), D2, D1, band in d (staging thread, see classify)
         const f32x2 m0 = pk(dmA[0], dmB[0]), m1 = pk(dmA[1], dmB[1]), m2 = pk(dmA[2], dmB[2]);
         const f32x2 r0 = mul2(fma2(m2, pk(q5.y, q5.y), fma2(m1, pk(q4.z, q4.z), mul2(m0, pk(q3.w, q3.w)))), pk(q3.x, q3.x));
         const f32x2 r1 = mul2(fma2(m2, pk(q5.z, q5.z), fma2(m1, pk(q4.w, q4.w), mul2(m0, pk(q4.x, q4.x)))), pk(q3.y, q3.y));
@@ -531,16 +558,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
         float       nlo, nhi, dlo, dhi;
         upk(num, nlo, nhi);
         upk(den, dlo, dhi);
-        const float distA = __fdividef(nlo, dlo), distB = __fdividef(nhi, dhi);
+        const float distA = nlo * rcpApprox(dlo), distB = nhi * rcpApprox(dhi);
         const float respA = ex2Approx(distA * -0.72134752044448170368f), respB = ex2Approx(distB * -0.72134752044448170368f);
         const float alA = fminf(a.gut.alphaClamp, respA * q1.w), alB = fminf(a.gut.alphaClamp, respB * q1.w);
-        const bool  dense = !(q1.w <= a.gut.alphaCullThreshold);
-        const bool  inA = dense && gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyA), inB = dense && gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyB);
-        const float THR = 1.0f / 255.0f, MINR = a.gut.kernelMinResponse;
-        nOp[0] = (inA && alA > THR && respA > MINR) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
-        nOp[1] = (inB && alB > THR && respB > MINR) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
-        const bool nearA = inA && (fabsf(alA - THR) <= band * THR || fabsf(respA - MINR) <= band * MINR);
-        const bool nearB = inB && (fabsf(alB - THR) <= band * THR || fabsf(respB - MINR) <= band * MINR);
+        const bool  inA = gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyA), inB = gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyB);
+        nOp[0] = (inA && distA < qc.x) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
+        nOp[1] = (inB && distB < qc.x) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
+        const bool nearA = inA && fminf(fabsf(distA - qc.y), fabsf(distA - qc.z)) <= qc.w;
+        const bool nearB = inB && fminf(fabsf(distB - qc.y), fabsf(distB - qc.z)) <= qc.w;
         if(nearA || nearB)
         {
           if(nearA)
@@ -614,7 +639,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
     {
       // threedgs_raster.frag.slang:316-350: normal * opacity under the same operator; first depth at
       // which the transmittance drops below the iso threshold; id of the last fragment that was kept
-      const uint32_t slot = (f.addr - (sbase + surfBuf * SMEM_REC)) / REC_BYTES;
+      const uint32_t slot = (f.addr - (sbase + surfBuf * SMEM_REC)) / SLOT_BYTES;
       const float4   sv   = ldsV4(sbase + SMEM_SURF + (surfBuf * BATCH + slot) * 16u);
       const uint32_t id   = ldsU32(sbase + SMEM_SID + (surfBuf * BATCH + slot) * 4u);
       fma2acc(sn0, nw2, pk(sv.x, sv.x));
@@ -681,10 +706,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
         for(uint32_t chunk = 0; chunk < BATCH / 32; chunk++)
         {
           unsigned       m         = ldsU32(hitBase + chunk * 4u);
-          const uint32_t chunkAddr = recBase + chunk * 32u * REC_BYTES;
+          const uint32_t chunkAddr = recBase + chunk * 32u * SLOT_BYTES;
           while(m)
           {
-            const uint32_t addr0 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
+            const uint32_t addr0 = chunkAddr + (__ffs(m) - 1) * SLOT_BYTES;
             m &= m - 1;
 #ifdef VKGS_BLEND_SINGLE
             if(false)
@@ -692,7 +717,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
             if(m)
 #endif
             {
-              const uint32_t addr1 = chunkAddr + (__ffs(m) - 1) * REC_BYTES;
+              const uint32_t addr1 = chunkAddr + (__ffs(m) - 1) * SLOT_BYTES;
               m &= m - 1;
               Frag f0 = evalFrag(addr0), f1 = evalFrag(addr1);
               if(fminf(f0.gmin, f1.gmin) <= BAND)
