@@ -145,7 +145,7 @@ static_assert(BLOCKS_X * BLOCKS_Y == BLEND_WARPS && TILE_W % 8 == 0 && BLEND_H %
 // ring + the world-space ray directions of every thread's two pixels (multi-instance scenes only)
 __host__ __device__ constexpr uint32_t blendSmemBytes(bool surf, bool gut)
 {
-  return 2u * BATCH * (gut ? GUT_RECORD_WORDS * 4u + 16u : RECORD_WORDS * 4u) + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u)
+  return 2u * BATCH * (gut ? GUT_RECORD_WORDS * 4u + 48u : RECORD_WORDS * 4u) + 2u * BLEND_WARPS * (BATCH / 32) * 4u + (surf ? 2u * BATCH * 20u : 0u)
          + (gut ? 2u * BATCH * 4u + BLEND_THREADS * 32u : 0u);
 }
 
@@ -246,9 +246,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
 {
   // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
   constexpr uint32_t REC_BYTES = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
-  // a staged entry: the record; 3DGUT: + 16 bytes the staging thread computes (the discard thresholds in the particle's
-  // squared distance, see evalFrag)
-  constexpr uint32_t SLOT_BYTES = GUT ? REC_BYTES + 16 : REC_BYTES;
+  // a staged entry: the record; 3DGUT: + 48 bytes the staging thread computes for the quadratic kernel's fast path (the
+  // ray-to-canonical-space matrix with the scale folded in, the discard threshold in the particle's squared distance
+  // and its guard band, see classify / evalFrag)
+  constexpr uint32_t SLOT_BYTES = GUT ? REC_BYTES + 48 : REC_BYTES;
   constexpr uint32_t SMEM_REC  = BATCH * SLOT_BYTES;  // bytes of one record buffer
   constexpr uint32_t SMEM_HIT  = 2 * SMEM_REC;       // hit masks: [2 buffers][BLEND_WARPS warps][BATCH/32 words]
   constexpr uint32_t SMEM_SURF = SMEM_HIT + 2 * BLEND_WARPS * (BATCH / 32) * 4;
@@ -405,23 +406,29 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
         if(fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + 3.501f)
           bits |= 1u << b;
       }
-      // Discard thresholds of the quadratic kernel's fast path, in the particle's squared distance d (response = exp(-d/2)):
+      // Fast path of the quadratic kernel, per entry: M = diag(1/scale) R^T (rows M0..M2, so r = M dm), and the discard
+      // threshold in the particle's squared distance d (response = exp(-d/2)):
       //   alpha = min(clamp, response * density) > 1/255   <=>  d < D2 = 2 ln(255 density)      (clamp > 1/255)
       //   response > kernelMinResponse                       <=>  d < D1 = -2 ln(kernelMinResponse)
-      // so a fragment is kept iff d < cut = min(D1, D2); a pixel whose d lies within `bd` of D1 or D2 is re-evaluated exactly.
-      // bd: the fast path's d differs from the oracle's by about 2^-24 |ro| sqrt(d) relative in the response (the canonical
-      // origin is hundreds of units long, so the cross product cancels), i.e. 2 (2e-3 + 4e-7 |ro|) in d, with a margin.
+      // so a fragment is kept iff d < cut = min(D1, D2), and a pixel whose d lies within `bd` of cut is re-evaluated
+      // exactly (a d further than bd from the smaller threshold is decided for both). bd: the canonical origin is
+      // hundreds of units long (distance / scale), so the cross product cancels and the fast and the exact evaluation
+      // orders differ by up to about 2.6e-6 |ro| sqrt(d) in d for |ro| < 400 and less than 3e-3 beyond (fp32 emulation
+      // of both orders over 3.3M random particle / ray pairs with d in 2..14, |ro| up to 4000); the band below is more
+      // than twice that envelope everywhere.
       {
         const uint32_t rec     = sbase + buf * SMEM_REC + slot * SLOT_BYTES;
-        const float    density = __uint_as_float(ldsU32(rec + 28));
-        const float4   q2      = ldsV4(rec + 32);
+        const float4   q1      = ldsV4(rec + 16), q2 = ldsV4(rec + 32), q3 = ldsV4(rec + 48), q4 = ldsV4(rec + 64), q5 = ldsV4(rec + 80);
+        const float    density = q1.w;
         const float    roLen   = (GUTX && a.gut.extentEigen) ? sqrtf(q2.x * q2.x + q2.y * q2.y + q2.z * q2.z) : q2.w;
         const bool     alive   = !(density <= a.gut.alphaCullThreshold) && a.gut.alphaClamp > 1.0f / 255.0f;
         const float    d2      = 1.3862943611198906f * __log2f(255.0f * density);
         const float    d1      = a.gut.kernelMinResponse > 0.0f ? -1.3862943611198906f * __log2f(a.gut.kernelMinResponse) : 3.0e38f;
         const float    bd      = alive ? 2.2f * (2e-3f + 4e-7f * roLen) + 1e-5f : -1.0f;
         const float    cut     = alive ? fminf(d1, d2) : -3.0e38f;
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rec + REC_BYTES), "f"(cut), "f"(d2), "f"(d1), "f"(bd) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rec + REC_BYTES), "f"(q3.x * q3.w), "f"(q3.x * q4.z), "f"(q3.x * q5.y), "f"(cut) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rec + REC_BYTES + 16), "f"(q3.y * q4.x), "f"(q3.y * q4.w), "f"(q3.y * q5.z), "f"(bd) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rec + REC_BYTES + 32), "f"(q3.z * q4.y), "f"(q3.z * q5.x), "f"(q3.z * q5.w), "f"(0.0f) : "memory");
       }
     }
     else if(have)
@@ -503,9 +510,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
       const float4 q0 = ldsV4(addr);       // cx cy ex ey
       const float4 q1 = ldsV4(addr + 16);  // r g b a
       const float4 q2 = ldsV4(addr + 32);  // canonical ray origin
-      const float4 q3 = ldsV4(addr + 48);  // 1/scale.xyz, R00
-      const float4 q4 = ldsV4(addr + 64);  // R01 R02 R10 R11
-      const float4 q5 = ldsV4(addr + 80);  // R12 R20 R21 R22
       f.r = q1.x, f.g = q1.y, f.b = q1.z, f.alpha = q1.w;
       f.gmin = 1.0f;
       f.A2   = pk(0.f, 0.f);
@@ -538,17 +542,17 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
       }
       else
       {
-        // Fast path of the default (quadratic = Gaussian) kernel, both pixels with packed fp32:
-        // dist = |rd x ro|^2 / |rd|^2 without normalising rd first, reciprocal and exp on the SFU. Within
-        // The canonical origin is hundreds of units long (distance / scale), so the cross product cancels and the
-        // two evaluation orders differ by about 2^-24 |ro| sqrt(dist) relative in the response; a pixel whose
-        // alpha or response lands within 2e-3 + 4e-7 |ro| (relative) of its discard threshold is re-evaluated
-        // exactly, so accept / reject decisions never differ from the oracle.
-        const float4 qc = ldsV4(addr + REC_BYTES);  // cut = min(D1, D2), D2, D1, band in d (staging thread, see classify)
+        // Fast path of the default (quadratic = Gaussian) kernel, both pixels with packed fp32: d = |r x ro|^2 / |r|^2
+        // with r = M dm not normalised, reciprocal and exp on the SFU; accept / reject is one comparison of d with the
+        // entry's threshold, and a pixel inside the guard band around it is re-evaluated exactly (classify), so the
+        // decisions never differ from the oracle's.
+        const float4 g0 = ldsV4(addr + REC_BYTES);       // M00 M01 M02 cut
+        const float4 g1 = ldsV4(addr + REC_BYTES + 16);  // M10 M11 M12 bd
+        const float4 g2 = ldsV4(addr + REC_BYTES + 32);  // M20 M21 M22
         const f32x2 m0 = pk(dmA[0], dmB[0]), m1 = pk(dmA[1], dmB[1]), m2 = pk(dmA[2], dmB[2]);
-        const f32x2 r0 = mul2(fma2(m2, pk(q5.y, q5.y), fma2(m1, pk(q4.z, q4.z), mul2(m0, pk(q3.w, q3.w)))), pk(q3.x, q3.x));
-        const f32x2 r1 = mul2(fma2(m2, pk(q5.z, q5.z), fma2(m1, pk(q4.w, q4.w), mul2(m0, pk(q4.x, q4.x)))), pk(q3.y, q3.y));
-        const f32x2 r2 = mul2(fma2(m2, pk(q5.w, q5.w), fma2(m1, pk(q5.x, q5.x), mul2(m0, pk(q4.y, q4.y)))), pk(q3.z, q3.z));
+        const f32x2 r0 = fma2(m2, pk(g0.z, g0.z), fma2(m1, pk(g0.y, g0.y), mul2(m0, pk(g0.x, g0.x))));
+        const f32x2 r1 = fma2(m2, pk(g1.z, g1.z), fma2(m1, pk(g1.y, g1.y), mul2(m0, pk(g1.x, g1.x))));
+        const f32x2 r2 = fma2(m2, pk(g2.z, g2.z), fma2(m1, pk(g2.y, g2.y), mul2(m0, pk(g2.x, g2.x))));
         const float nox = -q2.x, noy = -q2.y, noz = -q2.z;
         const f32x2 cx = fma2(r1, pk(q2.z, q2.z), mul2(r2, pk(noy, noy)));
         const f32x2 cy = fma2(r2, pk(q2.x, q2.x), mul2(r0, pk(noz, noz)));
@@ -562,10 +566,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
         const float respA = ex2Approx(distA * -0.72134752044448170368f), respB = ex2Approx(distB * -0.72134752044448170368f);
         const float alA = fminf(a.gut.alphaClamp, respA * q1.w), alB = fminf(a.gut.alphaClamp, respB * q1.w);
         const bool  inA = gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyA), inB = gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyB);
-        nOp[0] = (inA && distA < qc.x) ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
-        nOp[1] = (inB && distB < qc.x) ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
-        const bool nearA = inA && fminf(fabsf(distA - qc.y), fabsf(distA - qc.z)) <= qc.w;
-        const bool nearB = inB && fminf(fabsf(distB - qc.y), fabsf(distB - qc.z)) <= qc.w;
+        // outside the quad: d = +big, beyond every threshold and band
+        const float tA = (inA ? distA : 3.0e38f) - g0.w, tB = (inB ? distB : 3.0e38f) - g0.w;
+        nOp[0] = tA < 0.0f ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
+        nOp[1] = tB < 0.0f ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
+        const bool nearA = fabsf(tA) <= g1.w, nearB = fabsf(tB) <= g1.w;
         if(nearA || nearB)
         {
           if(nearA)
