@@ -32,6 +32,7 @@ def child(workloads):
          "cfg3": (6_000_000, 3840, 2160, 0x3D650002, dict(front_to_back=1, transmittance_epsilon=2.0 ** -15)),
          "cfg5": (30_000_000, 1920, 1080, 0x3D650004, dict(front_to_back=1, transmittance_epsilon=2.0 ** -15)),
          "gut": (1_000_000, 1920, 1080, 0x3D650001, dict(front_to_back=1, transmittance_epsilon=2.0 ** -15, pipeline=1)),
+         "gutx": (1_000_000, 1920, 1080, 0x3D650001, dict(front_to_back=1, transmittance_epsilon=2.0 ** -15, pipeline=1, extent_projection=0)),
          "u8": (1_000_000, 1920, 1080, 0x3D650001, dict(front_to_back=1, transmittance_epsilon=2.0 ** -15, sh_format=2, rgba_format=2)),
          "f16": (1_000_000, 1920, 1080, 0x3D650001, dict(front_to_back=1, transmittance_epsilon=2.0 ** -15, sh_format=1, rgba_format=1))}
     scenes = {}

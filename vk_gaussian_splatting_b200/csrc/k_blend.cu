@@ -241,8 +241,11 @@ __device__ __noinline__ float gutExactPixel(const GutFrameConstants& g, uint32_t
 #ifndef VKGS_BLEND_RESIDENT_THREADS
 #define VKGS_BLEND_RESIDENT_THREADS 1280
 #endif
+#ifndef VKGS_GUT_RESIDENT_THREADS
+#define VKGS_GUT_RESIDENT_THREADS 1024
+#endif
 template <bool FTB, bool NOGAUSS, bool COUNT, bool SURF, bool GUT, bool GUTX = false>
-__global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLEND_RESIDENT_THREADS) / BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
+__global__ void __launch_bounds__(BLEND_THREADS, (GUT ? VKGS_GUT_RESIDENT_THREADS : SURF ? 768 : VKGS_BLEND_RESIDENT_THREADS) / BLEND_THREADS) k_blend(const __grid_constant__ BlendArgs a)
 {
   // records ring | hit masks | (surface info only) per-entry (normal, NDC depth) ring | splat-id ring
   constexpr uint32_t REC_BYTES = (GUT ? GUT_RECORD_WORDS : RECORD_WORDS) * 4;
@@ -391,19 +394,27 @@ __global__ void __launch_bounds__(BLEND_THREADS, ((SURF || GUT) ? 768 : VKGS_BLE
       // 3DGUT quad: axis-aligned rectangle centre +- extent (EXTENT_CONIC); a block of pixel centres
       // [x0+0.5, x0+7.5] overlaps it iff |block centre - c| <= extent + 3.5 on both axes
       float4 r0 = ldsV4(sbase + buf * SMEM_REC + slot * SLOT_BYTES);  // cx cy ex ey
+      float  w1x = 0.f, w1y = 0.f, w2x = 0.f, w2y = 0.f, lim1 = 3.0e38f, lim2 = 3.0e38f;
       if(GUTX && a.gut.extentEigen)
       {
-        // words 2,3 hold w1 = b1 / |b1|^2, word 11 k = |w2| / |w1|, w2 = k (w1.y, -w1.x): bounding box of centre +- b1 +- b2
+        // words 2,3 hold w1 = b1 / |b1|^2, word 11 k = |w2| / |w1|, w2 = k (w1.y, -w1.x): bounding box of centre +- b1 +- b2,
+        // and a separating-axis test along the quad's own axes: over a block of pixel centres (half extents 3.5)
+        // dot(p - c, w_i) stays within its value at the block centre +- 3.5 (|w_i.x| + |w_i.y|)
         const float k   = __uint_as_float(ldsU32(sbase + buf * SMEM_REC + slot * SLOT_BYTES + 44));
         const float i1  = 1.0f / (r0.z * r0.z + r0.w * r0.w), i2 = i1 / k;  // 1/|w1|^2, and b2 = w2 / |w2|^2 = (w1.y, -w1.x) / (k |w1|^2)
         const float b1x = r0.z * i1, b1y = r0.w * i1, b2x = r0.w * i2, b2y = -r0.z * i2;
+        w1x = r0.z, w1y = r0.w, w2x = r0.w * k, w2y = -r0.z * k;
+        lim1 = 1.001f + 3.501f * (fabsf(w1x) + fabsf(w1y)), lim2 = 1.001f + 3.501f * (fabsf(w2x) + fabsf(w2y));
         r0.z = (fabsf(b1x) + fabsf(b2x)) * 1.0001f, r0.w = (fabsf(b1y) + fabsf(b2y)) * 1.0001f;
       }
 #pragma unroll
       for(uint32_t b = 0; b < BLEND_WARPS; b++)
       {
         const float ddx = tileCx + static_cast<float>(8u * (b % BLOCKS_X)) - r0.x, ddy = tileCy + static_cast<float>(8u * (b / BLOCKS_X)) - r0.y;
-        if(fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + 3.501f)
+        bool        hit = fabsf(ddx) <= r0.z + 3.501f && fabsf(ddy) <= r0.w + 3.501f;
+        if(GUTX)
+          hit = hit && fabsf(ddx * w1x + ddy * w1y) <= lim1 && fabsf(ddx * w2x + ddy * w2y) <= lim2;
+        if(hit)
           bits |= 1u << b;
       }
       // Fast path of the quadratic kernel, per entry: M = diag(1/scale) R^T (rows M0..M2, so r = M dm), and the discard
@@ -829,6 +840,8 @@ static void allowSmem()
 {
   cudaFuncSetAttribute(k_blend<FTB, NOGAUSS, COUNT, SURF, GUT, GUTX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        static_cast<int>(blendSmemBytes(SURF, GUT)));
+  if(GUT)  // four resident CTAs of 144-byte slots: ask for the carveout instead of leaving it to the launch heuristic
+    cudaFuncSetAttribute(k_blend<FTB, NOGAUSS, COUNT, SURF, GUT, GUTX>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 void initBlendKernels()
