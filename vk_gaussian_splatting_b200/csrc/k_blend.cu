@@ -573,12 +573,26 @@ __global__ void __launch_bounds__(BLEND_THREADS, (GUT ? VKGS_GUT_RESIDENT_THREAD
         float       nlo, nhi, dlo, dhi;
         upk(num, nlo, nhi);
         upk(den, dlo, dhi);
-        const float distA = nlo * rcpApprox(dlo), distB = nhi * rcpApprox(dhi);
-        const float respA = ex2Approx(distA * -0.72134752044448170368f), respB = ex2Approx(distB * -0.72134752044448170368f);
-        const float alA = fminf(a.gut.alphaClamp, respA * q1.w), alB = fminf(a.gut.alphaClamp, respB * q1.w);
-        const bool  inA = gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyA), inB = gutInsideQuad(GUTX && a.gut.extentEigen, q0, q2.w, -nfx, gutPyB);
-        // outside the quad: d = +big, beyond every threshold and band
-        const float tA = (inA ? distA : 3.0e38f) - g0.w, tB = (inB ? distB : 3.0e38f) - g0.w;
+        const f32x2 dist2 = mul2(num, pk(rcpApprox(dlo), rcpApprox(dhi)));
+        const f32x2 earg2 = mul2(dist2, pk(-0.72134752044448170368f, -0.72134752044448170368f));
+        float       distA, distB, eA, eB, alA, alB;
+        upk(dist2, distA, distB);
+        upk(earg2, eA, eB);
+        upk(mul2(pk(ex2Approx(eA), ex2Approx(eB)), pk(q1.w, q1.w)), alA, alB);
+        alA = fminf(a.gut.alphaClamp, alA), alB = fminf(a.gut.alphaClamp, alB);
+        // outside the quad: d = +big (rows) or the threshold = -big (the column both pixels share), beyond every band
+        float tA, tB;
+        if(GUTX && a.gut.extentEigen)
+        {
+          const bool inA = gutInsideQuad(true, q0, q2.w, -nfx, gutPyA), inB = gutInsideQuad(true, q0, q2.w, -nfx, gutPyB);
+          tA = (inA ? distA : 3.0e38f) - g0.w, tB = (inB ? distB : 3.0e38f) - g0.w;
+        }
+        else
+        {
+          const float cutX = fabsf(__fsub_rn(-nfx, q0.x)) <= q0.z ? g0.w : -3.0e38f;
+          tA = (fabsf(__fsub_rn(gutPyA, q0.y)) <= q0.w ? distA : 3.0e38f) - cutX;
+          tB = (fabsf(__fsub_rn(gutPyB, q0.y)) <= q0.w ? distB : 3.0e38f) - cutX;
+        }
         nOp[0] = tA < 0.0f ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
         nOp[1] = tB < 0.0f ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
         const bool nearA = fabsf(tA) <= g1.w, nearB = fabsf(tB) <= g1.w;
