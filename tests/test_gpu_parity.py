@@ -724,6 +724,24 @@ def test_3dgut_pipeline_matches_oracle(gpu_renderer):
             r.upload(s, g.default_options(pipeline=A.PIPELINE_3DGUT, **kw))
 
 
+def test_3dgut_bench_configuration_image_vs_oracle(gpu_renderer):
+    """The 3DGUT line of bench.py (`configs.cfg2_3dgut`): 1 M splats, SH3, 1080p, front to back, transmittance_epsilon
+    2^-15, pinhole, EXTENT_CONIC, quadratic kernel — the fast path of the blend (thresholds in squared distance, guard band,
+    exact re-evaluation) over a few hundred million fragments, four frames in flight, against the oracle's exact frame."""
+    s = g.synth_scene(1_000_000, 3, 0x3D650001)
+    cam, w, h = g.default_camera(), 1920, 1080
+    r = gpu_renderer
+    img, oimg, st, quads = _compare_gut_frame(r, s, cam, w, h, front_to_back=1, transmittance_epsilon=2.0 ** -15)
+    assert st.visible_count > 990_000 and quads["valid"].sum() > 900_000
+    r.set_frames_in_flight(4)
+    fp = g.frame_params(cam, w, h)
+    for _ in range(4):
+        r.render_async(fp)
+    r.sync()
+    again, _, _, _ = r.render(fp)
+    assert np.array_equal(again, img)
+
+
 def test_3dgut_fisheye_camera_matches_oracle(gpu_renderer):
     """CAMERA_FISHEYE on the VK3DGUT path: fisheye dist-stage cull (ids / keys bit-exact), equidistant projection of the
     sigma points, generateFisheyeRay per pixel with the field-of-view discard; fixed-sequence atan2 / acos / sin / cos on
