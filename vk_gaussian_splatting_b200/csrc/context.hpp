@@ -21,6 +21,10 @@ struct FrameSlot
   cudaStream_t   stream = nullptr;       // front end (preprocess, sorts, binning): HIGH priority; frame completion is visible here
   cudaStream_t   streamBlend = nullptr;  // blend + copies to host: LOW priority, so another frame's latency-bound front end is
                                          // scheduled ahead of the remaining blend CTAs and fills the issue slots they leave idle
+  cudaStream_t   streamCopy = nullptr;   // synchronous frames to host memory: the frame leaves in strips of tile rows, each copied
+                                         // while the next one is blended
+  static constexpr int COPY_STRIPS = 4;
+  cudaEvent_t    evStrip[COPY_STRIPS] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t    evFront = nullptr, evBlend = nullptr;
   uint32_t *     dKeys[2] = {nullptr, nullptr}, *dIds[2] = {nullptr, nullptr};
   uint32_t*      dRecords    = nullptr;

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, (GUT ? VKGS_GUT_RESIDENT_THREAD
   const uint32_t sbase = smemBaseOpaque(s_raw);
 
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t tile = blockIdx.x / BANDS, band = blockIdx.x % BANDS;
+  const uint32_t tile = a.firstTile + blockIdx.x / BANDS, band = blockIdx.x % BANDS;
   const uint32_t tx = tile % a.tilesX, ty = tile / a.tilesX;
   const uint32_t tileX0 = tx * TILE_W, tileY0 = ty * TILE_H + band * BLEND_H;  // origin of this CTA's band
   const uint32_t px = tileX0 + (warp % BLOCKS_X) * 8u + (lane & 7u), pyA = tileY0 + (warp / BLOCKS_X) * 8u + (lane >> 3), pyB = pyA + 4u;
@@ -874,7 +874,7 @@ void initBlendKernels()
 
 void launchBlend(const BlendArgs& args, cudaStream_t stream)
 {
-  const uint32_t tiles = args.tilesX * args.tilesY * BANDS;  // CTAs
+  const uint32_t tiles = (args.tileCount ? args.tileCount : args.tilesX * args.tilesY) * BANDS;  // CTAs
   const bool count = args.fragmentCounters != nullptr;
   if(args.outNormals)
   {

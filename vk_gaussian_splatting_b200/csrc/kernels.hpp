@@ -12,7 +12,10 @@ constexpr int      PRE_TILE        = 256;   // splats per preprocess tile (= blo
 constexpr int      RECORD_WORDS    = 12;    // per-splat record, 48 B
 constexpr int      GUT_RECORD_WORDS = 24;   // 3DGUT pipeline: 96 B, see k_preprocess.cu
 constexpr int      SORT_THREADS    = 256;
-constexpr int      SORT_ITEMS      = 16;    // keys per thread
+#ifndef VKGS_SORT_ITEMS
+#define VKGS_SORT_ITEMS 16
+#endif
+constexpr int      SORT_ITEMS      = VKGS_SORT_ITEMS;  // keys per thread
 constexpr int      SORT_PART       = SORT_THREADS * SORT_ITEMS;  // 4096 pairs per partition, four partitions resident per SM
 constexpr int      BIN_THREADS     = 256;
 constexpr int      TILE_W          = 32;
@@ -196,6 +199,7 @@ struct BlendArgs
   void*           image;     // [H][W] RGBA in targetFormat (float4 / half4 / uchar4)
   uint32_t        targetFormat;
   uint32_t        width, height, tilesX, tilesY;
+  uint32_t        firstTile = 0, tileCount = 0;  // the launch covers tiles [firstTile, firstTile + tileCount) in row-major order (0 = all)
   uint32_t        frontToBack;
   uint32_t        disableOpacityGaussian;
   float           transmittanceEpsilon;
