@@ -902,3 +902,28 @@ def test_rgba16f_target_within_rop_rounding_bar(gpu_renderer):
         assert d.max() <= 4.0 / 255.0, d.max()
         if ftb:
             assert np.abs(img.astype(np.float32)[..., 3] - rop[..., 3]).max() <= 4.0 / 255.0
+
+
+def test_synchronous_strip_copies_match_the_one_piece_frame(gpu_renderer):
+    """A synchronous frame of 12 MB or more leaves the device in four strips of tile rows, each copied while the next is
+    blended (context.cu::enqueueFrame); the asynchronous path blends and copies in one piece. Same bits either way, for
+    every target format, both orders, a height that is not a whole number of tiles and pageable as well as pinned memory."""
+    import torch
+    r = gpu_renderer
+    s = g.synth_scene(200_000, 3, 0x3D650021)
+    cam = g.default_camera()
+    for fmt, tdt, (w, h) in ((A.FORMAT_FLOAT32, torch.float32, (1600, 1001)), (A.FORMAT_FLOAT16, torch.float16, (1920, 1080)),
+                             (A.FORMAT_UINT8, torch.uint8, (2560, 1307))):
+        for ftb in (1, 0):
+            r.upload(s, g.default_options(front_to_back=ftb, target_format=fmt))
+            fp = g.frame_params(cam, w, h)
+            assert w * h * 4 * (4, 2, 1)[fmt] >= 12 << 20
+            whole = torch.zeros((h, w, 4), dtype=tdt, pin_memory=True).numpy()
+            r.set_frames_in_flight(2)
+            r.render_to_host_async(fp, whole)
+            r.sync()
+            r.set_frames_in_flight(1)
+            pinned = torch.zeros((h, w, 4), dtype=tdt, pin_memory=True).numpy()
+            r.render(fp, out=pinned)
+            pageable, _, _, _ = r.render(fp)
+            assert whole.any() and np.array_equal(pinned, whole) and np.array_equal(pageable, whole)
