@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/${tag}_ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ --launch-skip 20 --launch-count 10 -f -o gpurun_out/${tag}_full \
     python tools/prof_frame.py 4 cfg2 4 > gpurun_out/${tag}_ncu_full.log 2>&1
-python tools/bench_configs.py gut gutx surf > gpurun_out/${tag}_configs.jsonl 2>&1
+python tools/bench_configs.py gut gutx surf 2 3 5 sort > gpurun_out/${tag}_configs.jsonl 2>&1
 python tools/benchmark_3dgs.py > gpurun_out/${tag}_benchmark_3dgs.log 2>&1
 # the C++ host drivers over the C ABI (include/vkgs_b200.hpp)
 L=$PWD/vk_gaussian_splatting_b200/lib
