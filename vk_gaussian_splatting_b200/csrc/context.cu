@@ -209,7 +209,7 @@ struct FrameRequest
 int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& rq, int* slotOut)
 {
   void* const hostRgba       = rq.hostRgba;
-  const bool  throughputMode = rq.throughputMode;
+  bool        throughputMode = rq.throughputMode;
   const bool  presorted      = rq.presortedIds != nullptr;
   if(!c->uploaded)
     return fail(c, VKGS_ERR_NOT_UPLOADED, "vkgs_render before vkgs_upload");
@@ -223,6 +223,17 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
   CU_TRY(c, cudaSetDevice(c->device));
   const int  si = rq.forceSlot >= 0 ? rq.forceSlot : c->nextSlot;
   FrameSlot& s  = c->slots[si];
+  // A frame of the asynchronous path that finds the device idle (the previous frame has already left it: the first frame
+  // of a burst, or a caller slower than the GPU) has nothing to share the SMs with: it takes the full-width, latency-
+  // oriented launches of the synchronous path. Same bits either way (test_four_frames_in_flight_...).
+  static const bool idleFull = []() { const char* e = getenv("VKGS_NO_IDLE_FULL"); return !(e && *e == '1'); }();
+  if(throughputMode && idleFull && rq.forceSlot < 0 && !c->profiling)
+  {
+    if(c->lastSlot < 0 || !c->slots[c->lastSlot].haveFrame || cudaEventQuery(c->slots[c->lastSlot].evBlend) == cudaSuccess)
+      throughputMode = false;
+    else
+      (void)cudaGetLastError();  // cudaErrorNotReady is not an error
+  }
   if(int rc = ensureTargets(c, s, fp.width, fp.height))
     return rc;
   const uint32_t n  = c->totalSplats;

@@ -65,7 +65,7 @@ struct vkgs_ctx
   bool         profiling = false;
   int          framesInFlight = vkgs::MAX_FRAMES_IN_FLIGHT < 4 ? vkgs::MAX_FRAMES_IN_FLIGHT : 4;
   int          nextSlot  = 0;
-  int          lastSlot  = -1;
+  int          lastSlot  = -1;  // slot of the most recently enqueued frame
 
   // scene (shared by all slots): splat sets in HBM + the instances that place them in the world.
   // Global splat id = instance.globalOffset + local id, instances in creation order — the layout of
