@@ -463,6 +463,7 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
   }
   else
   {
+    // all launches first: a copy into pageable memory blocks the caller until it is done
     for(uint32_t k = 0; k < strips; k++)
     {
       const uint32_t ty0 = bl.tilesY * k / strips, ty1 = bl.tilesY * (k + 1) / strips;
@@ -470,6 +471,10 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
       launchBlend(bl, s.streamBlend);
       c->launches++;
       CU_TRY(c, cudaEventRecord(s.evStrip[k], s.streamBlend));
+    }
+    for(uint32_t k = 0; k < strips; k++)
+    {
+      const uint32_t ty0 = bl.tilesY * k / strips, ty1 = bl.tilesY * (k + 1) / strips;
       CU_TRY(c, cudaStreamWaitEvent(s.streamCopy, s.evStrip[k], 0));
       const size_t y0 = static_cast<size_t>(ty0) * TILE_H, y1 = std::min<size_t>(static_cast<size_t>(ty1) * TILE_H, fp.height);
       CU_TRY(c, cudaMemcpyAsync(static_cast<char*>(hostRgba) + y0 * rowBytes, static_cast<const char*>(s.dImage) + y0 * rowBytes,
