@@ -927,3 +927,80 @@ def test_synchronous_strip_copies_match_the_one_piece_frame(gpu_renderer):
             r.render(fp, out=pinned)
             pageable, _, _, _ = r.render(fp)
             assert whole.any() and np.array_equal(pinned, whole) and np.array_equal(pageable, whole)
+
+
+def test_random_api_sequences_reproduce_fresh_context_frames(gpu_renderer):
+    """Host-layer state machine: a seeded random walk over the entry points a caller mixes — synchronous frames, bursts of
+    asynchronous frames (to device and to pinned host memory), viewport changes, frames-in-flight changes, colour-target
+    changes, scene re-uploads with other options, caller-ordered frames — and after every step the frame must equal, bit
+    for bit, what a second context that does nothing else renders for the same (scene, options, frame parameters)."""
+    import torch
+    rng = np.random.default_rng(0x3D650F00)
+    scenes = [g.synth_scene(60_000, 3, 0x3D650F01), g.synth_scene(25_000, 0, 0x3D650F02)]
+    optsets = [dict(front_to_back=1, transmittance_epsilon=2.0 ** -15), dict(front_to_back=0), dict(front_to_back=1, ms_antialiasing=1),
+               dict(front_to_back=1, pipeline=A.PIPELINE_3DGUT), dict(front_to_back=1, sh_format=2, rgba_format=2)]
+    sizes = [(640, 360), (333, 217), (1920, 1080), (1024, 1024), (64, 48)]
+    cams = [g.default_camera(), g.orbit_camera(3, 8), g.orbit_camera(6, 8)]
+    fmts = [(A.FORMAT_FLOAT32, torch.float32), (A.FORMAT_FLOAT16, torch.float16), (A.FORMAT_UINT8, torch.uint8)]
+    r, fresh = gpu_renderer, g.GaussianSplatting(0)
+    try:
+        state = dict(scene=0, opt=0, size=0, cam=0, fmt=0, fif=1)
+        expected = {}
+
+        def upload(which):
+            which.upload(scenes[state["scene"]], g.default_options(target_format=fmts[state["fmt"]][0], **optsets[state["opt"]]))
+
+        def want():
+            key = tuple(state[k] for k in ("scene", "opt", "size", "cam", "fmt"))
+            if key not in expected:
+                upload(fresh)
+                w, h = sizes[state["size"]]
+                expected[key] = fresh.render(g.frame_params(cams[state["cam"]], w, h))[0].copy()
+            return expected[key]
+
+        upload(r)
+        r.set_frames_in_flight(1)
+        for step in range(240):
+            op = rng.integers(0, 9)
+            w, h = sizes[state["size"]]
+            fp = g.frame_params(cams[state["cam"]], w, h)
+            if op == 0:
+                state["size"] = int(rng.integers(0, len(sizes)))
+            elif op == 1:
+                state["cam"] = int(rng.integers(0, len(cams)))
+            elif op == 2:
+                state["fif"] = int(rng.integers(1, 5))
+                r.set_frames_in_flight(state["fif"])
+            elif op == 3:
+                state["fmt"] = int(rng.integers(0, len(fmts)))
+                r.set_target_format(fmts[state["fmt"]][0])
+            elif op == 4:
+                state["scene"], state["opt"] = int(rng.integers(0, len(scenes))), int(rng.integers(0, len(optsets)))
+                upload(r)
+                r.set_frames_in_flight(state["fif"])
+            elif op == 5:
+                img = r.render(fp)[0]
+                assert np.array_equal(img, want()), f"step {step}: synchronous frame differs ({state})"
+            elif op == 6:
+                for _ in range(int(rng.integers(1, 7))):
+                    r.render_async(fp)
+                r.sync()
+                img = r.render(fp)[0]
+                assert np.array_equal(img, want()), f"step {step}: frame after an asynchronous burst differs ({state})"
+            elif op == 7:
+                bufs = [torch.zeros((h, w, 4), dtype=fmts[state["fmt"]][1], pin_memory=True).numpy() for _ in range(int(rng.integers(1, 6)))]
+                for b in bufs:
+                    r.render_to_host_async(fp, b)
+                r.sync()
+                for b in bufs:
+                    assert np.array_equal(b, want()), f"step {step}: frame copied to pinned memory differs ({state})"
+            elif op == 8 and optsets[state["opt"]].get("pipeline") != A.PIPELINE_3DGUT:
+                # caller-ordered frame in the order of the last sorted frame: AT_RASTER culling, same picture within tolerance
+                img, st, ids, _ = r.render(fp, want_sorted=True)
+                pimg, _ = r.render_presorted(fp, ids)
+                assert np.isfinite(np.asarray(pimg, np.float32)).all()
+                assert np.array_equal(r.render(fp)[0], want()), f"step {step}: frame after a caller-ordered frame differs ({state})"
+    finally:
+        fresh.close()
+        r.set_frames_in_flight(1)
+        r.set_target_format(A.FORMAT_FLOAT32)
