@@ -243,6 +243,8 @@ __host__ inline float vkgsHostU2F(uint32_t u)
 // Same operation sequence as orc_expf (oracle/vkgs_oracle.c): Cody-Waite + Cephes polynomial.
 __host__ __device__ __forceinline__ float expfExact(float x)
 {
+  if(x != x)  // exp(NaN) = NaN, like the intrinsic this stands in for (fminf / fmaxf would turn it into -87)
+    return x;
   x              = fminf(fmaxf(x, -87.0f), 88.0f);
   const float kf = rintf(VKGS_MUL(x, 1.44269504088896341f));
   float       r  = VKGS_FMA(-kf, 0.693359375f, x);

@@ -435,7 +435,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, (GUT ? VKGS_GUT_RESIDENT_THREAD
         const bool     alive   = !(density <= a.gut.alphaCullThreshold) && a.gut.alphaClamp > 1.0f / 255.0f;
         const float    d2      = 1.3862943611198906f * __log2f(255.0f * density);
         const float    d1      = a.gut.kernelMinResponse > 0.0f ? -1.3862943611198906f * __log2f(a.gut.kernelMinResponse) : 3.0e38f;
-        const float    bd      = alive ? 2.2f * (2e-3f + 4e-7f * roLen) + 1e-5f : -1.0f;
+        // Degenerate particles (a scale below 1e-18 or so: |r|^2 or |r x ro|^2 overflow in the un-normalised fast path, while
+        // the oracle's normalised order stays finite) take the exact evaluation for every pixel: an infinite band.
+        const float mMax = fmaxf(fmaxf(fmaxf(fabsf(q3.x * q3.w), fabsf(q3.x * q4.z)), fmaxf(fabsf(q3.x * q5.y), fabsf(q3.y * q4.x))),
+                                 fmaxf(fmaxf(fabsf(q3.y * q4.w), fabsf(q3.y * q5.z)), fmaxf(fmaxf(fabsf(q3.z * q4.y), fabsf(q3.z * q5.x)), fabsf(q3.z * q5.w))));
+        const float roMax = fmaxf(fmaxf(fabsf(q2.x), fabsf(q2.y)), fmaxf(fabsf(q2.z), 1.0f));
+        const bool  tame  = mMax * roMax < 1e18f;  // (false for NaN)
+        const float bd    = !alive ? -1.0f : (tame ? 2.2f * (2e-3f + 4e-7f * roLen) + 1e-5f : __uint_as_float(0x7f800000u));
         const float    cut     = alive ? fminf(d1, d2) : -3.0e38f;
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rec + REC_BYTES), "f"(q3.x * q3.w), "f"(q3.x * q4.z), "f"(q3.x * q5.y), "f"(cut) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rec + REC_BYTES + 16), "f"(q3.y * q4.x), "f"(q3.y * q4.w), "f"(q3.y * q5.z), "f"(bd) : "memory");
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, (GUT ? VKGS_GUT_RESIDENT_THREAD
         }
         nOp[0] = tA < 0.0f ? (NOGAUSS ? -1.0f : -alA) : 0.0f;
         nOp[1] = tB < 0.0f ? (NOGAUSS ? -1.0f : -alB) : 0.0f;
-        const bool nearA = fabsf(tA) <= g1.w, nearB = fabsf(tB) <= g1.w;
+        const bool nearA = !(fabsf(tA) > g1.w), nearB = !(fabsf(tB) > g1.w);  // (a NaN distance is re-evaluated too)
         if(nearA || nearB)
         {
           if(nearA)

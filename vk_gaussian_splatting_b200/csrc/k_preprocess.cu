@@ -473,7 +473,13 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
           keep = false;
       }
     }
-    key = a.opt.front_to_back ? encodeMinMaxFp32(depth) : encodeMinMaxFp32(-depth);
+    // A NaN depth (NaN / inf position: every cull comparison is false, the splat is kept) takes the canonical quiet NaN
+    // 0x7FFFFFFF an arithmetic instruction of this GPU returns, AFTER the negation of the back-to-front order: its key is
+    // 0xFFFFFFFF and it sorts last in both orders, whatever instruction the compiler picks for the negation.
+    float kd = a.opt.front_to_back ? depth : -depth;
+    if(kd != kd)
+      kd = __uint_as_float(0x7fffffffu);
+    key = encodeMinMaxFp32(kd);
   }
 
   // ---- deterministic append, part 1: publish this tile's visible count as early as possible ----
