@@ -11,7 +11,11 @@ from oracle import oracle as O
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 pipeline = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 attrs = sys.argv[3].split(",") if len(sys.argv) > 3 else ["positions", "f_dc", "f_rest", "opacity", "scale", "rotation"]
+
+FINITE = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 3e38, -3e38, 1e20, -1e20, 1e-20, 88.0, -88.0, 104.0, -104.0, 17.0, -17.0, 5.5, -5.5], np.float32)
 SPECIAL = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-45, -1e-45, 1e-38, 3e38, -3e38, 1e20, -1e20, 1e-20, 88.0, -88.0, 104.0, -104.0], np.float32)
+if len(sys.argv) > 4 and sys.argv[4] == "finite":
+    SPECIAL = FINITE
 r = g.GaussianSplatting(0)
 bad = 0
 for t in range(trials):
@@ -54,6 +58,7 @@ for t in range(trials):
     d = np.abs(np.where(both, img, 0) - np.where(both, oimg, 0))
     if not ftb:
         d[..., 3] /= np.maximum(1.0, np.abs(np.where(both[..., 3], oimg[..., 3], 0)))
+    d = d / np.maximum(1.0, np.abs(np.where(both, oimg, 0)))  # huge colours: relative
     if d.max() > 1e-4:
         msg.append(f"max diff {d.max():.3g} at {np.unravel_index(d.argmax(), d.shape)}")
     print(f"trial {t} {kw}: " + ("ok" if not msg else "MISMATCH " + "; ".join(msg)), flush=True)
