@@ -1088,10 +1088,29 @@ def test_random_options_cameras_and_viewports_match_oracle(gpu_renderer):
     point cloud / SH-only / no-gaussian modes, kernel degrees, quad extents, fisheye), cameras (inside the cloud, far away,
     5 ... 170 degree fields of view, other near / far planes), viewports (1x1 ... 640x97) and per-frame parameters — ids /
     keys bit-exact and the image within tolerance in every trial."""
+    failures = []
+    assert _tool("fuzz_options").run(120, 0, gpu_renderer, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
+
+
+def _tool(name):
     import importlib.util
     import pathlib
-    spec = importlib.util.spec_from_file_location("fuzz_options", pathlib.Path(__file__).resolve().parent.parent / "tools" / "fuzz_options.py")
+    spec = importlib.util.spec_from_file_location(name, pathlib.Path(__file__).resolve().parent.parent / "tools" / f"{name}.py")
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    return mod
+
+
+def test_random_multi_instance_scenes_match_oracle(gpu_renderer):
+    """A slice of tools/fuzz_instances.py: 1-8 instances of 1-3 splat sets (ragged sizes, mixed SH degrees) under random
+    rotations, translations, uniform / non-uniform / mirrored scales, random options and viewports."""
     failures = []
-    assert mod.run(120, 0, gpu_renderer, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
+    assert _tool("fuzz_instances").run(40, 0, gpu_renderer, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
+
+
+def test_sort_pairs_fuzz_against_stable_argsort(gpu_renderer):
+    """A slice of tools/fuzz_sort.py: sizes around the partition boundaries (0, 1, 4095 / 4096 / 4097, 65 536 +- 1, 2^20 + 1,
+    3 000 001) and adversarial key distributions (constant, two values, sorted, reversed, few live bits, one live byte, one
+    hot bin, a multiplicative hash), against numpy's stable argsort."""
+    failures = []
+    assert _tool("fuzz_sort").run(120, gpu_renderer, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
