@@ -1114,3 +1114,11 @@ def test_sort_pairs_fuzz_against_stable_argsort(gpu_renderer):
     hot bin, a multiplicative hash), against numpy's stable argsort."""
     failures = []
     assert _tool("fuzz_sort").run(120, gpu_renderer, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
+
+
+def test_random_surface_info_frames_match_oracle(gpu_renderer):
+    """A slice of tools/fuzz_surface.py: NEED_SURFACE_INFO side outputs (normals, picked depth + transmittance, splat id) on
+    random scenes with flat and needle-like particles, cameras inside and outside the cloud, other iso / thin-particle
+    thresholds, both normal transports."""
+    failures = []
+    assert _tool("fuzz_surface").run(40, 0, gpu_renderer, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
