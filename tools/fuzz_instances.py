@@ -30,11 +30,19 @@ def run(trials, first, r, log=print):
         sets = [g.synth_scene(int(rng.choice([1, 77, 1000, 4099, 9000])), int(rng.choice([0, 3])), 0x3D65D000 + 16 * t + k) for k in range(nsets)]
         inst = [(int(rng.integers(0, nsets)), *random_transform(rng)) for _ in range(int(rng.integers(1, 9)))]
         kw = dict(front_to_back=int(rng.integers(0, 2)), ms_antialiasing=int(rng.integers(0, 2)), frustum_culling_mode=int(rng.integers(0, 3)))
+        gut = rng.random() < 0.35 and len(inst) <= 8
+        if gut:
+            kw.update(pipeline=A.PIPELINE_3DGUT, extent_projection=int(rng.integers(0, 2)))
         cam = g.orbit_camera(int(rng.integers(0, 8)), 8) if rng.random() < 0.5 else g.default_camera()
         w, h = [int(x) for x in rng.choice([(320, 200), (333, 217), (64, 48), (640, 97)])]
         r.upload_scene(sets, inst, g.default_options(**kw))
         img, st, ids, keys = r.render(g.frame_params(cam, w, h), want_sorted=True)
-        oimg, okeys, oids = O.render_scene([O.Packed(s) for s in sets], inst, O.frame_params(cam, w, h), O.default_options(**kw))
+        if gut:
+            okw = {k: v for k, v in kw.items() if k != "pipeline"}
+            oimg, okeys, oids = O.render_scene([O.Packed(s) for s in sets], inst, O.frame_params(cam, w, h), O.default_gut_options(**okw),
+                                               rotations=[s.rotation for s in sets])
+        else:
+            oimg, okeys, oids = O.render_scene([O.Packed(s) for s in sets], inst, O.frame_params(cam, w, h), O.default_options(**kw))
         msg = []
         if st.visible_count != len(oids):
             msg.append(f"visible {st.visible_count} vs {len(oids)}")
@@ -43,7 +51,10 @@ def run(trials, first, r, log=print):
         d = np.abs(img - oimg)
         if not kw["front_to_back"]:
             d[..., 3] /= np.maximum(1.0, np.abs(oimg[..., 3]))
-        if not (d.max() <= 1e-4):
+        tol = 1e-4
+        if gut:  # |ro| = distance / scale in the instance's model space (the instance scale cancels)
+            tol += 4e-8 * max(float(20.0 / np.exp(s.scale.min())) for s in sets)
+        if not (d.max() <= tol):
             msg.append(f"max diff {d.max():.3g}")
         if msg:
             log(f"trial {t}: sets {[s.size() for s in sets]} instances {[i[0] for i in inst]} {w}x{h} {kw} -> MISMATCH", "; ".join(msg), flush=True)
