@@ -19,6 +19,12 @@ def run(trials, first, r, log=print):
             s.scale[::int(rng.integers(5, 90)), :2] = np.log(np.float32(10.0 ** rng.uniform(-9, -3)))
         if rng.random() < 0.3:
             s.scale += np.float32(rng.uniform(-1.5, 2.0))
+        if os.environ.get("FUZZ_SPECIAL"):
+            SPECIAL = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-45, 1e-38, 3e38, -3e38, 1e20, -1e20, 88.0, -88.0, 104.0, -104.0], np.float32)
+            for name in ("positions", "scale", "rotation"):
+                flat = getattr(s, name).reshape(-1)
+                k = int(rng.integers(1, 30))
+                flat[rng.integers(0, flat.size, k)] = SPECIAL[rng.integers(0, SPECIAL.size, k)]
         kw = dict(front_to_back=1, quantize_normals=int(rng.integers(0, 2)), ms_antialiasing=int(rng.integers(0, 2)),
                   frustum_culling_mode=int(rng.integers(0, 3)))
         cam = g.orbit_camera(int(rng.integers(0, 8)), 8) if rng.random() < 0.5 else g.default_camera()
