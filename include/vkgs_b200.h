@@ -274,7 +274,9 @@ VKGS_API int vkgs_render(vkgs_ctx* ctx, const vkgs_frame_params* fp, vkgs_output
 VKGS_API int vkgs_render_presorted(vkgs_ctx* ctx, const vkgs_frame_params* fp, const uint32_t* ids, uint64_t count, vkgs_outputs* out);
 /* Stream-ordered: enqueue one frame, result stays in the device framebuffer. Up to four frames are
  * in flight, each on its own pair of internal streams (the frames-in-flight of the reference's swapchain loop,
- * nvpro_core2/nvapp/application.cpp:517-548); completion order == submission order. */
+ * nvpro_core2/nvapp/application.cpp:517-548); completion order == submission order. The call returns at once unless
+ * `frames in flight` frames are already queued: then it waits for the oldest one (whose slot it reuses), like the fence
+ * wait of that loop. */
 VKGS_API int vkgs_render_async(vkgs_ctx* ctx, const vkgs_frame_params* fp);
 /* Same, plus an asynchronous copy of the finished RGBA frame (W*H*4 elements of the target
  * format) to PINNED host memory; valid after vkgs_sync (or once the caller's stream reaches it). */
@@ -283,10 +285,11 @@ VKGS_API int vkgs_render_to_host_async(vkgs_ctx* ctx, const vkgs_frame_params* f
 VKGS_API int vkgs_set_target_format(vkgs_ctx* ctx, uint32_t target_format);
 /* 1 = strictly one frame at a time (full-occupancy kernels, lowest latency), 2..4 (default 4) = overlap consecutive frames. */
 VKGS_API int vkgs_set_frames_in_flight(vkgs_ctx* ctx, int frames);
-/* Wait for every frame in flight. A frame whose tile lists overflowed is handled here, out of the caller's sight: the lists
- * are grown and the frame is rendered again on its own slot with the same parameters and host destination. Only when a slot
- * was reused between two vkgs_sync calls (more frames enqueued than frames in flight) and one of its EARLIER frames
- * overflowed does the call return VKGS_ERR_OVERFLOW (lists grown; render the frames since the previous sync again). */
+/* Wait for every frame in flight. A frame whose tile lists overflowed is handled out of the caller's sight — here, or
+ * at the moment its slot is reused by a later vkgs_render_async / vkgs_render_to_host_async: the lists are grown and the
+ * frame is rendered again on its own slot with the same parameters and host destination, so after a successful vkgs_sync
+ * every frame enqueued since the previous one is complete. VKGS_ERR_OVERFLOW is left for lists that still overflow after
+ * four regrowths (the 2^32-pair limit) and for caller-ordered frames. */
 VKGS_API int vkgs_sync(vkgs_ctx* ctx);
 /* Enable per-kernel cudaEvent timing for subsequent frames (off by default). */
 VKGS_API int vkgs_set_profiling(vkgs_ctx* ctx, int enabled);

@@ -205,6 +205,8 @@ struct FrameRequest
   uint32_t        presortedCount = 0;
 };
 
+int repairSlotBeforeReuse(vkgs_ctx* c, int si);
+
 // Enqueue one frame on the next slot; optionally a device->host copy of the finished frame.
 int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& rq, int* slotOut)
 {
@@ -223,6 +225,13 @@ int enqueueFrame(vkgs_ctx* c, const vkgs_frame_params& fp, const FrameRequest& r
   CU_TRY(c, cudaSetDevice(c->device));
   const int  si = rq.forceSlot >= 0 ? rq.forceSlot : c->nextSlot;
   FrameSlot& s  = c->slots[si];
+  // Reusing a slot: the caller is `frames in flight` frames ahead of the frame that still lives here. Wait for it (the
+  // back-pressure of the asynchronous API) and, should its tile lists have overflowed, repair it now — grow the lists,
+  // render it again into the same destination — so that no frame is ever lost to a reused slot.
+  static const bool reuseCheck = []() { const char* e = getenv("VKGS_NO_REUSE_CHECK"); return !(e && *e == '1'); }();  // (A/B measurements)
+  if(reuseCheck && rq.forceSlot < 0 && s.haveFrame && s.framesSinceSync > 0)
+    if(int rc = repairSlotBeforeReuse(c, si))
+      return rc;
   // A frame of the asynchronous path that finds the device idle (the previous frame has already left it: the first frame
   // of a burst, or a caller slower than the GPU) has nothing to share the SMs with: it takes the full-width, latency-
   // oriented launches of the synchronous path. Same bits either way (test_four_frames_in_flight_...).
@@ -542,6 +551,48 @@ int checkOverflow(vkgs_ctx* c, bool* flagged /*[MAX_FRAMES_IN_FLIGHT], optional*
     }
   }
   return grown ? fail(c, VKGS_ERR_OVERFLOW, "tile lists overflowed; capacity was grown, render the frame again") : VKGS_OK;
+}
+
+// See enqueueFrame: slot `si` is about to be reused while it still holds a frame that has not been checked.
+int repairSlotBeforeReuse(vkgs_ctx* c, int si)
+{
+  FrameSlot& s = c->slots[si];
+  for(int attempt = 0; attempt < 4; attempt++)
+  {
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    if(!(s.hCounters->overflow || s.hCounters->stickyOverflow))
+    {
+      s.framesSinceSync = 0;
+      return VKGS_OK;
+    }
+    const bool     truncated = s.hCounters->overflow != 0;
+    const uint64_t pairs     = std::max(s.hCounters->tilePairs, s.hCounters->stickyPairs);
+    const uint64_t want      = pairs * 5 / 4 + 65536;
+    for(auto& t : c->slots)
+      if(t.tileCapacity && t.tileCapacity < want)
+      {
+        CU_TRY(c, cudaStreamSynchronize(t.stream));
+        if(int rc = allocTileLists(c, t, want))
+          return rc;
+      }
+    s.hCounters->overflow = s.hCounters->stickyOverflow = s.hCounters->stickyPairs = 0;
+    CU_TRY(c, cudaMemset(s.dCounters, 0, offsetof(FrameCounters, visible)));  // clear the sticky words
+    s.framesSinceSync = 0;
+    if(!truncated)
+      return VKGS_OK;  // (a sticky flag of an earlier, already repaired frame)
+    if(s.lastPresorted)
+      return fail(c, VKGS_ERR_OVERFLOW, "tile lists overflowed in a presorted frame; capacity was grown, render it again");
+    FrameRequest rq;
+    rq.hostRgba       = s.lastHost;
+    rq.throughputMode = s.lastThin;
+    rq.forceSlot      = si;
+    const vkgs_frame_params fp   = s.lastFp;
+    const int               last = c->lastSlot;
+    if(int rc = enqueueFrame(c, fp, rq, nullptr))
+      return rc;
+    c->lastSlot = last;
+  }
+  return fail(c, VKGS_ERR_OVERFLOW, "tile lists still overflow after regrowing");
 }
 
 int syncAll(vkgs_ctx* c)

@@ -430,13 +430,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, (GUT ? VKGS_GUT_RESIDENT_THREAD
       {
         const uint32_t rec     = sbase + buf * SMEM_REC + slot * SLOT_BYTES;
         const float4   q1      = ldsV4(rec + 16), q2 = ldsV4(rec + 32), q3 = ldsV4(rec + 48), q4 = ldsV4(rec + 64), q5 = ldsV4(rec + 80);
-        // (non-finite colours are clamped like on the 3DGS path: a discard is composited as 0 * colour)
-        if(!(fabsf(q1.x) <= 3.4028235e38f))
-          stsU32(rec + 16, __float_as_uint(fminf(fmaxf(q1.x, -3.4028235e38f), 3.4028235e38f)));
-        if(!(fabsf(q1.y) <= 3.4028235e38f))
-          stsU32(rec + 20, __float_as_uint(fminf(fmaxf(q1.y, -3.4028235e38f), 3.4028235e38f)));
-        if(!(fabsf(q1.z) <= 3.4028235e38f))
-          stsU32(rec + 24, __float_as_uint(fminf(fmaxf(q1.z, -3.4028235e38f), 3.4028235e38f)));
         const float    density = q1.w;
         const float    roLen   = (GUTX && a.gut.extentEigen) ? sqrtf(q2.x * q2.x + q2.y * q2.y + q2.z * q2.z) : q2.w;
         const bool     alive   = !(density <= a.gut.alphaCullThreshold) && a.gut.alphaClamp > 1.0f / 255.0f;
@@ -503,14 +496,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, (GUT ? VKGS_GUT_RESIDENT_THREAD
       const float aStar = NOGAUSS ? 3.0e38f : 1.3862943611198906f * __log2f(255.0f * r2.y);
       stsU32(src + 40, __float_as_uint(fminf(8.0f, aStar - 3e-5f)));
       stsU32(src + 44, __float_as_uint(aStar));
-      // Discards are composited as zeros (0 * colour): a non-finite colour (corrupt input, outside the parity contract) is
-      // clamped to +-FLT_MAX here so that it cannot turn the pixels it does NOT cover into NaN.
-      if(!(fabsf(r1.z) <= 3.4028235e38f))
-        stsU32(src + 24, __float_as_uint(fminf(fmaxf(r1.z, -3.4028235e38f), 3.4028235e38f)));
-      if(!(fabsf(r1.w) <= 3.4028235e38f))
-        stsU32(src + 28, __float_as_uint(fminf(fmaxf(r1.w, -3.4028235e38f), 3.4028235e38f)));
-      if(!(fabsf(r2.x) <= 3.4028235e38f))
-        stsU32(src + 32, __float_as_uint(fminf(fmaxf(r2.x, -3.4028235e38f), 3.4028235e38f)));
     }
 #pragma unroll
     for(uint32_t b = 0; b < BLEND_WARPS; b++)

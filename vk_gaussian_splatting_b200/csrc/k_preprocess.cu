@@ -50,6 +50,11 @@ struct PreSmem
   uint32_t basePrefix[2];  // exclusive prefix of the tile processed in iteration parity 0 / 1
 };
 
+__device__ __forceinline__ float clampFinite(float v)
+{
+  return fminf(fmaxf(v, -3.4028235e38f), 3.4028235e38f);  // NaN -> -FLT_MAX, +-inf -> +-FLT_MAX, finite values unchanged
+}
+
 __device__ __forceinline__ uint32_t encodeMinMaxFp32(float v)
 {
   uint32_t bits = __float_as_uint(v);
@@ -547,6 +552,7 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     else
     {
       float4* rec = reinterpret_cast<float4*>(a.records + (a.idBase + id) * GUT_RECORD_WORDS);
+      rec6[1].x = clampFinite(rec6[1].x), rec6[1].y = clampFinite(rec6[1].y), rec6[1].z = clampFinite(rec6[1].z);  // (see the 3DGS record)
 #pragma unroll
       for(int k = 0; k < 6; k++)
         rec[k] = rec6[k];
@@ -691,9 +697,12 @@ __global__ void __launch_bounds__(PRE_TILE) k_preprocess(const __grid_constant__
     float4* rec = reinterpret_cast<float4*>(a.records + (a.idBase + id) * RECORD_WORDS);
     if(!(ablate & 4u))
     {
+    // The blend composites a discarded fragment as 0 * colour: a non-finite colour (corrupt input, outside the parity
+    // contract) is clamped to +-FLT_MAX so that it cannot turn pixels the splat does not cover into NaN. Finite colours
+    // (everything the parity contract covers) pass through bit for bit.
     rec[0]      = make_float4(cx, cy, w1x, w1y);
-    rec[1]      = make_float4(w2x, w2y, col.x, col.y);
-    rec[2]      = make_float4(col.z, col.w, __uint_as_float(bb0), __uint_as_float(bb1));
+    rec[1]      = make_float4(w2x, w2y, clampFinite(col.x), clampFinite(col.y));
+    rec[2]      = make_float4(clampFinite(col.z), col.w, __uint_as_float(bb0), __uint_as_float(bb1));
     a.bboxes[a.idBase + id] = make_uint2(bb0, bb1);
     }
     if(a.surface && valid)
