@@ -861,7 +861,8 @@ def test_sort_pairs_device_in_place_with_device_count(gpu_renderer):
     import torch
     r = gpu_renderer
     rng = np.random.default_rng(21)
-    for max_count, count in ((1_000_000, 777_777), (8192, 8192), (5000, 1), (100_000, 0), (300_000, 300_000)):
+    # (the last case: a device-side count beyond the host bound — the caller's bug — is clamped, nothing is read past the buffers)
+    for max_count, count in ((1_000_000, 777_777), (8192, 8192), (5000, 1), (100_000, 0), (300_000, 300_000), (5000, 123_456)):
         keys = rng.integers(0, 1 << 32, size=max_count, dtype=np.uint64).astype(np.uint32)
         keys[: max_count // 3] &= np.uint32(0xff00ff)  # plenty of ties
         vals = np.arange(max_count, dtype=np.uint32)
@@ -877,6 +878,7 @@ def test_sort_pairs_device_in_place_with_device_count(gpu_renderer):
         stream.synchronize()
         k = dk.cpu().numpy().view(np.uint32)
         v = dv.cpu().numpy().view(np.uint32)
+        count = min(count, max_count)
         order = np.argsort(keys[:count], kind="stable")
         assert np.array_equal(k[:count], keys[:count][order]) and np.array_equal(v[:count], vals[:count][order])
         assert np.array_equal(k[count:], keys[count:]) and np.array_equal(v[count:], vals[count:])

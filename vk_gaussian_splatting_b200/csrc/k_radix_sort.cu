@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const __grid_cons
   sm.digitCount[tid] = 0u;
   pdl_wait();
   pdl_launch_dependents();
-  const uint32_t count = *a.countPtr;
+  const uint32_t count = min(*a.countPtr, a.maxCount);  // (a device-side count beyond the host bound is the caller's bug: no reads past the buffers)
   const uint32_t parts = (count + SORT_PART - 1) / SORT_PART;
   uint32_t       cur   = a.srcSelIn ? *a.srcSelIn : 0u;
   if(a.srcSelOut)
@@ -308,7 +308,7 @@ constexpr int HIST_THREADS = 512;
 constexpr int HIST_COPIES  = 4;
 
 template <int PASSES>
-__global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t* __restrict__ keys, const uint32_t* countPtr,
+__global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t* __restrict__ keys, const uint32_t* countPtr, uint32_t maxCount,
                                                             uint32_t* hist, int firstShift)
 {
   __shared__ uint32_t s[HIST_COPIES][PASSES][256];
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(HIST_THREADS) k_histogram(const uint32_t* __re
   for(int i = tid; i < HIST_COPIES * PASSES * 256; i += HIST_THREADS)
     (&s[0][0][0])[i] = 0u;
   __syncthreads();
-  const uint32_t count = *countPtr;
+  const uint32_t count = min(*countPtr, maxCount);
   uint32_t (*mine)[256] = s[tid % HIST_COPIES];
   const uint64_t vecs   = count / 4;
   const uint4*   k4     = reinterpret_cast<const uint4*>(keys);
@@ -367,11 +367,11 @@ void launchHistogram(const uint32_t* keys, const uint32_t* countPtr, uint32_t ma
   uint32_t blocks = (maxCount + HIST_THREADS * 16 - 1) / (HIST_THREADS * 16);
   blocks          = blocks < 1 ? 1 : (blocks > 148 * 4 ? 148 * 4 : blocks);
   if(passes == 4)
-    k_histogram<4><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, hist, firstShift);
+    k_histogram<4><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, maxCount, hist, firstShift);
   else if(passes == 2)
-    k_histogram<2><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, hist, firstShift);
+    k_histogram<2><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, maxCount, hist, firstShift);
   else
-    k_histogram<1><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, hist, firstShift);
+    k_histogram<1><<<blocks, HIST_THREADS, 0, stream>>>(keys, countPtr, maxCount, hist, firstShift);
 }
 
 void initSortKernels()
