@@ -1128,3 +1128,18 @@ def test_random_surface_info_frames_match_oracle(gpu_renderer):
     thresholds, both normal transports."""
     failures = []
     assert _tool("fuzz_surface").run(40, 0, gpu_renderer, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
+
+
+def test_overflow_stress_with_state_changes_under_frames_in_flight(gpu_renderer):
+    """A slice of tools/fuzz_overflow.py: bursts of asynchronous frames to pinned host memory, cameras alternating between few
+    and very many tile pairs (every burst starts from the initial tile-list capacity, more frames than slots), ended by
+    vkgs_sync or by one of the calls that change state under frames in flight (frames-in-flight count, colour target,
+    scene upload: they complete the pending frames first, in the old state); every destination must hold exactly the
+    frame a second context renders synchronously."""
+    fresh = g.GaussianSplatting(0)
+    try:
+        failures = []
+        assert _tool("fuzz_overflow").run(30, gpu_renderer, fresh, log=lambda *a, **k: failures.append(" ".join(str(x) for x in a))) == 0, "\n".join(failures)
+    finally:
+        fresh.close()
+        gpu_renderer.set_target_format(A.FORMAT_FLOAT32)

@@ -30,7 +30,18 @@ def run(bursts, r, fresh, log=print):
         try:
             for cam, buf in zip(cams, bufs):
                 r.render_to_host_async(g.frame_params(cam, w, h), buf)
-            r.sync()
+            # every call that ends a batch must leave the host destinations complete: vkgs_sync, or one of the calls that
+            # change state under frames in flight (they complete the pending frames first, in the old state)
+            how = int(rng.integers(0, 4))
+            if how == 0:
+                r.sync()
+            elif how == 1:
+                r.set_frames_in_flight(int(rng.integers(1, 5)))
+            elif how == 2:
+                r.set_target_format(1)   # RGBA16F from now on: the pending fp32 frames must still arrive as fp32
+                r.set_target_format(0)
+            else:
+                r.upload(g.synth_scene(1000, 0, 1), opt)
             lost = False
         except g.VkgsError as e:
             # documented: a slot reused before vkgs_sync by a frame after an overflowing one cannot be repaired

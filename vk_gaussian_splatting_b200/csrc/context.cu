@@ -47,6 +47,12 @@ void freeSlotScene(FrameSlot& s)
   freeDev(s.dRecords), freeDev(s.dBboxes), freeDev(s.dBigList), freeDev(s.dSurface), freeDev(s.dPreStatus), freeDev(s.dSortStatus), freeDev(s.dBinStatus), freeDev(s.dTileSortStatus);
   s.tileCapacity = 0;
   s.haveFrame    = false;
+  // nothing of the old scene is pending any more: no stale overflow flag may trigger a repair of a frame that is gone
+  s.framesSinceSync = 0;
+  if(s.hCounters)
+    s.hCounters->overflow = s.hCounters->stickyOverflow = s.hCounters->stickyPairs = 0;
+  if(s.dCounters)
+    cudaMemset(s.dCounters, 0, offsetof(FrameCounters, visible));
 }
 
 void freeScene(vkgs_ctx* c)
@@ -802,7 +808,9 @@ int vkgs_set_target_format(vkgs_ctx* c, uint32_t target_format)
 {
   if(!c || target_format > VKGS_FORMAT_UINT8)
     return VKGS_ERR_INVALID_ARGUMENT;
-  if(int rc = syncAll(c))
+  // (vkgs_sync, not a plain wait: frames still in flight are completed — an overflowed one repaired — in the OLD format,
+  //  into destinations sized for it)
+  if(int rc = c->uploaded ? vkgs_sync(c) : syncAll(c))
     return rc;
   c->opt.target_format = target_format;
   return VKGS_OK;
@@ -812,7 +820,7 @@ int vkgs_set_frames_in_flight(vkgs_ctx* c, int frames)
 {
   if(!c || frames < 1 || frames > MAX_FRAMES_IN_FLIGHT)
     return VKGS_ERR_INVALID_ARGUMENT;
-  if(int rc = syncAll(c))
+  if(int rc = c->uploaded ? vkgs_sync(c) : syncAll(c))
     return rc;
   c->framesInFlight = frames;
   c->nextSlot       = 0;
@@ -877,7 +885,15 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
   if(total > 0x7fffffffull)
     return fail(c, VKGS_ERR_INVALID_ARGUMENT, "splat count must be in 1..2^31-1");
   CU_TRY(c, cudaSetDevice(c->device));
-  if(int rc = syncAll(c))
+  // frames of the previous scene that are still in flight are completed first (an overflowed one repaired), so that every
+  // host destination handed to vkgs_render_to_host_async holds its frame before the scene it was rendered from goes away
+  if(c->uploaded)
+  {
+    const int rc = vkgs_sync(c);
+    if(rc != VKGS_OK && rc != VKGS_ERR_OVERFLOW)
+      return rc;
+  }
+  else if(int rc = syncAll(c))
     return rc;
 
   freeScene(c);
