@@ -1143,3 +1143,19 @@ def test_overflow_stress_with_state_changes_under_frames_in_flight(gpu_renderer)
     finally:
         fresh.close()
         gpu_renderer.set_target_format(A.FORMAT_FLOAT32)
+
+
+def test_sort_pairs_repeated_uploads_are_ordered_before_the_sort(gpu_renderer):
+    """Regression: vkgs_sort_pairs uploads keys and values from pageable memory on the legacy stream and sorts on a non-blocking
+    stream; without a barrier in between the tail of the LAST upload (the values) could still be in flight when the sort
+    read it — about one sort in ten at 300 k pairs on one box, keys always right, values corrupted. 200 sorts in a row."""
+    r = gpu_renderer
+    rng = np.random.default_rng(9)
+    n = 294_912
+    k = (np.arange(n, dtype=np.uint32) * np.uint32(2654435761)).astype(np.uint32)
+    v = rng.permutation(n).astype(np.uint32)
+    order = np.argsort(k, kind="stable")
+    wk, wv = k[order], v[order]
+    for it in range(200):
+        ks, vs, _ = r.sort_pairs(k, v)
+        assert np.array_equal(ks, wk) and np.array_equal(vs, wv), f"sort {it}"

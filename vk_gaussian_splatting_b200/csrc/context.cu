@@ -40,6 +40,14 @@ int fail(vkgs_ctx* ctx, int code, const char* msg)
   return code;
 }
 
+// cudaMemset / cudaMemcpy from pageable memory run on the legacy default stream and may return before the device has finished
+// them; the frame streams are non-blocking (not ordered behind the legacy stream), so every group of such calls is closed
+// with this barrier before anything on a frame stream can touch the memory. (All callers are rare: upload, regrowth, repair.)
+void legacyStreamBarrier()
+{
+  cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 void freeSlotScene(FrameSlot& s)
 {
   for(int i = 0; i < 2; i++)
@@ -52,7 +60,10 @@ void freeSlotScene(FrameSlot& s)
   if(s.hCounters)
     s.hCounters->overflow = s.hCounters->stickyOverflow = s.hCounters->stickyPairs = 0;
   if(s.dCounters)
+  {
     cudaMemset(s.dCounters, 0, offsetof(FrameCounters, visible));
+    legacyStreamBarrier();
+  }
 }
 
 void freeScene(vkgs_ctx* c)
@@ -87,6 +98,8 @@ int allocTileLists(vkgs_ctx* c, FrameSlot& s, uint64_t capacity)
     e = cudaMalloc(&nst, parts * 256 * sizeof(uint64_t));
   if(e == cudaSuccess)
     e = cudaMemset(nst, 0, parts * 256 * sizeof(uint64_t));
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(cudaStreamLegacy);
   if(e != cudaSuccess)
   {
     for(int i = 0; i < 2; i++)
@@ -127,6 +140,7 @@ int allocSlotScene(vkgs_ctx* c, FrameSlot& s, uint64_t n, uint64_t preTiles)
   CU_TRY(c, cudaMemset(s.dPreStatus, 0, preTiles * sizeof(uint64_t)));
   CU_TRY(c, cudaMemset(s.dBinStatus, 0, binParts * sizeof(uint64_t)));
   CU_TRY(c, cudaMemset(s.dSortStatus, 0, sortParts * 256 * sizeof(uint64_t)));
+  legacyStreamBarrier();
   return allocTileLists(c, s, std::max<uint64_t>(8 * n, 1u << 20));
 }
 
@@ -173,6 +187,7 @@ uint32_t nextEpoch(vkgs_ctx* c)
       cudaMemset(s.dSortStatus, 0, ((n + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
       cudaMemset(s.dTileSortStatus, 0, ((s.tileCapacity + SORT_PART - 1) / SORT_PART) * 256 * sizeof(uint64_t));
     }
+    legacyStreamBarrier();
     c->epoch = 1;
   }
   return c->epoch;
@@ -553,6 +568,7 @@ int checkOverflow(vkgs_ctx* c, bool* flagged /*[MAX_FRAMES_IN_FLIGHT], optional*
         flagged[i] = s.hCounters->overflow != 0;
       s.hCounters->overflow = s.hCounters->stickyOverflow = s.hCounters->stickyPairs = 0;
       cudaMemset(s.dCounters, 0, offsetof(FrameCounters, visible));  // clear the sticky words
+      legacyStreamBarrier();
       grown = true;
     }
   }
@@ -583,6 +599,7 @@ int repairSlotBeforeReuse(vkgs_ctx* c, int si)
       }
     s.hCounters->overflow = s.hCounters->stickyOverflow = s.hCounters->stickyPairs = 0;
     CU_TRY(c, cudaMemset(s.dCounters, 0, offsetof(FrameCounters, visible)));  // clear the sticky words
+    legacyStreamBarrier();
     s.framesSinceSync = 0;
     if(!truncated)
       return VKGS_OK;  // (a sticky flag of an earlier, already repaired frame)
@@ -743,6 +760,7 @@ int vkgs_create(int device, vkgs_ctx** out)
     if(ok)
       std::memset(s.hCounters, 0, sizeof(FrameCounters));
   }
+  legacyStreamBarrier();  // (the memsets above)
   initSortKernels();
   initPreprocessKernels();
   initBlendKernels();
@@ -962,6 +980,9 @@ int uploadScene(vkgs_ctx* c, const vkgs_splat_set_view* sets, uint32_t setCount,
   for(auto& s : c->slots)
     if(int rc = allocSlotScene(c, s, offset, tiles))
       return rc;
+  // the scene arrays were copied from pageable host memory on the legacy stream: the copies may still be in flight when
+  // cudaMemcpy returns, and the frame streams are not ordered behind them
+  CU_TRY(c, cudaStreamSynchronize(cudaStreamLegacy));
   c->uploaded = true;
   c->nextSlot = 0;
   return VKGS_OK;

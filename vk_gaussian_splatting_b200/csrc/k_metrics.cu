@@ -257,6 +257,8 @@ int vkgs_image_metrics_host(vkgs_ctx* c, const float* reference, const float* cu
     e = cudaMemcpy(dRef, reference, bytes, cudaMemcpyHostToDevice);
   if(e == cudaSuccess)
     e = cudaMemcpy(dCur, current, bytes, cudaMemcpyHostToDevice);
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(cudaStreamLegacy);  // pageable uploads may still be in flight; the metric kernels run on a non-blocking stream
   int rc = VKGS_OK;
   if(e != cudaSuccess)
   {
@@ -294,7 +296,10 @@ int vkgs_capture_frame(vkgs_ctx* c)
     CU_TRY(c, cudaMalloc(&c->dCapture, bytes));
     c->captureW = s.imgW, c->captureH = s.imgH;
   }
-  CU_TRY(c, cudaMemcpy(c->dCapture, s.dImage, bytes, cudaMemcpyDeviceToDevice));
+  // on the frame's own stream: a device-to-device cudaMemcpy on the legacy stream is asynchronous to the host and the next
+  // frame (non-blocking streams) could overwrite the image under it
+  CU_TRY(c, cudaMemcpyAsync(c->dCapture, s.dImage, bytes, cudaMemcpyDeviceToDevice, s.stream));
+  CU_TRY(c, cudaStreamSynchronize(s.stream));
   return VKGS_OK;
 }
 

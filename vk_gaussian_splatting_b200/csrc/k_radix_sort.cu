@@ -87,7 +87,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 4) k_sort_pass(const __grid_cons
   sm.digitCount[tid] = 0u;
   pdl_wait();
   pdl_launch_dependents();
+#ifdef VKGS_NO_COUNT_CLAMP  // (A/B builds only)
+  const uint32_t count = *a.countPtr;
+#else
   const uint32_t count = min(*a.countPtr, a.maxCount);  // (a device-side count beyond the host bound is the caller's bug: no reads past the buffers)
+#endif
   const uint32_t parts = (count + SORT_PART - 1) / SORT_PART;
   uint32_t       cur   = a.srcSelIn ? *a.srcSelIn : 0u;
   if(a.srcSelOut)

@@ -55,6 +55,11 @@ int vkgs_sort_pairs(vkgs_ctx* c, const uint32_t* keys, const uint32_t* values, u
     e = cudaMemcpy(dIn[0], keys, n * 4, cudaMemcpyHostToDevice);
   if(e == cudaSuccess)
     e = cudaMemcpy(dIn[1], values, n * 4, cudaMemcpyHostToDevice);
+  // The memset and the copies from pageable memory run on the legacy stream and may still be in flight when the calls
+  // return; the sort runs on a non-blocking stream that is not ordered behind them (seen as corrupted VALUES — the last
+  // upload — in about one sort of ten at 300 k pairs on one box).
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(cudaStreamLegacy);
   if(e != cudaSuccess)
   {
     cleanup();
