@@ -26,10 +26,12 @@ def run(bursts, r, fresh, log=print):
         fif = int(rng.integers(1, 5))
         r.upload(s, opt)
         r.set_frames_in_flight(fif)
-        bufs = [torch.zeros((h, w, 4), dtype=torch.float32, pin_memory=True).numpy() for _ in cams]
+        # half of the bursts change the viewport from frame to frame (the slot's targets are reallocated under frames in flight)
+        sizes = [(w, h)] * len(cams) if rng.random() < 0.5 else [tuple(int(x) for x in rng.choice([(640, 360), (320, 200), (960, 540), (333, 217)])) for _ in cams]
+        bufs = [torch.zeros((hh, ww, 4), dtype=torch.float32, pin_memory=True).numpy() for (ww, hh) in sizes]
         try:
-            for cam, buf in zip(cams, bufs):
-                r.render_to_host_async(g.frame_params(cam, w, h), buf)
+            for cam, buf, (ww, hh) in zip(cams, bufs, sizes):
+                r.render_to_host_async(g.frame_params(cam, ww, hh), buf)
             # every call that ends a batch must leave the host destinations complete: vkgs_sync, or one of the calls that
             # change state under frames in flight (they complete the pending frames first, in the old state)
             how = int(rng.integers(0, 4))
@@ -47,12 +49,12 @@ def run(bursts, r, fresh, log=print):
             # documented: a slot reused before vkgs_sync by a frame after an overflowing one cannot be repaired
             lost = True
             log(f"burst {b}: sync reported {str(e)[:70]} (fif {fif}, {len(cams)} frames)")
-            for cam, buf in zip(cams, bufs):
-                r.render_to_host_async(g.frame_params(cam, w, h), buf)
+            for cam, buf, (ww, hh) in zip(cams, bufs, sizes):
+                r.render_to_host_async(g.frame_params(cam, ww, hh), buf)
             r.sync()
         fresh.upload(s, opt)
-        for i, (cam, buf) in enumerate(zip(cams, bufs)):
-            want = fresh.render(g.frame_params(cam, w, h))[0]
+        for i, (cam, buf, (ww, hh)) in enumerate(zip(cams, bufs, sizes)):
+            want = fresh.render(g.frame_params(cam, ww, hh))[0]
             if not np.array_equal(buf, want):
                 bad += 1
                 log(f"burst {b}: frame {i} of {len(cams)} differs (fif {fif}, n {n}, {w}x{h}, lost={lost}, max diff {np.abs(buf - want).max():.3g})", flush=True)
