@@ -1089,7 +1089,7 @@ def test_non_finite_colours_stay_inside_their_splats_footprint(gpu_renderer):
 
 
 def test_random_options_cameras_and_viewports_match_oracle(gpu_renderer):
-    """A slice of tools/fuzz_options.py (850 trials were run clean on a B200 during development): random scene sizes
+    """A slice of tools/fuzz_options.py (2050 trials were run clean on a B200 during development): random scene sizes
     (1 ... 20 000 splats), splat sizes, option combinations of both pipelines (culling modes, mip-splatting, storage formats,
     point cloud / SH-only / no-gaussian modes, kernel degrees, quad extents, fisheye), cameras (inside the cloud, far away,
     5 ... 170 degree fields of view, other near / far planes), viewports (1x1 ... 640x97) and per-frame parameters — ids /
