@@ -1159,3 +1159,11 @@ def test_sort_pairs_repeated_uploads_are_ordered_before_the_sort(gpu_renderer):
     for it in range(200):
         ks, vs, _ = r.sort_pairs(k, v)
         assert np.array_equal(ks, wk) and np.array_equal(vs, wv), f"sort {it}"
+
+
+def test_garbage_options_and_frame_parameters_are_rejected_or_rendered(gpu_renderer):
+    """A slice of tools/fuzz_abi.py: invalid enums, NaN / inf / huge values and absurd sizes in vkgs_options and
+    vkgs_frame_params — every call returns an error code or a frame (no crash, no hang), and afterwards the context still
+    renders the reference frame bit for bit."""
+    lines = []
+    assert _tool("fuzz_abi").run(150, gpu_renderer, log=lambda *a, **k: lines.append(" ".join(str(x) for x in a))) == 0, "\n".join(lines)
