@@ -187,6 +187,22 @@ def test_dist_cull_frustum_and_depth_order():
     assert ids_n.tolist() == list(range(n))  # no culling at the dist stage
 
 
+def test_nan_depth_takes_the_canonical_key_and_sorts_last_in_both_orders():
+    """A NaN / inf position fails no cull comparison, so the splat is kept; its key is the encoding of the canonical quiet NaN
+    0x7FFFFFFF of the reference's platform, taken AFTER the back-to-front negation: 0xFFFFFFFF in both orders (x86 would
+    hand the oracle 0xFFC00000 or the operand's payload, and the two orders would disagree)."""
+    pts = np.array([[0, 0, 0], [np.nan, 0, 0], [0, 0, 1], [0, np.inf, 0], [0, 0, -np.inf]], np.float32)
+    n = len(pts)
+    s = g.SplatSet(pts, np.zeros((n, 3)), np.zeros((n, 0)), np.ones(n), np.full((n, 3), -3.0), np.tile([1, 0, 0, 0], (n, 1)))
+    pk = O.Packed(s)
+    fp = O.frame_params(_front_camera(4.0), 128, 128)
+    for ftb in (0, 1):
+        keys, ids = O.dist_cull(pk, fp, O.default_options(front_to_back=ftb))
+        by_id = dict(zip(ids.tolist(), keys.tolist()))
+        assert by_id[1] == 0xFFFFFFFF and by_id[3] == 0xFFFFFFFF, by_id
+        assert by_id[0] < 0xFFFFFFFF and by_id[2] < 0xFFFFFFFF
+
+
 def test_depth_clip_and_alpha_cull_reject_quads():
     fp = O.frame_params(_front_camera(4.0), 128, 128)
     # alpha cull: sigmoid(-8) < 1/255
@@ -507,6 +523,11 @@ def test_kernel_exact_math_host_instantiations_equal_the_oracle_bitwise():
     got, _ = run(0, x)
     ref = np.array([ol.orc_expf(float(v)) for v in x], np.float32)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # exp(NaN) = NaN on both sides (the clamps would otherwise turn it into exp(-87)); +-inf take the clamped tails
+    got, _ = run(0, np.array([np.nan, np.inf, -np.inf], np.float32))
+    ol.orc_expf.restype = C.c_float
+    assert np.isnan(got[0]) and np.isnan(ol.orc_expf(float("nan")))
+    assert got[1] == np.float32(ol.orc_expf(float("inf"))) and got[2] == np.float32(ol.orc_expf(float("-inf"))) and got[2] > 0
     # atan2(y > 0, x)
     y = (10.0 ** rng.uniform(-7, 4, 100_000)).astype(np.float32)
     xx = (rng.choice([-1.0, 1.0], 100_000) * 10.0 ** rng.uniform(-7, 4, 100_000)).astype(np.float32)
