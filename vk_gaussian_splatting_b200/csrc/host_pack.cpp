@@ -36,7 +36,9 @@ uint32_t formatSize(uint32_t format)
 uint8_t toUint8(float v, float rangeMin, float rangeMax)
 {
   const float normalized = (v - rangeMin) / (rangeMax - rangeMin);
-  return static_cast<uint8_t>(std::clamp(std::round(normalized * 255.0f), 0.0f, 255.0f));
+  const float q          = std::clamp(std::round(normalized * 255.0f), 0.0f, 255.0f);
+  // (a NaN survives the clamp and its conversion is undefined behaviour in the reference's expression; x86 yields 0: stated)
+  return q == q ? static_cast<uint8_t>(q) : uint8_t(0);
 }
 
 // glm::detail::toFloat16: round-half-up on the 13 dropped mantissa bits, denormals by shifting.
